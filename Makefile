@@ -1,0 +1,26 @@
+# Builds libtsgpu.so (product, sm_100a only), the CPU oracle and the test-only SIMT build.
+PKG := tiered-storage-for-apache-kafka_b200
+CSRC := $(PKG)/csrc
+NVCC ?= nvcc
+NVCCFLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-Wall -Xptxas -v \
+             --expt-relaxed-constexpr
+HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h $(CSRC)/*.hpp) include/tsgpu.h
+
+all: $(PKG)/libtsgpu.so oracle tests/simt/libtsgpu_simt.so
+
+$(PKG)/libtsgpu.so: $(CSRC)/tsgpu.cu $(HDRS)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/tsgpu.cu -lcudart 2> build_ptxas.log || (cat build_ptxas.log; false)
+	@grep -E "error|warning: .*spill|bytes spill" build_ptxas.log | grep -v " 0 bytes spill" | head -20 || true
+
+oracle:
+	$(MAKE) -s -C oracle
+
+# TEST-ONLY: the same sources compiled for the fiber emulator (never loaded by the package)
+tests/simt/libtsgpu_simt.so: $(CSRC)/tsgpu.cu $(HDRS) tests/simt/simt.h tests/simt/simt.cpp
+	g++ -O2 -g -std=c++17 -fPIC -shared -DTSGPU_SIMT=1 -Itests/simt -I$(CSRC) -x c++ $(CSRC)/tsgpu.cu tests/simt/simt.cpp \
+	    -o $@ -Wall -Wno-unknown-pragmas -Wno-unused-function -Wno-unused-variable
+
+clean:
+	rm -f $(PKG)/libtsgpu.so tests/simt/libtsgpu_simt.so build_ptxas.log
+	$(MAKE) -C oracle clean
+.PHONY: all oracle clean
