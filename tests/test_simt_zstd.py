@@ -1,0 +1,122 @@
+"""Runs the REAL zstd compressor/decompressor kernel sources under the test-only SIMT emulator (tests/simt/)
+through the C-ABI and checks them against the oracle (system libzstd): our frames decode with libzstd, libzstd's
+level-3 frames decode with ours, Frame_Content_Size is present, corrupt input is an error and never a crash.
+Logic check for the GPU-less build box; the -m gpu tests repeat this on a B200 at full sizes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as ora
+import tsgpu
+from tsgpu import binding, corpus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIMT_LIB = os.path.join(ROOT, "tests", "simt", "libtsgpu_simt.so")
+Z, A = tsgpu.FLAG_ZSTD, tsgpu.FLAG_AES
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    subprocess.check_call(["make", "-s", "-C", ROOT, "tests/simt/libtsgpu_simt.so"])
+    c = tsgpu.Context(max_chunk_bytes=1 << 20, max_batch=4, lib_path=SIMT_LIB)
+    yield c
+    c.close()
+
+
+def _mixed(n, seed):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, 256, n, dtype=np.uint8)
+    src[: n // 2] = corpus.gen_chunk("K", seed, 0, n // 2)
+    if n > 4000:
+        src[n // 2: n // 2 + 1500] = 7            # a run inside the random half
+    return src
+
+
+CASES = [("K", 1, 0), ("K", 4, 0), ("K", 5, 0), ("K", 255, 0), ("K", 256, 0), ("K", 300, 0), ("K", 16383, 0),
+         ("K", 16384, 0), ("K", 16385, 0), ("K", 65791, 0), ("K", 65792, 0), ("R", 40000, 0), ("Z", 70000, 32768),
+         ("K", 200000, 65536), ("M", 150000, 50000), ("K", 1 << 20, 1 << 20), ("R", 300000, 1 << 17)]
+
+
+@pytest.mark.parametrize("kind,n,cs", CASES)
+def test_simt_zstd_both_directions(ctx, kind, n, cs):
+    src = _mixed(n, 11) if kind == "M" else corpus.gen_segment(kind, 0, n, cs if cs else n)
+    out, sizes = ctx.transform(Z, src, cs)
+    c = cs if cs else n
+    pos = 0
+    for i, s in enumerate(sizes):
+        frame = out[pos:pos + s]
+        pos += s
+        want = src[i * c:min(n, (i + 1) * c)]
+        assert ora.zstd_content_size(frame) == want.size
+        assert ora.zstd_decompress_chunk(frame) == want.tobytes()
+    back, osz = ctx.detransform(Z, out, sizes, n)
+    assert np.array_equal(back, src)
+    ref, rs = ora.transform_segment(Z, src, cs)
+    back, osz = ctx.detransform(Z, ref, rs, n)
+    assert np.array_equal(back, src)
+
+
+def test_simt_frame_headers_match_libzstd_choice(ctx):
+    # same Frame_Header_Descriptor / FCS field width libzstd picks for a pledged size (golden vector form 28B52FFD 20 0F)
+    for n in (15, 255, 256, 65791, 65792, 300000):
+        src = corpus.gen_chunk("K", 1, 0, n)
+        mine, _ = ctx.transform(Z, src, 0)
+        ref = ora.zstd_compress_chunk(src)
+        hl = 6 if n < 256 else 7 if n < 65792 else 9
+        assert bytes(mine[:hl]) == ref[:hl]
+
+
+@pytest.mark.parametrize("flags", [Z | A])
+@pytest.mark.parametrize("cs", [0, 1, 13, 1024, 5123, 60000])
+def test_simt_full_chain_round_trip(ctx, flags, cs):
+    n = 60001 if cs == 0 or cs >= 1024 else 300
+    src = _mixed(n, cs + 3)
+    rng = np.random.default_rng(cs)
+    nch = (n + cs - 1) // cs if cs else 1
+    key, aad, ivs = rng.bytes(32), rng.bytes(32), rng.bytes(12 * nch)
+    got, gs = ctx.transform(flags, src, cs, key, aad, ivs)
+    back_ref, _ = ora.detransform_chunks(flags, got, gs, n, key, aad)
+    assert np.array_equal(back_ref, src)
+    ref, rs = ora.transform_segment(flags, src, cs, key, aad, ivs)
+    back, _ = ctx.detransform(flags, ref, rs, n, key, aad)
+    assert np.array_equal(back, src)
+    back2, _ = ctx.detransform(flags, got, gs, n, key, aad)
+    assert np.array_equal(back2, src)
+
+
+def test_simt_corrupt_frames_never_crash(ctx):
+    src = corpus.gen_chunk("K", 5, 0, 120000)
+    for frame in (np.frombuffer(ora.zstd_compress_chunk(src), dtype=np.uint8), ctx.transform(Z, src, 0)[0]):
+        rng = np.random.default_rng(1)
+        for trial in range(40):
+            bad = frame.copy()
+            where = int(rng.integers(0, len(bad)))
+            bad[where] ^= 1 << int(rng.integers(0, 8))
+            try:
+                back, osz = ctx.detransform(Z, bad, [len(bad)], len(src))
+            except tsgpu.TsgpuError as e:
+                assert e.code == binding.E_CORRUPT
+            else:
+                assert len(back) == len(src)
+        for cut in (3, 5, 9, len(frame) // 2, len(frame) - 1):
+            with pytest.raises(tsgpu.TsgpuError) as e:
+                ctx.detransform(Z, frame[:cut], [cut], len(src))
+            assert e.value.code == binding.E_CORRUPT
+
+
+def test_simt_frame_without_content_size_is_invalid(ctx):
+    # DecompressionChunkEnumeration.java:41-44: "Invalid decompressed size"
+    frame = bytes.fromhex("28b52ffd") + bytes([0x00, 0x58]) + bytes([0x01 | (0 << 1) | (3 << 3), 0, 0]) + b"abc"
+    with pytest.raises(tsgpu.TsgpuError) as e:
+        ctx.detransform(Z, np.frombuffer(frame, dtype=np.uint8), [len(frame)], 100)
+    assert e.value.code == binding.E_CORRUPT
+
+
+def test_simt_reference_written_index_deserializes(ctx):
+    sizes = [1000000 + (i * 7919) % 5000 for i in range(600)]
+    assert ctx.transformed_chunks_deserialize(ora.transformed_chunks_serialize(sizes)) == sizes
+    assert ctx.transformed_chunks_deserialize("KLUv/SAPeQAAAAAAAwAAAAoBAAoAAAAe") == [10, 20, 30]
+    pos = ctx.chunk_positions(sizes)
+    assert [int(p) for p in pos[:-1]] == [c[3] for c in ora.ChunkIndex.variable(1 << 20, 599 * (1 << 20) + 1, sizes).chunks()]

@@ -1,14 +1,443 @@
-// zstd_enc.cuh — placeholder until the compressor lands (next commit).
+// zstd_enc.cuh — batched Zstandard compression for sm_100a (kernel K1 of SURVEY.md §2a).
+//
+// Replaces ZstdCompressCtx.compress as called per chunk from
+//   core/M/transform/CompressionChunkEnumeration.java:49-62 (new ctx, default level, setPledgedSrcSize,
+//   setContentSize(true)): one independent RFC 8878 frame WITH Frame_Content_Size per chunk.
+// Parity bar: libzstd decodes every frame to the original bytes and
+// ZSTD_getFrameContentSize(frame) == original size.  Compressed bytes are not expected to equal libzstd's.
+//
+// B200-first decomposition: a chunk is cut into ZB = 16 KiB zstd blocks that never reference each other
+// (no cross-block matches, no repeat offsets, no repeated tables), so a 1 GiB segment is 65,536 independent
+// units instead of 256 sequential ones.
+//   zstd_enc_blocks_kernel    one WARP per block: block staged in shared memory; 32 positions hashed and
+//                             verified per step against a per-warp hash table, greedy left-to-right selection
+//                             by ballot/ffs, match extension per lane then warp-wide; literals (Raw or
+//                             Huffman, see zstd_huf_enc.cuh) + sequences (predefined FSE tables; the three
+//                             state chains run on lanes 0-2, bit packing on all lanes with shuffle prefix sums)
+//   zstd_enc_assemble_kernel  one CTA per chunk: frame header (same form libzstd picks for the size), exclusive
+//                             scan of block sizes, byte-granular gather of the blocks into the frame
+// Everything is integer/byte work on the ALU and shared-memory pipes; there is no dense contraction to put
+// on tensor cores.
 #pragma once
 #include "ts_common.cuh"
 #include "rt.h"
 #include "launch_prof.h"
+#include "zstd_format.h"
+#include "index_scan.cuh"
+
 namespace ts {
-struct ZstdEncScratch { void* p = nullptr; };
-inline const char* zstd_enc_scratch_alloc(ZstdEncScratch&, uint32_t, uint32_t) { return nullptr; }
-inline void zstd_enc_scratch_free(ZstdEncScratch&) {}
-inline const char* zstd_kernels_configure() { return nullptr; }
-inline const char* zstd_last_error() { return "zstd kernels not built yet"; }
-inline int zstd_compress_batch(ZstdEncScratch&, rt::stream_t, const uint8_t*, const uint64_t*, const uint32_t*, uint32_t, uint32_t,
-                               uint8_t*, const uint64_t*, uint32_t*, LaunchProf&) { return -2; }
+
+constexpr uint32_t ZB = 16384;                 // bytes of original data per zstd block
+constexpr int ZE_HLOG = 11;                    // per-warp hash table: 2^11 x u16
+constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
+constexpr int ZE_WPB = 2;                      // warps (= blocks in flight) per CTA
+constexpr uint32_t ZE_MAXSEQ = ZB / 8;         // sequences kept per block; beyond that the rest goes out as literals
+constexpr uint32_t ZE_LANE_EXT = 60;           // bytes a lane extends its own match beyond the first 4
+constexpr uint32_t ZE_BUF_PAD = 160;
+constexpr uint32_t ZE_SLOT = ZB + 64;          // per-block output slot: 3-byte header + payload (<= ZB when compressed)
+constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 2 + 3 * 32 + 3 * 32 * 2 + 3 * 32;   // buf, ht, codes, stv, stn
+constexpr uint32_t ZE_SMEM_WARP_AL = (ZE_SMEM_WARP + 15) & ~15u;
+
+__constant__ zf::SeqTables g_seq_tables = zf::make_seq_tables();
+__constant__ zf::PredefinedCTables g_pre_ctables = zf::make_predefined_ctables();
+
+struct ZstdEncScratch {
+    uint8_t* blk_out = nullptr;      // n_chunks * blocks_per_chunk * ZE_SLOT
+    uint32_t* blk_size = nullptr;    // n_chunks * blocks_per_chunk
+    uint2* seqs = nullptr;           // n_chunks * blocks_per_chunk * ZE_MAXSEQ
+    uint8_t* lits = nullptr;         // n_chunks * blocks_per_chunk * ZB   (literal staging for Huffman)
+    uint32_t blocks_per_chunk = 0;
+    uint32_t max_batch = 0;
+};
+
+struct ZstdEncArgs {
+    const uint8_t* in_base; const uint64_t* in_off; const uint32_t* in_len;
+    uint8_t* blk_out; uint32_t* blk_size; uint2* seqs; uint8_t* lits;
+    uint32_t blocks_per_chunk;
+    uint8_t* out_base; const uint64_t* out_off; uint32_t* out_len;
+};
+
+// ------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ uint32_t ze_hash(uint32_t v) { return (v * 2654435761u) >> (32 - ZE_HLOG); }
+
+// number of equal leading bytes (0..4) of two words given their XOR
+__device__ __forceinline__ uint32_t ze_common_bytes(uint32_t x) { return x ? (uint32_t)(__ffs((int)x) - 1) >> 3 : 4u; }
+
+__device__ __forceinline__ uint32_t ze_ll_code(uint32_t ll) {
+    return ll < 64 ? g_seq_tables.ll_code[ll] : (uint32_t)zf::highbit32(ll) + 19;
 }
+__device__ __forceinline__ uint32_t ze_ml_code(uint32_t mlbase) {
+    return mlbase < 128 ? g_seq_tables.ml_code[mlbase] : (uint32_t)zf::highbit32(mlbase) + 36;
+}
+
+// OR a bit field (val, nb <= 58 bits) into a zeroed little-endian word buffer at bit offset `o` (shared memory)
+__device__ __forceinline__ void ze_put_bits(uint32_t* words, uint32_t o, uint64_t val, uint32_t nb) {
+    if (nb == 0) return;
+    const uint32_t w = o >> 5, sh = o & 31;
+    atomicOr(&words[w], (uint32_t)(val << sh));
+    if (sh + nb > 32) atomicOr(&words[w + 1], (uint32_t)(val >> (32 - sh)));
+    if (sh + nb > 64) atomicOr(&words[w + 2], (uint32_t)(val >> (64 - sh)));
+}
+
+#ifdef TSGPU_SIMT
+static inline unsigned __match_any_sync(unsigned, unsigned v) {
+    simt::Warp& w = simt::g_blk->warps[simt::g_cur->warp];
+    w.buf[simt::g_cur->lane] = v;
+    simt::warp_barrier();
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) if (w.buf[i] == v) r |= 1u << i;
+    simt::warp_barrier();
+    return r;
+}
+#endif
+
+}  // namespace ts
+
+#include "zstd_huf_enc.cuh"
+
+namespace ts {
+
+// ------------------------------------------------------------------------------------------ block compressor
+// Encodes the sequences section with the predefined FSE tables into the zeroed word buffer `bits`.
+// Returns the number of bytes of the bit stream (uniform across the warp).  N >= 1.
+struct ZeFseShared {      // per-CTA copy of the predefined encoding tables
+    zf::PredefinedCTables t;
+};
+
+__device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict__ seqs, uint32_t N, uint32_t* bits,
+                                                        uint8_t* codes /*[3][32]*/, uint16_t* stv /*[3][32]*/, uint8_t* stn /*[3][32]*/,
+                                                        const ZeFseShared* fs, uint32_t lane) {
+    uint32_t bitpos = 0;
+    uint32_t state = 0;                              // lanes 0..2: OF, ML, LL chains
+    for (uint32_t t0 = 0; t0 < N; t0 += 32) {
+        const uint32_t j = t0 + lane;                // stream order: j = 0 is the LAST sequence
+        const bool have = j < N;
+        uint32_t ll = 0, mlb = 0, offb = 0, llc = 0, mlc = 0, ofc = 0;
+        if (have) {
+            const uint2 s = seqs[N - 1 - j];
+            ll = s.x & 0xffff; mlb = s.x >> 16; offb = s.y + 3;       // mlb = matchLength - 3, offb = offset + 3 (no repcodes)
+            llc = ze_ll_code(ll); mlc = ze_ml_code(mlb); ofc = (uint32_t)zf::highbit32(offb);
+            codes[lane] = (uint8_t)ofc; codes[32 + lane] = (uint8_t)mlc; codes[64 + lane] = (uint8_t)llc;
+        }
+        __syncwarp();
+        if (lane < 3) {
+            const uint32_t cnt = min(32u, N - t0);
+            const uint16_t* st_tab = lane == 0 ? fs->t.of.state : lane == 1 ? fs->t.ml.state : fs->t.ll.state;
+            const zf::FseCSym* sy = lane == 0 ? fs->t.of.sym : lane == 1 ? fs->t.ml.sym : fs->t.ll.sym;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const zf::FseCSym c = sy[codes[lane * 32 + i]];
+                if (t0 + i == 0) {                   // FSE_initCState2
+                    const uint32_t nb = (uint32_t)(c.delta_nb_bits + (1 << 15)) >> 16;
+                    const uint32_t v = (nb << 16) - (uint32_t)c.delta_nb_bits;
+                    state = st_tab[(int32_t)(v >> nb) + c.delta_find_state];
+                    stv[lane * 32 + i] = 0; stn[lane * 32 + i] = 0;
+                } else {                             // FSE_encodeSymbol
+                    const uint32_t nb = (state + (uint32_t)c.delta_nb_bits) >> 16;
+                    stv[lane * 32 + i] = (uint16_t)(state & ((1u << nb) - 1));
+                    stn[lane * 32 + i] = (uint8_t)nb;
+                    state = st_tab[(int32_t)(state >> nb) + c.delta_find_state];
+                }
+            }
+        }
+        __syncwarp();
+        uint64_t field = 0; uint32_t nb = 0;
+        if (have) {
+            const uint32_t llb = g_seq_tables.ll_bits[llc], mlbits = g_seq_tables.ml_bits[mlc];
+            // order inside a field (first written = lowest bits): OF state, ML state, LL state, LL extra, ML extra, OF extra
+            field = stv[lane]; nb = stn[lane];
+            field |= (uint64_t)stv[32 + lane] << nb; nb += stn[32 + lane];
+            field |= (uint64_t)stv[64 + lane] << nb; nb += stn[64 + lane];
+            field |= (uint64_t)(ll & ((1u << llb) - 1)) << nb; nb += llb;
+            field |= (uint64_t)(mlb & ((1u << mlbits) - 1)) << nb; nb += mlbits;
+            field |= (uint64_t)(offb & ((1u << ofc) - 1)) << nb; nb += ofc;
+        }
+        const uint32_t inc = warp_inclusive_scan_u32(nb, lane);
+        ze_put_bits(bits, bitpos + inc - nb, field, nb);
+        bitpos += __shfl_sync(TS_FULL, inc, 31);
+        __syncwarp();
+    }
+    // FSE_flushCState x3 (ML, OF, LL) then the closing 1 bit
+    const uint32_t st_of = __shfl_sync(TS_FULL, state, 0), st_ml = __shfl_sync(TS_FULL, state, 1),
+                   st_ll = __shfl_sync(TS_FULL, state, 2);
+    if (lane == 0) {
+        uint64_t f = st_ml & ((1u << zf::ML_DEFAULT_LOG) - 1);
+        uint32_t nb = zf::ML_DEFAULT_LOG;
+        f |= (uint64_t)(st_of & ((1u << zf::OF_DEFAULT_LOG) - 1)) << nb; nb += zf::OF_DEFAULT_LOG;
+        f |= (uint64_t)(st_ll & ((1u << zf::LL_DEFAULT_LOG) - 1)) << nb; nb += zf::LL_DEFAULT_LOG;
+        f |= 1ull << nb; nb += 1;
+        ze_put_bits(bits, bitpos, f, nb);
+    }
+    bitpos += zf::ML_DEFAULT_LOG + zf::OF_DEFAULT_LOG + zf::LL_DEFAULT_LOG + 1;
+    __syncwarp();
+    return (bitpos + 7) >> 3;
+}
+
+__global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __grid_constant__ ZstdEncArgs A) {
+    TS_DYN_SMEM(smem);
+    __shared__ ZeFseShared fs;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < sizeof(ZeFseShared) / 4; i += blockDim.x)
+        ((uint32_t*)&fs)[i] = ((const uint32_t*)&g_pre_ctables)[i];
+    __syncthreads();
+
+    const uint32_t chunk = blockIdx.y;
+    const uint32_t blk = blockIdx.x * ZE_WPB + warp;
+    const uint32_t clen = A.in_len[chunk];
+    if ((uint64_t)blk * ZB >= clen) return;                       // whole warp
+    const uint32_t bn = min(ZB, clen - blk * ZB);
+    const bool last_block = (uint64_t)(blk + 1) * ZB >= clen;
+    const uint8_t* src = A.in_base + A.in_off[chunk] + (size_t)blk * ZB;
+    const size_t gblk = (size_t)chunk * A.blocks_per_chunk + blk;
+    uint8_t* out = A.blk_out + gblk * ZE_SLOT;
+    uint2* seqs = A.seqs + gblk * ZE_MAXSEQ;
+    uint8_t* lits = A.lits + gblk * ZB;
+
+    uint8_t* wbase = smem + warp * ZE_SMEM_WARP_AL;
+    uint8_t* buf = wbase;
+    uint16_t* ht = (uint16_t*)(wbase + ZB + ZE_BUF_PAD);
+    uint8_t* codes = (uint8_t*)(ht + ZE_HSIZE);
+    uint16_t* stv = (uint16_t*)(codes + 96);
+    uint8_t* stn = (uint8_t*)(stv + 96);
+
+    // ---- stage the block in shared memory (128-bit loads when the source is aligned), zero the pad, reset the table
+    if ((((uintptr_t)src) & 15) == 0) {
+        for (uint32_t i = lane * 16; i < bn; i += 512) {
+            if (i + 16 <= bn) *(uint4*)(buf + i) = ldg128_stream((const uint4*)(src + i));
+            else for (uint32_t k = i; k < bn; k++) buf[k] = src[k];
+        }
+    } else {
+        for (uint32_t i = lane; i < bn; i += 32) buf[i] = src[i];
+    }
+    for (uint32_t i = bn + lane; i < ZB + ZE_BUF_PAD; i += 32) buf[i] = 0;
+    for (uint32_t i = lane; i < ZE_HSIZE / 2; i += 32) ((uint32_t*)ht)[i] = 0xffffffffu;
+    __syncwarp();
+
+    // ---- phase A: greedy LZ parse, 32 positions per step
+    uint32_t anchor = 0, cur = 0, nseq = 0, nlit = 0;
+    while (cur + 4 <= bn && nseq < ZE_MAXSEQ) {
+        const uint32_t p = cur + lane;
+        const bool valid = p + 4 <= bn;
+        const uint32_t v = ld_u32_unaligned(buf + p);
+        const uint32_t h = ze_hash(v);
+        const uint32_t cand = valid ? ht[h] : 0xffffu;
+        __syncwarp();
+        const uint32_t same = __match_any_sync(TS_FULL, valid ? h : 0x10000u + lane);
+        if (valid && lane == (uint32_t)(31 - __clz((int)same))) ht[h] = (uint16_t)p;   // newest position wins, deterministically
+        __syncwarp();
+        bool ok = cand != 0xffffu && ld_u32_unaligned(buf + cand) == v;
+        uint32_t len = 0;
+        if (ok) {
+            len = 4;
+            const uint32_t lim = min(bn - p, 4 + ZE_LANE_EXT);
+            while (len < lim) {
+                const uint32_t x = ld_u32_unaligned(buf + p + len) ^ ld_u32_unaligned(buf + cand + len);
+                const uint32_t c = ze_common_bytes(x);
+                len += c;
+                if (c < 4) break;
+            }
+            len = min(len, lim);
+        }
+        const uint32_t mask = __ballot_sync(TS_FULL, ok);
+        uint32_t pos = 0;
+        while (pos < 32 && nseq < ZE_MAXSEQ) {
+            const uint32_t m2 = (mask >> pos) << pos;
+            if (!m2) break;
+            const uint32_t f = (uint32_t)__ffs((int)m2) - 1;
+            uint32_t L = __shfl_sync(TS_FULL, len, f);
+            const uint32_t off = __shfl_sync(TS_FULL, p - cand, f);
+            const uint32_t mpos = cur + f;
+            if (L == 4 + ZE_LANE_EXT && mpos + L < bn) {           // warp-wide extension of a long match
+                while (true) {
+                    const uint32_t q = mpos + L + 4 * lane;
+                    uint32_t c = 0;
+                    if (q < bn) {
+                        c = ze_common_bytes(ld_u32_unaligned(buf + q) ^ ld_u32_unaligned(buf + q - off));
+                        c = min(c, bn - q);
+                    }
+                    const uint32_t stop = __ballot_sync(TS_FULL, c < 4);
+                    if (stop) {
+                        const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
+                        L += 4 * fl + __shfl_sync(TS_FULL, c, fl);
+                        break;
+                    }
+                    L += 128;
+                }
+            }
+            const uint32_t ll = mpos - anchor;
+            for (uint32_t k = lane; k < ll; k += 32) lits[nlit + k] = buf[anchor + k];
+            if (lane == 0) seqs[nseq] = make_uint2(ll | ((L - 3) << 16), off);
+            nlit += ll; nseq++;
+            anchor = mpos + L;
+            pos = f + L;
+        }
+        cur = max(cur + 32, anchor);
+    }
+    {   // trailing literals
+        const uint32_t ll = bn - anchor;
+        for (uint32_t k = lane; k < ll; k += 32) lits[nlit + k] = buf[anchor + k];
+        nlit += ll;
+    }
+    __syncwarp();
+    __threadfence_block();
+
+    // ---- phase B: entropy stage into the (now free) shared block buffer, then emit
+    uint32_t payload = 0xffffffffu;                                // "not compressible"
+    if (nseq > 0) {
+        // literals section first (into `out` directly), then the sequences bit stream staged in `buf`
+        uint8_t* body = out + 3;
+        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, ht, lane);   // header + payload
+        __syncwarp();
+        for (uint32_t i = lane; i < (ZB + ZE_BUF_PAD) / 4; i += 32) ((uint32_t*)buf)[i] = 0;
+        __syncwarp();
+        const uint32_t sbytes = ze_encode_sequences(seqs, nseq, (uint32_t*)buf, codes, stv, stn, &fs, lane);
+        const uint32_t shdr = nseq < 128 ? 1u : (nseq < 0x7f00 ? 2u : 3u);
+        const uint32_t total = lit_bytes + shdr + 1 + sbytes;
+        if (total < bn) {
+            uint8_t* sp = body + lit_bytes;
+            if (lane == 0) {
+                if (shdr == 1) sp[0] = (uint8_t)nseq;
+                else if (shdr == 2) { sp[0] = (uint8_t)((nseq >> 8) + 0x80); sp[1] = (uint8_t)nseq; }
+                else { sp[0] = 0xff; sp[1] = (uint8_t)(nseq - 0x7f00); sp[2] = (uint8_t)((nseq - 0x7f00) >> 8); }
+                sp[shdr] = 0;                                      // LL/OF/ML all Predefined_Mode
+            }
+            for (uint32_t i = lane; i < sbytes; i += 32) sp[shdr + 1 + i] = buf[i];
+            payload = total;
+        }
+    }
+    if (payload == 0xffffffffu) {                                  // Raw_Block
+        for (uint32_t i = lane; i < bn; i += 32) out[3 + i] = src[i];
+    }
+    if (lane == 0) {
+        const uint32_t type = payload == 0xffffffffu ? 0u : 2u;
+        const uint32_t bsize = payload == 0xffffffffu ? bn : payload;
+        const uint32_t hdr = (last_block ? 1u : 0u) | (type << 1) | (bsize << 3);
+        out[0] = (uint8_t)hdr; out[1] = (uint8_t)(hdr >> 8); out[2] = (uint8_t)(hdr >> 16);
+        A.blk_size[gblk] = 3 + bsize;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ frame assembly
+__device__ __forceinline__ uint32_t ze_frame_header(uint8_t* h, uint32_t n) {     // see tshost::zstdFrameHeader
+    uint32_t p = 0;
+    h[p++] = 0x28; h[p++] = 0xB5; h[p++] = 0x2F; h[p++] = 0xFD;
+    if (n <= (1u << 21)) {
+        if (n < 256) { h[p++] = 0x20; h[p++] = (uint8_t)n; }
+        else if (n < 65536 + 256) { h[p++] = 0x60; h[p++] = (uint8_t)(n - 256); h[p++] = (uint8_t)((n - 256) >> 8); }
+        else { h[p++] = 0xA0; h[p++] = (uint8_t)n; h[p++] = (uint8_t)(n >> 8); h[p++] = (uint8_t)(n >> 16); h[p++] = (uint8_t)(n >> 24); }
+    } else {
+        h[p++] = 0x80; h[p++] = 0x58;
+        h[p++] = (uint8_t)n; h[p++] = (uint8_t)(n >> 8); h[p++] = (uint8_t)(n >> 16); h[p++] = (uint8_t)(n >> 24);
+    }
+    return p;
+}
+
+// warp copy of n bytes, src 4-byte aligned (block slots are), dst arbitrary: aligned 32-bit stores in the middle
+__device__ __forceinline__ void ze_warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t lane) {
+    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+    if (lane < head) dst[lane] = src[lane];
+    const uint32_t words = (n - head) >> 2;
+    uint32_t* d32 = (uint32_t*)(dst + head);
+    const uint8_t* s = src + head;
+    for (uint32_t i = lane; i < words; i += 32) d32[i] = ld_u32_unaligned(s + 4 * i);
+    const uint32_t done = head + 4 * words;
+    if (lane < n - done) dst[done + lane] = src[done + lane];
+}
+
+__global__ void __launch_bounds__(256) zstd_enc_assemble_kernel(const __grid_constant__ ZstdEncArgs A) {
+    __shared__ uint32_t pos[1024 + 1];
+    __shared__ uint32_t hdr_len;
+    const uint32_t chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t clen = A.in_len[chunk];
+    const uint32_t nblk = (clen + ZB - 1) / ZB;
+    uint8_t* frame = A.out_base + A.out_off[chunk];
+    const uint32_t* bs = A.blk_size + (size_t)chunk * A.blocks_per_chunk;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nblk; base += 1024) {          // chunks of up to 1024 blocks at a time
+        const uint32_t cnt = min(1024u, nblk - base);
+        if (warp == 0) {
+            uint32_t run = carry;
+            for (uint32_t b0 = 0; b0 < cnt; b0 += 32) {
+                const uint32_t i = b0 + lane;
+                const uint32_t v = i < cnt ? bs[base + i] : 0;
+                const uint32_t inc = warp_inclusive_scan_u32(v, lane);
+                if (i < cnt) pos[i] = run + inc - v;
+                run += __shfl_sync(TS_FULL, inc, 31);
+            }
+            if (lane == 0) {
+                pos[cnt] = run;
+                if (base == 0) {
+                    uint8_t h[16];
+                    const uint32_t hl = ze_frame_header(h, clen);
+                    for (uint32_t k = 0; k < hl; k++) frame[k] = h[k];
+                    hdr_len = hl;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t hl = hdr_len;
+        for (uint32_t b = warp; b < cnt; b += blockDim.x >> 5) {
+            const uint8_t* s = A.blk_out + ((size_t)chunk * A.blocks_per_chunk + base + b) * ZE_SLOT;
+            ze_warp_copy(frame + hl + pos[b], s, pos[b + 1] - pos[b], lane);
+        }
+        carry = pos[cnt];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        uint32_t total = hdr_len + carry;
+        if (nblk == 0) {                                           // empty chunk: header + empty last raw block
+            uint8_t h[16];
+            const uint32_t hl = ze_frame_header(h, 0);
+            for (uint32_t k = 0; k < hl; k++) frame[k] = h[k];
+            frame[hl] = 1; frame[hl + 1] = 0; frame[hl + 2] = 0;
+            total = hl + 3;
+        }
+        A.out_len[chunk] = total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static thread_local const char* g_zstd_err = "";
+inline const char* zstd_last_error() { return g_zstd_err; }
+
+inline const char* zstd_enc_scratch_alloc(ZstdEncScratch& s, uint32_t chunk_cap, uint32_t max_batch) {
+    s.blocks_per_chunk = (chunk_cap + ZB - 1) / ZB;
+    s.max_batch = max_batch;
+    const size_t nblk = (size_t)s.blocks_per_chunk * max_batch;
+    const char* e;
+    if ((e = rt::malloc_device((void**)&s.blk_out, nblk * ZE_SLOT + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.blk_size, nblk * 4 + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.seqs, nblk * ZE_MAXSEQ * sizeof(uint2) + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.lits, nblk * ZB + 256))) return e;
+    return nullptr;
+}
+inline void zstd_enc_scratch_free(ZstdEncScratch& s) {
+    rt::free_device(s.blk_out); rt::free_device(s.blk_size); rt::free_device(s.seqs); rt::free_device(s.lits);
+    s = ZstdEncScratch{};
+}
+
+constexpr uint32_t ZE_SMEM_BYTES = ZE_WPB * ZE_SMEM_WARP_AL;
+
+inline int zstd_compress_batch(ZstdEncScratch& s, rt::stream_t st, const uint8_t* in_base, const uint64_t* d_in_off,
+                               const uint32_t* d_in_len, uint32_t n_chunks, uint32_t chunk_size,
+                               uint8_t* out_base, const uint64_t* d_out_off, uint32_t* d_out_len, LaunchProf& prof) {
+    if (n_chunks > s.max_batch) { g_zstd_err = "batch larger than the context"; return -1; }
+    const uint32_t bpc = (chunk_size + ZB - 1) / ZB;
+    if (bpc > s.blocks_per_chunk) { g_zstd_err = "chunk larger than the context"; return -1; }
+    ZstdEncArgs A;
+    A.in_base = in_base; A.in_off = d_in_off; A.in_len = d_in_len;
+    A.blk_out = s.blk_out; A.blk_size = s.blk_size; A.seqs = s.seqs; A.lits = s.lits;
+    A.blocks_per_chunk = s.blocks_per_chunk;
+    A.out_base = out_base; A.out_off = d_out_off; A.out_len = d_out_len;
+    if (bpc) {
+        TS_LAUNCH_P(prof, "zstd_enc_blocks", zstd_enc_blocks_kernel, dim3((bpc + ZE_WPB - 1) / ZE_WPB, n_chunks), dim3(ZE_WPB * 32),
+                    ZE_SMEM_BYTES, st, A);
+        const char* e = rt::last_error();
+        if (e) { g_zstd_err = e; return -7; }
+    }
+    TS_LAUNCH_P(prof, "zstd_enc_assemble", zstd_enc_assemble_kernel, dim3(n_chunks), dim3(256), 0, st, A);
+    const char* e = rt::last_error();
+    if (e) { g_zstd_err = e; return -7; }
+    return 0;
+}
+
+}  // namespace ts
