@@ -24,3 +24,9 @@ clean:
 	rm -f $(PKG)/libtsgpu.so tests/simt/libtsgpu_simt.so build_ptxas.log
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean
+
+# C++ host-mirror tests: `_simt` links the test-only emulator build (CPU box), `_gpu` links the product library.
+tests/cpp/test_host_mirror_simt: tests/cpp/test_host_mirror.cpp $(PKG)/host/chunk_transform.hpp tests/simt/libtsgpu_simt.so oracle
+	g++ -O1 -g -std=c++17 -o $@ tests/cpp/test_host_mirror.cpp -Ltests/simt -ltsgpu_simt -Loracle -ltsoracle -Wl,-rpath,'$$ORIGIN/../simt' -Wl,-rpath,'$$ORIGIN/../../oracle'
+tests/cpp/test_host_mirror_gpu: tests/cpp/test_host_mirror.cpp $(PKG)/host/chunk_transform.hpp $(PKG)/libtsgpu.so oracle
+	g++ -O1 -g -std=c++17 -o $@ tests/cpp/test_host_mirror.cpp -L$(PKG) -ltsgpu -Loracle -ltsoracle -Wl,-rpath,'$$ORIGIN/../../$(PKG)' -Wl,-rpath,'$$ORIGIN/../../oracle' -Wl,-rpath,/usr/local/cuda/lib64

@@ -1,0 +1,88 @@
+/*
+ * tsgpu_jni.c — JNI glue between the reference's Java operator surface and the C-ABI of include/tsgpu.h.
+ * NOT compiled in this repository's image (no JDK / jni.h); build on the broker host with
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude jni/tsgpu_jni.c -L<pkg> -ltsgpu -o libtsgpu_jni.so
+ * Java side: jni/io/aiven/kafka/tieredstorage/transform/gpu/*.java (implements TransformChunkEnumeration /
+ * DetransformChunkEnumeration of the reference, core/M/transform/TransformChunkEnumeration.java:28-42).
+ *
+ * Buffers are direct ByteBuffers (ideally over tsgpu_host_alloc'ed pinned memory, see allocPinned), so there is no
+ * JNI array copy on the data path.  Errors become RuntimeException(tsgpu_last_error()), which is what the
+ * reference's operators throw and RemoteStorageManager converts (RemoteStorageManager.java:258-267, :566-575).
+ */
+#include <jni.h>
+#include <stdint.h>
+#include "tsgpu.h"
+
+#define CLS "io/aiven/kafka/tieredstorage/transform/gpu/TsGpu"
+
+static void throw_rt(JNIEnv* env, int rc) {
+    jclass ex = (*env)->FindClass(env, rc == TSGPU_E_ARG ? "java/lang/IllegalArgumentException" : "java/lang/RuntimeException");
+    (*env)->ThrowNew(env, ex, tsgpu_last_error());
+}
+
+JNIEXPORT jlong JNICALL Java_io_aiven_kafka_tieredstorage_transform_gpu_TsGpu_create(JNIEnv* env, jclass c, jintArray devices,
+                                                                                     jint maxChunkBytes, jint maxBatch) {
+    tsgpu_ctx* ctx = NULL;
+    jint n = devices ? (*env)->GetArrayLength(env, devices) : 0;
+    jint* ids = n ? (*env)->GetIntArrayElements(env, devices, NULL) : NULL;
+    int rc = tsgpu_create((const int*)ids, n, (uint32_t)maxChunkBytes, (uint32_t)maxBatch, &ctx);
+    if (ids) (*env)->ReleaseIntArrayElements(env, devices, ids, JNI_ABORT);
+    if (rc) { throw_rt(env, rc); return 0; }
+    return (jlong)(intptr_t)ctx;
+}
+JNIEXPORT void JNICALL Java_io_aiven_kafka_tieredstorage_transform_gpu_TsGpu_destroy(JNIEnv* env, jclass c, jlong h) {
+    tsgpu_destroy((tsgpu_ctx*)(intptr_t)h);
+}
+JNIEXPORT jobject JNICALL Java_io_aiven_kafka_tieredstorage_transform_gpu_TsGpu_allocPinned(JNIEnv* env, jclass c, jlong bytes) {
+    void* p = tsgpu_host_alloc((size_t)bytes);
+    return p ? (*env)->NewDirectByteBuffer(env, p, bytes) : NULL;
+}
+JNIEXPORT void JNICALL Java_io_aiven_kafka_tieredstorage_transform_gpu_TsGpu_freePinned(JNIEnv* env, jclass c, jobject buf) {
+    tsgpu_host_free((*env)->GetDirectBufferAddress(env, buf));
+}
+JNIEXPORT jlong JNICALL Java_io_aiven_kafka_tieredstorage_transform_gpu_TsGpu_transformBound(JNIEnv* env, jclass c, jint flags,
+                                                                                             jlong srcLen, jint chunkSize) {
+    return (jlong)tsgpu_transform_bound((uint32_t)flags, (uint64_t)srcLen, (uint32_t)chunkSize);
+}
+/* returns the number of chunks; transformedSizes (int[]) receives one entry per chunk */
+JNIEXPORT jint JNICALL Java_io_aiven_kafka_tieredstorage_transform_gpu_TsGpu_transform(
+    JNIEnv* env, jclass c, jlong h, jint flags, jobject src, jlong srcLen, jint chunkSize, jbyteArray key, jbyteArray aad,
+    jbyteArray ivs, jobject dst, jintArray transformedSizes) {
+    uint8_t* s = (uint8_t*)(*env)->GetDirectBufferAddress(env, src);
+    uint8_t* d = (uint8_t*)(*env)->GetDirectBufferAddress(env, dst);
+    jlong dcap = (*env)->GetDirectBufferCapacity(env, dst);
+    jbyte* k = key ? (*env)->GetByteArrayElements(env, key, NULL) : NULL;
+    jbyte* a = aad ? (*env)->GetByteArrayElements(env, aad, NULL) : NULL;
+    jbyte* iv = ivs ? (*env)->GetByteArrayElements(env, ivs, NULL) : NULL;
+    jint alen = aad ? (*env)->GetArrayLength(env, aad) : 0;
+    uint32_t n = (uint32_t)(*env)->GetArrayLength(env, transformedSizes);
+    jint* sizes = (*env)->GetIntArrayElements(env, transformedSizes, NULL);
+    int rc = tsgpu_transform((tsgpu_ctx*)(intptr_t)h, (uint32_t)flags, s, (uint64_t)srcLen, (uint32_t)chunkSize, (const uint8_t*)k,
+                             (const uint8_t*)a, (uint32_t)alen, (const uint8_t*)iv, d, (uint64_t)dcap, (uint32_t*)sizes, &n);
+    (*env)->ReleaseIntArrayElements(env, transformedSizes, sizes, 0);
+    if (k) (*env)->ReleaseByteArrayElements(env, key, k, JNI_ABORT);
+    if (a) (*env)->ReleaseByteArrayElements(env, aad, a, JNI_ABORT);
+    if (iv) (*env)->ReleaseByteArrayElements(env, ivs, iv, JNI_ABORT);
+    if (rc) { throw_rt(env, rc); return -1; }
+    return (jint)n;
+}
+JNIEXPORT void JNICALL Java_io_aiven_kafka_tieredstorage_transform_gpu_TsGpu_detransform(
+    JNIEnv* env, jclass c, jlong h, jint flags, jobject src, jlong srcLen, jintArray transformedSizes, jbyteArray key, jbyteArray aad,
+    jobject dst, jintArray originalSizes) {
+    uint8_t* s = (uint8_t*)(*env)->GetDirectBufferAddress(env, src);
+    uint8_t* d = (uint8_t*)(*env)->GetDirectBufferAddress(env, dst);
+    jlong dcap = (*env)->GetDirectBufferCapacity(env, dst);
+    jbyte* k = key ? (*env)->GetByteArrayElements(env, key, NULL) : NULL;
+    jbyte* a = aad ? (*env)->GetByteArrayElements(env, aad, NULL) : NULL;
+    jint alen = aad ? (*env)->GetArrayLength(env, aad) : 0;
+    uint32_t n = (uint32_t)(*env)->GetArrayLength(env, transformedSizes);
+    jint* ts = (*env)->GetIntArrayElements(env, transformedSizes, NULL);
+    jint* os = (*env)->GetIntArrayElements(env, originalSizes, NULL);
+    int rc = tsgpu_detransform((tsgpu_ctx*)(intptr_t)h, (uint32_t)flags, s, (uint64_t)srcLen, (const uint32_t*)ts, n, (const uint8_t*)k,
+                               (const uint8_t*)a, (uint32_t)alen, d, (uint64_t)dcap, (uint32_t*)os);
+    (*env)->ReleaseIntArrayElements(env, transformedSizes, ts, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, originalSizes, os, 0);
+    if (k) (*env)->ReleaseByteArrayElements(env, key, k, JNI_ABORT);
+    if (a) (*env)->ReleaseByteArrayElements(env, aad, a, JNI_ABORT);
+    if (rc) throw_rt(env, rc);
+}

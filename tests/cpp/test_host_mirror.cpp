@@ -1,0 +1,151 @@
+// Mirrors the reference's unit tests for the operator surface, against the C++ host mirror
+// (tiered-storage-for-apache-kafka_b200/host/chunk_transform.hpp):
+//   core/T/manifest/index/ChunkIndexBuilderCommonTest.java:37-127, FixedSizeChunkIndexBuilderTest.java:35-88,
+//   VariableSizeChunkIndexBuilderTest.java:45-81, core/T/transform/BaseTransformChunkEnumerationTest.java:65-94,
+//   core/T/transform/TransformFinisherTest.java:97-125, core/T/fetch/FetchChunkEnumerationTest.java:105-145,
+//   core/T/transform/TransformsEndToEndTest.java:44-116 (round trip through the batched GPU chain, checked
+//   against the oracle's libzstd/OpenSSL reader).
+// Links libtsgpu.so on a GPU box, or the test-only SIMT build on the CPU box (same sources, emulated kernels).
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <sstream>
+#include "../../tiered-storage-for-apache-kafka_b200/host/chunk_transform.hpp"
+#include "../../oracle/tsoracle.h"
+
+using namespace tieredstorage;
+static int checks = 0, failures = 0;
+#define CHECK(c) do { checks++; if (!(c)) { failures++; printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); } } while (0)
+template <class E, class F> static bool throwsWith(F f, const char* msg) {
+    try { f(); } catch (const E& e) { if (std::string(e.what()).find(msg) != std::string::npos) return true; printf("  got: %s\n", e.what()); return false; }
+    catch (...) { return false; }
+    return false;
+}
+
+static void builderTests() {
+    for (int fixed = 0; fixed < 2; fixed++) {
+        auto mk = [&](int ocs, int ofs) -> std::unique_ptr<AbstractChunkIndexBuilder> {
+            if (fixed) return std::make_unique<FixedSizeChunkIndexBuilder>(ocs, ofs, 110);
+            return std::make_unique<VariableSizeChunkIndexBuilder>(ocs, ofs);
+        };
+        CHECK(throwsWith<IllegalArgumentException>([&] { mk(-1, 250); }, "Original chunk size must be non-negative, -1 given"));
+        CHECK(throwsWith<IllegalArgumentException>([&] { mk(100, -1); }, "Original file size must be non-negative, -1 given"));
+        auto b = mk(100, 250);
+        CHECK(throwsWith<IllegalArgumentException>([&] { b->addChunk(-1); }, "Transformed chunk size must be non-negative, -1 given"));
+        b->addChunk(110); b->addChunk(110);
+        CHECK(throwsWith<IllegalStateException>([&] { b->addChunk(110); }, "This must be final chunk. Call `finish` instead."));
+        auto idx = b->finish(30);
+        CHECK(throwsWith<IllegalStateException>([&] { b->addChunk(110); }, "Cannot add chunk to already finished index"));
+        CHECK(throwsWith<IllegalStateException>([&] { b->finish(30); }, "Cannot finish already finished index"));
+        CHECK(idx->chunks().size() == 3);
+        CHECK((idx->chunks()[2] == Chunk{2, 200, 50, 220, 30}));
+        for (int off = 0; off < 250; off++) CHECK(*idx->findChunkForOriginalOffset(off) == idx->chunks()[off / 100]);
+        CHECK(!idx->findChunkForOriginalOffset(250).has_value());
+        CHECK(throwsWith<IllegalArgumentException>([&] { idx->findChunkForOriginalOffset(-1); }, "Offset must be non-negative, -1 given"));
+        auto b2 = mk(100, 250); b2->addChunk(110);
+        CHECK(throwsWith<IllegalStateException>([&] { b2->finish(30); }, "This cannot be final chunk: not enough chunks to cover original file"));
+        auto e = mk(100, 0)->finish(0);
+        CHECK(e->chunks().size() == 1 && (e->chunks()[0] == Chunk{0, 0, 0, 0, 0}));
+        CHECK(!e->findChunkForOriginalOffset(0).has_value());
+    }
+    FixedSizeChunkIndexBuilder fb(100, 250, 110);
+    CHECK(throwsWith<IllegalArgumentException>([&] { fb.addChunk(109); }, "Non-final chunk must be of size 110, but 109 given"));
+    // golden JSON (ChunkIndexSerializationTest.java:63-74)
+    CHECK(FixedSizeChunkIndex(100, 250, 110, 30).toJson() ==
+          "{\"type\":\"fixed\",\"originalChunkSize\":100,\"originalFileSize\":250,\"transformedChunkSize\":110,\"finalTransformedChunkSize\":30}");
+    CHECK(VariableSizeChunkIndex(100, 250, {10, 20, 30}).toJson() ==
+          "{\"type\":\"variable\",\"originalChunkSize\":100,\"originalFileSize\":250,\"transformedChunks\":\"KLUv/SAPeQAAAAAAAwAAAAoBAAoAAAAe\"}");
+    // fetch plan (FetchChunkEnumerationTest.java:105-145)
+    FixedSizeChunkIndex f(10, 30, 10, 10);
+    auto p = fetchPlan(f, 2, 4);     CHECK(p.size() == 1 && p[0].chunkId == 0 && p[0].skip == 2 && p[0].take == 3);
+    p = fetchPlan(f, 5, 24);         CHECK(p.size() == 3 && p[0].skip == 5 && p[0].take == 5 && p[1].take == 10 && p[2].take == 5);
+    p = fetchPlan(f, 25, 1000);      CHECK(p.size() == 1 && p[0].chunkId == 2 && p[0].skip == 5 && p[0].take == 5);
+    CHECK(throwsWith<IllegalArgumentException>([&] { fetchPlan(f, 30, 31); }, "Invalid start position 30"));
+}
+
+static void baseAndFinisherTests() {
+    std::istringstream in(std::string("0123456789"));
+    BaseTransformChunkEnumeration base(&in, 3);                       // BaseTransformChunkEnumerationTest: "012" "345" "678" "9"
+    CHECK(base.originalChunkSize() == 3 && *base.transformedChunkSize() == 3);
+    std::vector<std::string> got;
+    while (base.hasMoreElements()) { Bytes c = base.nextElement(); got.emplace_back(c.begin(), c.end()); }
+    CHECK((got == std::vector<std::string>{"012", "345", "678", "9"}));
+    CHECK(throwsWith<NoSuchElementException>([&] { base.nextElement(); }, "NoSuchElement"));
+    CHECK(throwsWith<IllegalArgumentException>([&] { BaseTransformChunkEnumeration(&in, -1); }, "originalChunkSize must be non-negative, -1 given"));
+    CHECK(throwsWith<NullPointerException>([&] { BaseTransformChunkEnumeration(nullptr, 1); }, "inputStream cannot be null"));
+    // TransformFinisherTest.java:97-125: 7 bytes, chunk 3 -> Chunk(0,0,3,0,3),(1,3,3,3,3),(2,6,1,6,1); fixed index for the base transform
+    std::istringstream in2(std::string("\0\1\2\3\4\5\6", 7));
+    BaseTransformChunkEnumeration b2(&in2, 3);
+    TransformFinisher fin(&b2, 7);
+    Bytes all = fin.readAll();
+    CHECK(all.size() == 7);
+    auto idx = fin.chunkIndex();
+    CHECK(dynamic_cast<FixedSizeChunkIndex*>(idx.get()) != nullptr);
+    CHECK(idx->chunks().size() == 3 && (idx->chunks()[1] == Chunk{1, 3, 3, 3, 3}) && (idx->chunks()[2] == Chunk{2, 6, 1, 6, 1}));
+    // not consumed + base transform => index computed from the file size (TransformFinisher.java:124-132)
+    std::istringstream in3(std::string(250, 'x'));
+    BaseTransformChunkEnumeration b3(&in3, 100);
+    CHECK(TransformFinisher(&b3, 250).chunkIndex()->chunks().size() == 3);
+}
+
+static void gpuChainTests(tsgpu_ctx* ctx) {
+    std::mt19937 rng(7);
+    const int n = 181200;
+    Bytes src(n);
+    for (int i = 0; i < n; i++) src[i] = (i < n / 2) ? (uint8_t)("the quick brown fox jumps over the lazy dog "[(i * 7 + (i >> 9)) % 44]) : (uint8_t)rng();
+    DataKeyAndAAD km{Bytes(32), Bytes(32)};
+    for (auto& b : km.dataKey) b = (uint8_t)rng();
+    for (auto& b : km.aad) b = (uint8_t)rng();
+    uint32_t ivc = 0;
+    IvSupplier ivs = [&](uint8_t* iv) { memset(iv, 0, 12); memcpy(iv, &ivc, 4); ivc++; };
+    for (int cs : {0, 13, 1024, 5123, n - 1, 2 * n}) {
+        for (int mode = 1; mode < 4; mode++) {                         // 1 = zstd, 2 = aes, 3 = both (TransformsEndToEndTest grid)
+            const int use_n = cs == 13 ? 1300 : n;
+            std::istringstream in(std::string((const char*)src.data(), use_n));
+            BaseTransformChunkEnumeration base(&in, cs);
+            std::unique_ptr<CompressionChunkEnumeration> comp;
+            std::unique_ptr<EncryptionChunkEnumeration> enc;
+            TransformChunkEnumeration* top = &base;
+            if (mode & 1) { comp = std::make_unique<CompressionChunkEnumeration>(ctx, top, 8); top = comp.get(); }
+            if (mode & 2) { enc = std::make_unique<EncryptionChunkEnumeration>(ctx, top, km, ivs, 8); top = enc.get(); }
+            // transformedChunkSize(): fixed only without compression (EncryptionChunkEnumeration.java:35-47)
+            if (mode == 2 && cs) CHECK(*top->transformedChunkSize() == cs + 28); else if (mode & 1) CHECK(!top->transformedChunkSize().has_value());
+            TransformFinisher fin(top, use_n, cs != 0);
+            Bytes obj = fin.readAll();
+            auto idx = fin.chunkIndex();
+            CHECK((mode & 1) ? dynamic_cast<VariableSizeChunkIndex*>(idx.get()) != nullptr : dynamic_cast<FixedSizeChunkIndex*>(idx.get()) != nullptr);
+            const auto& chunks = idx->chunks();
+            CHECK((size_t)(chunks.back().transformedPosition + chunks.back().transformedSize) == obj.size());
+            // the reference-side reader (oracle: libzstd + OpenSSL) recovers the bytes chunk by chunk
+            std::vector<uint32_t> ts; for (auto& c : chunks) ts.push_back((uint32_t)c.transformedSize);
+            Bytes back(use_n + 64); std::vector<uint32_t> osz(ts.size());
+            int rc = ora_detransform_chunks(mode, obj.data(), ts.data(), (uint32_t)ts.size(), km.dataKey.data(), km.aad.data(), 32, back.data(), back.size(), osz.data());
+            CHECK(rc == 0);
+            CHECK(memcmp(back.data(), src.data(), use_n) == 0);
+            // and our batched detransform enumeration does too
+            std::istringstream oin(std::string((const char*)obj.data(), obj.size()));
+            DetransformChunkEnumeration de(ctx, &oin, chunks, mode & 1, (mode & 2) ? &km : nullptr, cs ? (uint32_t)std::min(cs, use_n) : use_n, 8);
+            Bytes round;
+            while (de.hasMoreElements()) { Bytes c = de.nextElement(); round.insert(round.end(), c.begin(), c.end()); }
+            CHECK(round.size() == (size_t)use_n && memcmp(round.data(), src.data(), use_n) == 0);
+            // truncated stream: "Stream has fewer bytes than expected" (BaseDetransformChunkEnumerationTest.java:100-117)
+            std::istringstream tin(std::string((const char*)obj.data(), obj.size() - 1));
+            DetransformChunkEnumeration dt(ctx, &tin, chunks, mode & 1, (mode & 2) ? &km : nullptr, cs ? (uint32_t)std::min(cs, use_n) : use_n, 1024);
+            CHECK(throwsWith<std::runtime_error>([&] { while (dt.hasMoreElements()) dt.nextElement(); }, "Stream has fewer bytes than expected"));
+        }
+    }
+}
+
+int main(int argc, char** argv) {
+    builderTests();
+    baseAndFinisherTests();
+    if (argc > 1 && !strcmp(argv[1], "--device")) {
+        tsgpu_ctx* ctx = nullptr;
+        int rc = tsgpu_create(nullptr, 0, 400000, 16, &ctx);
+        if (rc) { printf("tsgpu_create failed: %s\n", tsgpu_last_error()); return 2; }
+        gpuChainTests(ctx);
+        tsgpu_destroy(ctx);
+    }
+    printf("%s: %d checks, %d failures\n", failures ? "FAILED" : "OK", checks, failures);
+    return failures ? 1 : 0;
+}

@@ -38,7 +38,7 @@ extern "C" const char* tsgpu_last_error(void) { return g_err; }
 extern "C" const char* tsgpu_version(void) { return "tsgpu 0.1 (sm_100a)"; }
 
 static inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
-static inline uint64_t frame_bound(uint64_t n) { return n + (n >> 8) + 64; }   // >= header + 3 bytes per 16 KiB block
+static inline uint64_t frame_bound(uint64_t n) { return n + (n >> 8) + 64; }   // >= header + 3 bytes per 8 KiB block
 
 // ------------------------------------------------------------------------------------------ context
 namespace {

@@ -9,9 +9,9 @@
 //
 // Three kernels per batch:
 //   zstd_dec_index_kernel    one warp per chunk: frame header, Frame_Content_Size, block offsets; marks frames
-//                            whose block structure matches this library's writer (ceil(FCS / 16 KiB) blocks)
-//   zstd_dec_blocks_kernel   fast path, one warp PER BLOCK of such frames (65,536 independent units per GiB);
-//                            every assumption (block regenerates exactly 16 KiB, no offset before the block, no
+//                            whose block structure matches this library's writer (ceil(FCS / ZB), ZB = 8 KiB blocks)
+//   zstd_dec_blocks_kernel   fast path, one warp PER BLOCK of such frames (131,072 independent units per GiB);
+//                            every assumption (block regenerates exactly ZB bytes, no offset before the block, no
 //                            repeat offsets/tables carried in) is verified while decoding, and a violation only
 //                            flags the frame for the general path — correctness never depends on the guess
 //   zstd_dec_frames_kernel   general path, one warp per frame walking its blocks in order (what libzstd frames need)

@@ -6,8 +6,8 @@
 // Parity bar: libzstd decodes every frame to the original bytes and
 // ZSTD_getFrameContentSize(frame) == original size.  Compressed bytes are not expected to equal libzstd's.
 //
-// B200-first decomposition: a chunk is cut into ZB = 16 KiB zstd blocks that never reference each other
-// (no cross-block matches, no repeat offsets, no repeated tables), so a 1 GiB segment is 65,536 independent
+// B200-first decomposition: a chunk is cut into ZB = 8 KiB zstd blocks that never reference each other
+// (no cross-block matches, no repeat offsets, no repeated tables), so a 1 GiB segment is 131,072 independent
 // units instead of 256 sequential ones.
 //   zstd_enc_blocks_kernel    one WARP per block: block staged in shared memory; 32 positions hashed and
 //                             verified per step against a per-warp hash table, greedy left-to-right selection
@@ -27,15 +27,15 @@
 
 namespace ts {
 
-constexpr uint32_t ZB = 16384;                 // bytes of original data per zstd block
-constexpr int ZE_HLOG = 11;                    // per-warp hash table: 2^11 x u16
+constexpr uint32_t ZB = 8192;                  // bytes of original data per zstd block
+constexpr int ZE_HLOG = 10;                    // per-warp hash table: 2^10 x u32 (position + 1)
 constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
-constexpr int ZE_WPB = 2;                      // warps (= blocks in flight) per CTA
+constexpr int ZE_WPB = 1;                      // warps (= blocks in flight) per CTA
 constexpr uint32_t ZE_MAXSEQ = ZB / 8;         // sequences kept per block; beyond that the rest goes out as literals
 constexpr uint32_t ZE_LANE_EXT = 60;           // bytes a lane extends its own match beyond the first 4
 constexpr uint32_t ZE_BUF_PAD = 160;
 constexpr uint32_t ZE_SLOT = ZB + 64;          // per-block output slot: 3-byte header + payload (<= ZB when compressed)
-constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 2 + 3 * 32 + 3 * 32 * 2 + 3 * 32;   // buf, ht, codes, stv, stn
+constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 4 + 3 * 32 + 3 * 32 * 2 + 3 * 32;   // buf, ht, codes, stv, stn
 constexpr uint32_t ZE_SMEM_WARP_AL = (ZE_SMEM_WARP + 15) & ~15u;
 
 __constant__ zf::SeqTables g_seq_tables = zf::make_seq_tables();
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
 
     uint8_t* wbase = smem + warp * ZE_SMEM_WARP_AL;
     uint8_t* buf = wbase;
-    uint16_t* ht = (uint16_t*)(wbase + ZB + ZE_BUF_PAD);
+    uint32_t* ht = (uint32_t*)(wbase + ZB + ZE_BUF_PAD);
     uint8_t* codes = (uint8_t*)(ht + ZE_HSIZE);
     uint16_t* stv = (uint16_t*)(codes + 96);
     uint8_t* stn = (uint8_t*)(stv + 96);
@@ -209,44 +209,46 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
         for (uint32_t i = lane; i < bn; i += 32) buf[i] = src[i];
     }
     for (uint32_t i = bn + lane; i < ZB + ZE_BUF_PAD; i += 32) buf[i] = 0;
-    for (uint32_t i = lane; i < ZE_HSIZE / 2; i += 32) ((uint32_t*)ht)[i] = 0xffffffffu;
+    for (uint32_t i = lane; i < ZE_HSIZE; i += 32) ht[i] = 0;
     __syncwarp();
 
     // ---- phase A: greedy LZ parse, 32 positions per step
-    uint32_t anchor = 0, cur = 0, nseq = 0, nlit = 0;
+    // Selection (which of the 32 candidate matches survive, left to right) is the only serial part and costs a
+    // handful of instructions per taken match; sequences are then written by their own lanes in parallel and
+    // literals are gathered in one pass afterwards.
+    uint32_t anchor = 0, cur = 0, nseq = 0;
     while (cur + 4 <= bn && nseq < ZE_MAXSEQ) {
         const uint32_t p = cur + lane;
         const bool valid = p + 4 <= bn;
         const uint32_t v = ld_u32_unaligned(buf + p);
         const uint32_t h = ze_hash(v);
-        const uint32_t cand = valid ? ht[h] : 0xffffu;
+        const uint32_t slot = valid ? ht[h] : 0u;                  // position + 1, 0 = empty
         __syncwarp();
-        const uint32_t same = __match_any_sync(TS_FULL, valid ? h : 0x10000u + lane);
-        if (valid && lane == (uint32_t)(31 - __clz((int)same))) ht[h] = (uint16_t)p;   // newest position wins, deterministically
+        if (valid) atomicMax(&ht[h], p + 1);                       // newest position wins, deterministically
         __syncwarp();
-        bool ok = cand != 0xffffu && ld_u32_unaligned(buf + cand) == v;
+        const uint32_t cand = slot - 1;
+        const bool ok = slot != 0 && ld_u32_unaligned(buf + cand) == v;
         uint32_t len = 0;
         if (ok) {
             len = 4;
             const uint32_t lim = min(bn - p, 4 + ZE_LANE_EXT);
             while (len < lim) {
-                const uint32_t x = ld_u32_unaligned(buf + p + len) ^ ld_u32_unaligned(buf + cand + len);
-                const uint32_t c = ze_common_bytes(x);
+                const uint32_t c = ze_common_bytes(ld_u32_unaligned(buf + p + len) ^ ld_u32_unaligned(buf + cand + len));
                 len += c;
                 if (c < 4) break;
             }
             len = min(len, lim);
         }
         const uint32_t mask = __ballot_sync(TS_FULL, ok);
-        uint32_t pos = 0;
-        while (pos < 32 && nseq < ZE_MAXSEQ) {
+        uint32_t taken = 0, pos = 0, budget = ZE_MAXSEQ - nseq;
+        while (pos < 32 && budget) {
             const uint32_t m2 = (mask >> pos) << pos;
             if (!m2) break;
             const uint32_t f = (uint32_t)__ffs((int)m2) - 1;
             uint32_t L = __shfl_sync(TS_FULL, len, f);
-            const uint32_t off = __shfl_sync(TS_FULL, p - cand, f);
-            const uint32_t mpos = cur + f;
-            if (L == 4 + ZE_LANE_EXT && mpos + L < bn) {           // warp-wide extension of a long match
+            if (L == 4 + ZE_LANE_EXT && cur + f + L < bn) {        // warp-wide extension of a long match
+                const uint32_t off = __shfl_sync(TS_FULL, p - cand, f);
+                const uint32_t mpos = cur + f;
                 while (true) {
                     const uint32_t q = mpos + L + 4 * lane;
                     uint32_t c = 0;
@@ -262,18 +264,50 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
                     }
                     L += 128;
                 }
+                if (lane == f) len = L;
             }
-            const uint32_t ll = mpos - anchor;
-            for (uint32_t k = lane; k < ll; k += 32) lits[nlit + k] = buf[anchor + k];
-            if (lane == 0) seqs[nseq] = make_uint2(ll | ((L - 3) << 16), off);
-            nlit += ll; nseq++;
-            anchor = mpos + L;
+            taken |= 1u << f;
             pos = f + L;
+            budget--;
+        }
+        if (taken) {
+            const uint32_t my_end = p + len;                       // meaningful on taken lanes
+            const uint32_t lower = taken & ((1u << lane) - 1);
+            const uint32_t prev_lane = lower ? (uint32_t)(31 - __clz((int)lower)) : 0u;
+            uint32_t prev_end = __shfl_sync(TS_FULL, my_end, prev_lane);
+            if (!lower) prev_end = anchor;
+            if ((taken >> lane) & 1)
+                seqs[nseq + (uint32_t)__popc(lower)] = make_uint2((p - prev_end) | ((len - 3) << 16), p - cand);
+            nseq += (uint32_t)__popc(taken);
+            anchor = cur + pos;
         }
         cur = max(cur + 32, anchor);
     }
-    {   // trailing literals
-        const uint32_t ll = bn - anchor;
+    __syncwarp();
+    __threadfence_block();
+    // ---- literal gather: one lane per sequence copies its literal run; long runs are finished by the whole warp
+    uint32_t nlit = 0;
+    {
+        uint32_t src_pos = 0;
+        for (uint32_t t0 = 0; t0 < nseq; t0 += 32) {
+            const uint32_t i = t0 + lane;
+            uint32_t ll = 0, ml = 0;
+            if (i < nseq) { const uint2 sq = seqs[i]; ll = sq.x & 0xffff; ml = (sq.x >> 16) + 3; }
+            const uint32_t inc_l = warp_inclusive_scan_u32(ll, lane), inc_s = warp_inclusive_scan_u32(ll + ml, lane);
+            const uint32_t lo = nlit + inc_l - ll, so = src_pos + inc_s - ll - ml;
+            const uint32_t quick = min(ll, 16u);
+            for (uint32_t k = 0; k < quick; k++) lits[lo + k] = buf[so + k];
+            uint32_t longs = __ballot_sync(TS_FULL, ll > 16);
+            while (longs) {
+                const uint32_t f = (uint32_t)__ffs((int)longs) - 1;
+                longs &= longs - 1;
+                const uint32_t flo = __shfl_sync(TS_FULL, lo, f), fso = __shfl_sync(TS_FULL, so, f), fll = __shfl_sync(TS_FULL, ll, f);
+                for (uint32_t k = 16 + lane; k < fll; k += 32) lits[flo + k] = buf[fso + k];
+            }
+            nlit += __shfl_sync(TS_FULL, inc_l, 31);
+            src_pos += __shfl_sync(TS_FULL, inc_s, 31);
+        }
+        const uint32_t ll = bn - anchor;                           // trailing literals
         for (uint32_t k = lane; k < ll; k += 32) lits[nlit + k] = buf[anchor + k];
         nlit += ll;
     }
@@ -285,7 +319,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
     if (nseq > 0) {
         // literals section first (into `out` directly), then the sequences bit stream staged in `buf`
         uint8_t* body = out + 3;
-        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, ht, lane);   // header + payload
+        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, (uint16_t*)ht, lane);   // header + payload
         __syncwarp();
         for (uint32_t i = lane; i < (ZB + ZE_BUF_PAD) / 4; i += 32) ((uint32_t*)buf)[i] = 0;
         __syncwarp();

@@ -1,7 +1,15 @@
-// zstd_huf_enc.cuh — literals section of a compressed block (RFC 8878 §3.1.1.3.1).
+// zstd_huf_enc.cuh — literals section of a compressed block (RFC 8878 §3.1.1.3.1, §4.2): Raw, RLE or
+// Huffman-compressed (4 streams, direct 4-bit weight table).  One warp per block, everything in shared memory:
+//   histogram (shared-memory atomics) -> rank sort of the used symbols -> two-queue Huffman merge on lane 0
+//   (depth limited to 11 by halving counts and rebuilding) -> canonical codes in the order the decoder's table
+//   is filled (weight ascending, symbol ascending) -> the four streams packed by all lanes with a shuffle
+//   suffix-scan of code lengths and atomicOr into a zeroed staging buffer.
+// Blocks whose highest used byte value needs more than 128 listed weights (FSE-compressed weight tables) and
+// blocks that Huffman would not shrink fall back to Raw literals.
 #pragma once
 #include "ts_common.cuh"
 #include "zstd_format.h"
+#include "index_scan.cuh"
 
 namespace ts {
 
@@ -15,12 +23,179 @@ __device__ __forceinline__ uint32_t ze_raw_literals(const uint8_t* __restrict__ 
     for (uint32_t i = lane; i < n; i += 32) body[3 + i] = lits[i];
     return 3 + n;
 }
+__device__ __forceinline__ uint32_t ze_rle_literals(uint8_t v, uint32_t n, uint8_t* body, uint32_t lane) {
+    if (lane == 0) {
+        body[0] = (uint8_t)(1u | (3u << 2) | ((n & 0xf) << 4));
+        body[1] = (uint8_t)(n >> 4);
+        body[2] = (uint8_t)(n >> 12);
+        body[3] = v;
+    }
+    return 4;
+}
 
-// Returns the bytes written at `body`.  `work` is ZB bytes of shared memory, `aux` the (free) hash table area.
+constexpr uint32_t ZE_HUF_MIN = 64;            // below this many literals a table cannot pay for itself
+
+// Returns the bytes written at `body`.  `work`: >= ZB + 160 bytes of shared memory (tree scratch, then the
+// stream staging area); `aux`: 4 KiB of shared memory (histogram + code table).
 __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict__ lits, uint32_t n, uint8_t* body,
-                                                       uint32_t* work, uint16_t* aux, uint32_t lane) {
-    (void)work; (void)aux;
-    return ze_raw_literals(lits, n, body, lane);
+                                                       uint32_t* work, uint16_t* aux16, uint32_t lane) {
+    if (n < ZE_HUF_MIN) return ze_raw_literals(lits, n, body, lane);
+    uint32_t* hist = (uint32_t*)aux16;         // [256]
+    uint32_t* ctab = hist + 256;               // [256] code | len << 16
+    uint32_t* keys = ctab + 256;               // [256] used symbols: count << 8 | symbol
+    uint32_t* sorted = work;                   // [256]
+    uint32_t* nodew = work + 256;              // [512]
+    uint16_t* parent = (uint16_t*)(work + 768);   // [512]
+    uint8_t* depth = (uint8_t*)(work + 1024);  // [512]
+    uint32_t* meta = work + 1200;              // small scalars shared by the warp
+
+    for (uint32_t i = lane; i < 256; i += 32) { hist[i] = 0; ctab[i] = 0; }
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[lits[i]], 1u);
+    __syncwarp();
+
+    // compact the used symbols (8 per lane, ascending symbol order)
+    uint32_t mine = 0;
+    for (uint32_t k = 0; k < 8; k++) mine += hist[lane * 8 + k] ? 1u : 0u;
+    const uint32_t inc = warp_inclusive_scan_u32(mine, lane);
+    const uint32_t m = __shfl_sync(TS_FULL, inc, 31);
+    {
+        uint32_t at = inc - mine;
+        for (uint32_t k = 0; k < 8; k++) { const uint32_t s = lane * 8 + k; if (hist[s]) keys[at++] = (hist[s] << 8) | s; }
+    }
+    __syncwarp();
+    if (m == 1) return ze_rle_literals((uint8_t)(keys[0] & 0xff), n, body, lane);
+    const uint32_t last_sym = keys[m - 1] & 0xff;
+    if (last_sym > 128) return ze_raw_literals(lits, n, body, lane);      // would need FSE-compressed weights
+
+    // ---- code lengths: rebuild with halved counts until the tree is at most 11 deep
+    uint32_t max_len = 0;
+    for (uint32_t round = 0; round < 16; round++) {
+        for (uint32_t e = lane; e < m; e += 32) {                         // rank sort (keys are distinct)
+            const uint32_t key = keys[e];
+            uint32_t r = 0;
+            for (uint32_t j = 0; j < m; j++) r += keys[j] < key ? 1u : 0u;
+            sorted[r] = key;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            for (uint32_t i = 0; i < m; i++) nodew[i] = sorted[i] >> 8;
+            uint32_t li = 0, ii = m, ni = m;
+            for (uint32_t k = 0; k + 1 < m; k++) {
+                uint32_t a, b;
+                if (li < m && (ii >= ni || nodew[li] <= nodew[ii])) a = li++; else a = ii++;
+                if (li < m && (ii >= ni || nodew[li] <= nodew[ii])) b = li++; else b = ii++;
+                nodew[ni] = nodew[a] + nodew[b];
+                parent[a] = (uint16_t)ni; parent[b] = (uint16_t)ni;
+                ni++;
+            }
+            const uint32_t root = 2 * m - 2;
+            depth[root] = 0;
+            uint32_t mx = 0;
+            for (int32_t i = (int32_t)root - 1; i >= 0; i--) {
+                depth[i] = (uint8_t)(depth[parent[i]] + 1);
+                if ((uint32_t)i < m && depth[i] > mx) mx = depth[i];
+            }
+            meta[0] = mx;
+        }
+        __syncwarp();
+        max_len = meta[0];
+        if (max_len <= (uint32_t)zf::HUF_MAX_LOG) break;
+        for (uint32_t e = lane; e < m; e += 32) {                         // flatten the distribution and retry
+            const uint32_t key = keys[e];
+            keys[e] = ((((key >> 8) + 1) >> 1) << 8) | (key & 0xff);
+        }
+        __syncwarp();
+    }
+    if (max_len > (uint32_t)zf::HUF_MAX_LOG) return ze_raw_literals(lits, n, body, lane);
+
+    // ---- canonical codes: weight w = max_len + 1 - len; cells are dealt weight-ascending, symbol-ascending
+    if (lane == 0) {
+        uint32_t cnt[16];
+        for (int w = 0; w < 16; w++) cnt[w] = 0;
+        for (uint32_t i = 0; i < m; i++) cnt[max_len + 1 - depth[i]]++;
+        uint32_t start[16], pos = 0;
+        for (uint32_t w = 1; w <= max_len; w++) { start[w] = pos; pos += cnt[w] << (w - 1); }
+        // sorted[] is ordered by count; symbol order inside a weight class comes from walking symbols ascending
+        for (uint32_t i = 0; i < m; i++) ctab[sorted[i] & 0xff] = (uint32_t)depth[i] << 16;      // park the length
+        uint64_t total_bits = 0;
+        for (uint32_t s = 0; s <= last_sym; s++) {
+            const uint32_t len = ctab[s] >> 16;
+            if (!len) continue;
+            const uint32_t w = max_len + 1 - len;
+            ctab[s] = (start[w] >> (w - 1)) | (len << 16);
+            start[w] += 1u << (w - 1);
+            total_bits += (uint64_t)len * hist[s];
+        }
+        meta[1] = (uint32_t)total_bits;
+    }
+    __syncwarp();
+    const uint32_t nweights = last_sym;                                   // symbols 0 .. last_sym-1 are listed
+    const uint32_t tree_bytes = 1 + (nweights + 1) / 2;
+    const uint32_t est = tree_bytes + 6 + (meta[1] >> 3) + 8;
+    if (est + 5 >= n) return ze_raw_literals(lits, n, body, lane);        // Huffman would not pay
+
+    // ---- the four streams, staged in `work` (cleared first; tree scratch is dead from here on)
+    const uint32_t seg = (n + 3) / 4;
+    __syncwarp();
+    for (uint32_t i = lane; i < (ZB + 128) / 4; i += 32) work[i] = 0;
+    __syncwarp();
+    uint32_t byte_pos = 0;
+    uint32_t ssz[4];
+    for (uint32_t st = 0; st < 4; st++) {
+        const uint32_t s0 = st * seg, s1 = st < 3 ? min(n, s0 + seg) : n;
+        const uint32_t cnt = s1 > s0 ? s1 - s0 : 0;
+        const uint32_t per = (cnt + 31) / 32;
+        const uint32_t a = min(cnt, lane * per), b = min(cnt, a + per);   // this lane's run [a, b) of the stream
+        uint32_t mybits = 0;
+        for (uint32_t i = a; i < b; i++) mybits += ctab[lits[s0 + i]] >> 16;
+        // symbols are written last-to-first: the offset of a run is the number of bits of all LATER runs
+        const uint32_t incb = warp_inclusive_scan_u32(mybits, lane);
+        const uint32_t total = __shfl_sync(TS_FULL, incb, 31);
+        uint32_t off = byte_pos * 8 + (total - incb);
+        for (uint32_t i = b; i > a; i--) {
+            const uint32_t c = ctab[lits[s0 + i - 1]];
+            const uint32_t len = c >> 16, code = c & 0xffff;
+            const uint32_t w = off >> 5, sh = off & 31;
+            atomicOr(&work[w], code << sh);
+            if (sh + len > 32) atomicOr(&work[w + 1], code >> (32 - sh));
+            off += len;
+        }
+        if (lane == 0) {                                                  // end mark
+            const uint32_t o = byte_pos * 8 + total;
+            atomicOr(&work[o >> 5], 1u << (o & 31));
+        }
+        ssz[st] = (total + 1 + 7) >> 3;
+        byte_pos += ssz[st];
+        __syncwarp();
+    }
+    const uint32_t comp = tree_bytes + 6 + byte_pos;
+    const uint32_t hsz = (n < 1024 && comp < 1024) ? 3u : (n < 16384 && comp < 16384) ? 4u : 5u;
+    if (hsz + comp >= 3 + n) return ze_raw_literals(lits, n, body, lane);
+    if (lane == 0) {
+        const uint32_t sf = hsz - 2;                                      // 1, 2, 3: all with four streams
+        uint64_t h;
+        if (hsz == 3) h = 2u | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 14);
+        else if (hsz == 4) h = 2u | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 18);
+        else h = 2u | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 22);
+        for (uint32_t k = 0; k < hsz; k++) body[k] = (uint8_t)(h >> (8 * k));
+        uint8_t* t = body + hsz;
+        t[0] = (uint8_t)(127 + nweights);
+        for (uint32_t i = 0; i < nweights; i += 2) {
+            const uint32_t l0 = ctab[i] >> 16, l1 = i + 1 < nweights ? ctab[i + 1] >> 16 : 0;
+            const uint32_t w0 = l0 ? max_len + 1 - l0 : 0, w1 = l1 ? max_len + 1 - l1 : 0;
+            t[1 + i / 2] = (uint8_t)((w0 << 4) | w1);
+        }
+        uint8_t* j = t + tree_bytes;
+        j[0] = (uint8_t)ssz[0]; j[1] = (uint8_t)(ssz[0] >> 8);
+        j[2] = (uint8_t)ssz[1]; j[3] = (uint8_t)(ssz[1] >> 8);
+        j[4] = (uint8_t)ssz[2]; j[5] = (uint8_t)(ssz[2] >> 8);
+    }
+    uint8_t* sp = body + hsz + tree_bytes + 6;
+    const uint8_t* wb = (const uint8_t*)work;
+    for (uint32_t i = lane; i < byte_pos; i += 32) sp[i] = wb[i];
+    __syncwarp();
+    return hsz + comp;
 }
 
 }  // namespace ts

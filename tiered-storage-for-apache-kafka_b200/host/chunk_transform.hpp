@@ -1,0 +1,408 @@
+// chunk_transform.hpp — host side above the C-ABI: a C++ mirror of the reference's operator surface for this path
+// (the reference is Java and there is no JVM in the build image; the JNI binding of the same C-ABI is in jni/).
+// Same names, argument meaning and error behaviour as
+//   core/M/transform/{BaseTransform,Compression,Encryption}ChunkEnumeration.java, TransformFinisher.java,
+//   core/M/transform/{BaseDetransform,Decryption,Decompression}ChunkEnumeration.java, DetransformFinisher.java,
+//   core/M/manifest/index/{AbstractChunkIndexBuilder,FixedSizeChunkIndexBuilder,VariableSizeChunkIndexBuilder}.java,
+//   core/M/manifest/index/{AbstractChunkIndex,FixedSizeChunkIndex,VariableSizeChunkIndex}.java, core/M/Chunk.java,
+//   core/M/fetch/FetchChunkEnumeration.java
+// (core/M = /root/reference/core/src/main/java/io/aiven/kafka/tieredstorage).
+//
+// Difference that makes it B200-native: the reference pulls ONE chunk through the decorator chain per
+// nextElement(); here the outermost enumeration pulls a BATCH of original chunks from the base enumeration,
+// hands the whole batch to tsgpu_transform / tsgpu_detransform once, and then serves the results one at a time.
+// The decorators only contribute their flag, key material and transformedChunkSize() arithmetic.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <functional>
+#include <istream>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/tsgpu.h"
+
+namespace tieredstorage {
+
+using Bytes = std::vector<uint8_t>;
+struct NoSuchElementException : std::runtime_error { NoSuchElementException() : std::runtime_error("NoSuchElementException") {} };
+struct IllegalArgumentException : std::invalid_argument { using std::invalid_argument::invalid_argument; };
+struct IllegalStateException : std::logic_error { using std::logic_error::logic_error; };
+struct NullPointerException : std::invalid_argument { using std::invalid_argument::invalid_argument; };
+
+// ------------------------------------------------------------------ core/M/Chunk.java:21-36
+struct Chunk {
+    int id, originalPosition, originalSize, transformedPosition, transformedSize;
+    bool operator==(const Chunk& o) const {
+        return id == o.id && originalPosition == o.originalPosition && originalSize == o.originalSize &&
+               transformedPosition == o.transformedPosition && transformedSize == o.transformedSize;
+    }
+    // Chunk.range(): inclusive byte range of the transformed chunk inside the object
+    std::pair<int, int> range() const { return {transformedPosition, transformedPosition + transformedSize - 1}; }
+};
+
+// ------------------------------------------------------------------ AbstractChunkIndex.java:27-152
+class ChunkIndex {
+public:
+    virtual ~ChunkIndex() = default;
+    const std::vector<Chunk>& chunks() const { return chunks_; }
+    // findChunkForOriginalOffset :75-110 — nullopt is the reference's `null`
+    std::optional<Chunk> findChunkForOriginalOffset(int offset) const {
+        if (offset < 0) throw IllegalArgumentException("Offset must be non-negative, " + std::to_string(offset) + " given");
+        if (offset >= originalFileSize) return std::nullopt;
+        int chunkI = 0, op = 0, tp = 0;
+        for (; chunkI < chunkCount; chunkI++) {
+            const long long beyond = (long long)(chunkI + 1) * originalChunkSize;
+            if (offset < beyond) break;
+            op += originalChunkSizeAt(chunkI); tp += transformedChunkSizeAt(chunkI);
+        }
+        return Chunk{chunkI, op, originalChunkSizeAt(chunkI), tp, transformedChunkSizeAt(chunkI)};
+    }
+    // chunksForRange :113-123 (BytesRange is inclusive on both ends)
+    std::vector<Chunk> chunksForRange(int first, int last) const {
+        std::vector<Chunk> r;
+        Chunk cur{};
+        for (long long i = first; i <= last && i < originalFileSize; i += cur.originalSize) {
+            cur = *findChunkForOriginalOffset((int)i);
+            r.push_back(cur);
+        }
+        return r;
+    }
+    virtual std::string toJson() const = 0;
+    const int originalChunkSize, originalFileSize, finalTransformedChunkSize, chunkCount;
+
+protected:
+    ChunkIndex(int ocs, int ofs, int ftcs, int count)
+        : originalChunkSize(checkPositive(ocs, "Original chunk size")), originalFileSize(checkNonNeg(ofs, "Original file size")),
+          finalTransformedChunkSize(checkNonNeg(ftcs, "Final transformed chunk size")), chunkCount(count) {}
+    static int checkNonNeg(int v, const char* name) {
+        if (v < 0) throw IllegalArgumentException(std::string(name) + " must be non-negative, " + std::to_string(v) + " given");
+        return v;
+    }
+    static int checkPositive(int v, const char* name) {
+        if (v <= 0) throw IllegalArgumentException(std::string(name) + " must be positive, " + std::to_string(v) + " given");
+        return v;
+    }
+    int originalChunkSizeAt(int i) const { return i == chunkCount - 1 ? originalFileSize - (chunkCount - 1) * originalChunkSize : originalChunkSize; }
+    virtual int transformedChunkSizeAt(int i) const = 0;
+    void materializeChunks() {       // :52-72
+        chunks_.clear();
+        if (chunkCount == 0) { chunks_.push_back(Chunk{0, 0, 0, 0, 0}); return; }
+        int op = 0, tp = 0;
+        for (int i = 0; i < chunkCount; i++) {
+            Chunk c{i, op, originalChunkSizeAt(i), tp, transformedChunkSizeAt(i)};
+            chunks_.push_back(c);
+            op += c.originalSize; tp += c.transformedSize;
+        }
+    }
+    std::vector<Chunk> chunks_;
+};
+
+inline std::string jsonFromAbi(int ocs, int ofs, int tcs, int ftcs, const std::vector<int32_t>* sizes) {
+    std::vector<char> buf(1024 + (sizes ? sizes->size() * 8 : 0));
+    uint32_t n = (uint32_t)buf.size();
+    int rc = tsgpu_chunk_index_json(ocs, ofs, tcs, ftcs, sizes ? sizes->data() : nullptr, sizes ? (uint32_t)sizes->size() : 0, buf.data(), &n);
+    if (rc) throw IllegalArgumentException(tsgpu_last_error());
+    return std::string(buf.data(), n);
+}
+
+class FixedSizeChunkIndex : public ChunkIndex {       // FixedSizeChunkIndex.java:45-120
+public:
+    FixedSizeChunkIndex(int ocs, int ofs, int tcs, int ftcs)
+        : ChunkIndex(ocs, ofs, ftcs, count(ocs, ofs)), transformedChunkSize(checkNonNeg(tcs, "Transformed chunk size")) { materializeChunks(); }
+    const int transformedChunkSize;
+    std::string toJson() const override { return jsonFromAbi(originalChunkSize, originalFileSize, transformedChunkSize, finalTransformedChunkSize, nullptr); }
+protected:
+    int transformedChunkSizeAt(int i) const override { return i == chunkCount - 1 ? finalTransformedChunkSize : transformedChunkSize; }
+private:
+    static int count(int ocs, int ofs) { checkPositive(ocs, "Original chunk size"); return ofs % ocs == 0 ? ofs / ocs : ofs / ocs + 1; }
+};
+
+class VariableSizeChunkIndex : public ChunkIndex {    // VariableSizeChunkIndex.java:49-110
+public:
+    VariableSizeChunkIndex(int ocs, int ofs, std::vector<int32_t> sizes)
+        : ChunkIndex(ocs, ofs, last(sizes), (int)sizes.size()), transformedChunks(std::move(sizes)) { materializeChunks(); }
+    const std::vector<int32_t> transformedChunks;
+    std::string toJson() const override { return jsonFromAbi(originalChunkSize, originalFileSize, -1, 0, &transformedChunks); }
+protected:
+    int transformedChunkSizeAt(int i) const override { return transformedChunks[i]; }
+private:
+    static int last(const std::vector<int32_t>& s) { if (s.empty()) throw NullPointerException("transformedChunks cannot be null"); return s.back(); }
+};
+
+// ------------------------------------------------------------------ AbstractChunkIndexBuilder.java:19-97
+class AbstractChunkIndexBuilder {
+public:
+    virtual ~AbstractChunkIndexBuilder() = default;
+    void addChunk(int transformedChunkSize) {
+        if (finished) throw IllegalStateException("Cannot add chunk to already finished index");
+        checkSize(transformedChunkSize, "Transformed chunk size");
+        if (remainOfOriginalFileSize() <= originalChunkSize) throw IllegalStateException("This must be final chunk. Call `finish` instead.");
+        addChunk0(transformedChunkSize);
+        chunksAdded += 1;
+    }
+    std::shared_ptr<ChunkIndex> finish(int finalTransformedChunkSize) {
+        if (finished) throw IllegalStateException("Cannot finish already finished index");
+        checkSize(finalTransformedChunkSize, "Transformed chunk size");
+        if (remainOfOriginalFileSize() > originalChunkSize)
+            throw IllegalStateException("This cannot be final chunk: not enough chunks to cover original file. Call `addChunk` instead.");
+        auto r = finish0(finalTransformedChunkSize);
+        chunksAdded += 1; finished = true;
+        return r;
+    }
+protected:
+    AbstractChunkIndexBuilder(int ocs, int ofs) : originalChunkSize(checkSize(ocs, "Original chunk size")), originalFileSize(checkSize(ofs, "Original file size")) {}
+    virtual void addChunk0(int) = 0;
+    virtual std::shared_ptr<ChunkIndex> finish0(int) = 0;
+    static int checkSize(int v, const char* name) {
+        if (v < 0) throw IllegalArgumentException(std::string(name) + " must be non-negative, " + std::to_string(v) + " given");
+        return v;
+    }
+    int remainOfOriginalFileSize() const { return originalFileSize - chunksAdded * originalChunkSize; }
+    const int originalChunkSize, originalFileSize;
+private:
+    int chunksAdded = 0;
+    bool finished = false;
+};
+class FixedSizeChunkIndexBuilder : public AbstractChunkIndexBuilder {     // FixedSizeChunkIndexBuilder.java:19-45
+public:
+    FixedSizeChunkIndexBuilder(int ocs, int ofs, int tcs) : AbstractChunkIndexBuilder(ocs, ofs), transformedChunkSize(checkSize(tcs, "Transformed chunk size")) {}
+protected:
+    void addChunk0(int t) override {
+        if (t != transformedChunkSize)
+            throw IllegalArgumentException("Non-final chunk must be of size " + std::to_string(transformedChunkSize) + ", but " + std::to_string(t) + " given");
+    }
+    std::shared_ptr<ChunkIndex> finish0(int ft) override { return std::make_shared<FixedSizeChunkIndex>(originalChunkSize, originalFileSize, transformedChunkSize, ft); }
+private:
+    const int transformedChunkSize;
+};
+class VariableSizeChunkIndexBuilder : public AbstractChunkIndexBuilder {  // VariableSizeChunkIndexBuilder.java:21-43
+public:
+    VariableSizeChunkIndexBuilder(int ocs, int ofs) : AbstractChunkIndexBuilder(ocs, ofs) {}
+protected:
+    void addChunk0(int t) override { sizes.push_back(t); }
+    std::shared_ptr<ChunkIndex> finish0(int ft) override { sizes.push_back(ft); return std::make_shared<VariableSizeChunkIndex>(originalChunkSize, originalFileSize, sizes); }
+private:
+    std::vector<int32_t> sizes;
+};
+
+// ------------------------------------------------------------------ key material (AesEncryptionProvider.java:52-75)
+struct DataKeyAndAAD { Bytes dataKey /*32*/; Bytes aad; };
+// The reference draws a fresh 12-byte IV per chunk from SecureRandom.getInstanceStrong(); the host supplies it.
+using IvSupplier = std::function<void(uint8_t iv[TSGPU_IV_SIZE])>;
+
+// ------------------------------------------------------------------ TransformChunkEnumeration.java:28-42
+class TransformChunkEnumeration {
+public:
+    virtual ~TransformChunkEnumeration() = default;
+    virtual int originalChunkSize() const = 0;
+    virtual std::optional<int> transformedChunkSize() const = 0;     // nullopt = variable (Java null)
+    virtual bool hasMoreElements() = 0;
+    virtual Bytes nextElement() = 0;
+    // --- batching plumbing (not in the reference)
+    virtual TransformChunkEnumeration* innerEnumeration() { return nullptr; }
+    virtual uint32_t flag() const { return 0; }
+    virtual const DataKeyAndAAD* keyMaterial() const { return nullptr; }
+    virtual const IvSupplier* ivSupplier() const { return nullptr; }
+};
+
+// BaseTransformChunkEnumeration.java:29-98
+class BaseTransformChunkEnumeration : public TransformChunkEnumeration {
+public:
+    BaseTransformChunkEnumeration(std::istream* inputStream, int originalChunkSize) : in(inputStream), ocs(originalChunkSize) {
+        if (!inputStream) throw NullPointerException("inputStream cannot be null");
+        if (originalChunkSize < 0) throw IllegalArgumentException("originalChunkSize must be non-negative, " + std::to_string(originalChunkSize) + " given");
+    }
+    int originalChunkSize() const override { return ocs; }
+    std::optional<int> transformedChunkSize() const override { return ocs; }
+    bool hasMoreElements() override { fill(); return !chunk->empty(); }
+    Bytes nextElement() override {
+        fill();
+        if (chunk->empty()) throw NoSuchElementException();
+        Bytes r = std::move(*chunk); chunk.reset(); return r;
+    }
+private:
+    void fill() {
+        if (chunk) return;
+        chunk = Bytes();
+        if (ocs != 0) { chunk->resize((size_t)ocs); in->read((char*)chunk->data(), ocs); chunk->resize((size_t)in->gcount()); }
+        else { char buf[65536]; while (in->read(buf, sizeof buf) || in->gcount()) chunk->insert(chunk->end(), buf, buf + in->gcount()); }
+    }
+    std::istream* in; int ocs; std::optional<Bytes> chunk;
+};
+
+// Shared batching core of the decorators.
+class GpuBatchingEnumeration : public TransformChunkEnumeration {
+public:
+    bool hasMoreElements() override { return !ready.empty() || base()->hasMoreElements(); }
+    Bytes nextElement() override {
+        if (ready.empty()) pump();
+        if (ready.empty()) throw NoSuchElementException();
+        Bytes r = std::move(ready.front()); ready.erase(ready.begin()); return r;
+    }
+    TransformChunkEnumeration* innerEnumeration() override { return inner; }
+    int originalChunkSize() const override { return inner->originalChunkSize(); }
+protected:
+    GpuBatchingEnumeration(tsgpu_ctx* c, TransformChunkEnumeration* in, uint32_t batchChunks) : ctx(c), inner(in), batch(batchChunks ? batchChunks : 1) {
+        if (!in) throw NullPointerException("inner cannot be null");
+    }
+    tsgpu_ctx* ctx; TransformChunkEnumeration* inner; uint32_t batch;
+private:
+    TransformChunkEnumeration* base() { TransformChunkEnumeration* e = this; while (e->innerEnumeration()) e = e->innerEnumeration(); return e; }
+    void pump() {
+        uint32_t flags = 0; const DataKeyAndAAD* km = nullptr; const IvSupplier* ivs = nullptr;
+        for (TransformChunkEnumeration* e = this; e; e = e->innerEnumeration()) {
+            flags |= e->flag();
+            if (e->keyMaterial()) km = e->keyMaterial();
+            if (e->ivSupplier()) ivs = e->ivSupplier();
+        }
+        TransformChunkEnumeration* b = base();
+        Bytes src; std::vector<uint32_t> lens;
+        while (lens.size() < batch && b->hasMoreElements()) { Bytes c = b->nextElement(); lens.push_back((uint32_t)c.size()); src.insert(src.end(), c.begin(), c.end()); }
+        if (lens.empty()) return;
+        const uint32_t cs = lens.front();                  // every non-final chunk has the base chunk size
+        Bytes iv(lens.size() * TSGPU_IV_SIZE);
+        if (flags & TSGPU_FLAG_AES) for (size_t i = 0; i < lens.size(); i++) (*ivs)(iv.data() + i * TSGPU_IV_SIZE);
+        Bytes dst((size_t)tsgpu_transform_bound(flags, src.size(), cs) + 64);
+        std::vector<uint32_t> sizes(lens.size());
+        uint32_t n = (uint32_t)sizes.size();
+        int rc = tsgpu_transform(ctx, flags, src.data(), src.size(), cs, km ? km->dataKey.data() : nullptr, km ? km->aad.data() : nullptr,
+                                 km ? (uint32_t)km->aad.size() : 0, iv.data(), dst.data(), dst.size(), sizes.data(), &n);
+        if (rc) throw std::runtime_error(tsgpu_last_error());      // RuntimeException in the reference
+        size_t pos = 0;
+        for (uint32_t i = 0; i < n; i++) { ready.emplace_back(dst.begin() + pos, dst.begin() + pos + sizes[i]); pos += sizes[i]; }
+    }
+    std::vector<Bytes> ready;
+};
+
+// CompressionChunkEnumeration.java:26-63
+class CompressionChunkEnumeration : public GpuBatchingEnumeration {
+public:
+    CompressionChunkEnumeration(tsgpu_ctx* ctx, TransformChunkEnumeration* inner, uint32_t batchChunks = 32) : GpuBatchingEnumeration(ctx, inner, batchChunks) {}
+    std::optional<int> transformedChunkSize() const override { return std::nullopt; }   // variable
+    uint32_t flag() const override { return TSGPU_FLAG_ZSTD; }
+};
+
+// EncryptionChunkEnumeration.java:30-85
+class EncryptionChunkEnumeration : public GpuBatchingEnumeration {
+public:
+    EncryptionChunkEnumeration(tsgpu_ctx* ctx, TransformChunkEnumeration* inner, DataKeyAndAAD keyAndAad, IvSupplier ivSupplier, uint32_t batchChunks = 32)
+        : GpuBatchingEnumeration(ctx, inner, batchChunks), km(std::move(keyAndAad)), ivs(std::move(ivSupplier)) {
+        if (!ivs) throw NullPointerException("cipherSupplier cannot be null");
+        if (km.dataKey.size() != 32) throw IllegalArgumentException("dataKey must be 32 bytes");
+        auto in = inner->transformedChunkSize();
+        if (in) tcs = TSGPU_IV_SIZE + *in + TSGPU_TAG_SIZE;          // encryptedChunkSize :82-84 (ivSize + getOutputSize(n))
+    }
+    std::optional<int> transformedChunkSize() const override { return tcs; }
+    uint32_t flag() const override { return TSGPU_FLAG_AES; }
+    const DataKeyAndAAD* keyMaterial() const override { return &km; }
+    const IvSupplier* ivSupplier() const override { return &ivs; }
+private:
+    DataKeyAndAAD km; IvSupplier ivs; std::optional<int> tcs;
+};
+
+// TransformFinisher.java:47-199 (without the rate limiter, which wraps the resulting stream in the reference)
+class TransformFinisher {
+public:
+    TransformFinisher(TransformChunkEnumeration* inner, int originalFileSize, bool chunkingEnabled = true) : inner(inner), originalFileSize(originalFileSize) {
+        if (!inner) throw NullPointerException("inner cannot be null");
+        if (originalFileSize < 0) throw IllegalArgumentException("originalFileSize must be non-negative, " + std::to_string(originalFileSize) + " given");
+        const int ocs = chunkingEnabled ? inner->originalChunkSize() : originalFileSize;
+        auto t = inner->transformedChunkSize();
+        if (!t) builder = std::make_unique<VariableSizeChunkIndexBuilder>(ocs, originalFileSize);
+        else builder = std::make_unique<FixedSizeChunkIndexBuilder>(ocs, originalFileSize, *t);
+    }
+    bool hasMoreElements() { return inner->hasMoreElements(); }
+    Bytes nextElement() {                                    // :101-110
+        Bytes chunk = inner->nextElement();
+        if (hasMoreElements()) builder->addChunk((int)chunk.size());
+        else index = builder->finish((int)chunk.size());
+        return chunk;
+    }
+    std::shared_ptr<ChunkIndex> chunkIndex() {               // :112-132
+        if (!index) {
+            if (dynamic_cast<BaseTransformChunkEnumeration*>(inner)) {
+                const int cs = *inner->transformedChunkSize();
+                int size = originalFileSize;
+                while (size > cs) { builder->addChunk(cs); size -= cs; }
+                index = builder->finish(size);
+            } else throw IllegalStateException("Chunk index was not built, was finisher used?");
+        }
+        return index;
+    }
+    Bytes readAll() { Bytes all; while (hasMoreElements()) { Bytes c = nextElement(); all.insert(all.end(), c.begin(), c.end()); } return all; }   // SequenceInputStream
+private:
+    TransformChunkEnumeration* inner; int originalFileSize;
+    std::unique_ptr<AbstractChunkIndexBuilder> builder; std::shared_ptr<ChunkIndex> index;
+};
+
+// ------------------------------------------------------------------ detransform side
+// DefaultChunkManager.getChunk (DefaultChunkManager.java:50-70) generalised to a list of consecutive chunks:
+// BaseDetransform (cut at transformedSize; "Stream has fewer bytes than expected") -> Decryption -> Decompression.
+class DetransformChunkEnumeration {
+public:
+    DetransformChunkEnumeration(tsgpu_ctx* ctx, std::istream* inputStream, std::vector<Chunk> chunks, bool decompress,
+                                const DataKeyAndAAD* decryptWith, uint32_t maxOriginalChunkSize, uint32_t batchChunks = 32)
+        : ctx(ctx), in(inputStream), chunks(std::move(chunks)), flags((decompress ? TSGPU_FLAG_ZSTD : 0) | (decryptWith ? TSGPU_FLAG_AES : 0)),
+          ocs(maxOriginalChunkSize), batch(batchChunks ? batchChunks : 1) {
+        if (!inputStream) throw NullPointerException("inputStream cannot be null");
+        if (decryptWith) km = *decryptWith;
+    }
+    bool hasMoreElements() { return !ready.empty() || next < chunks.size(); }
+    Bytes nextElement() {
+        if (ready.empty()) pump();
+        if (ready.empty()) throw NoSuchElementException();
+        Bytes r = std::move(ready.front()); ready.erase(ready.begin()); return r;
+    }
+private:
+    void pump() {
+        std::vector<uint32_t> ts;
+        Bytes src;
+        while (ts.size() < batch && next < chunks.size()) {
+            const uint32_t t = (uint32_t)chunks[next++].transformedSize;
+            const size_t at = src.size();
+            src.resize(at + t);
+            in->read((char*)src.data() + at, t);
+            if ((uint32_t)in->gcount() < t) throw std::runtime_error("Stream has fewer bytes than expected");
+            ts.push_back(t);
+        }
+        if (ts.empty()) return;
+        Bytes dst((size_t)ocs * ts.size() + 64);
+        std::vector<uint32_t> osz(ts.size());
+        int rc = tsgpu_detransform(ctx, flags, src.data(), src.size(), ts.data(), (uint32_t)ts.size(), km.dataKey.empty() ? nullptr : km.dataKey.data(),
+                                   km.aad.data(), (uint32_t)km.aad.size(), dst.data(), dst.size(), osz.data());
+        if (rc) throw std::runtime_error(tsgpu_last_error());
+        size_t pos = 0;
+        for (size_t i = 0; i < ts.size(); i++) { ready.emplace_back(dst.begin() + pos, dst.begin() + pos + osz[i]); pos += osz[i]; }
+    }
+    tsgpu_ctx* ctx; std::istream* in; std::vector<Chunk> chunks; uint32_t flags; uint32_t ocs; uint32_t batch; size_t next = 0;
+    DataKeyAndAAD km; std::vector<Bytes> ready;
+};
+
+// FetchChunkEnumeration.java:54-138: which chunks cover [from, to] and how much of the first / last one to keep.
+struct FetchPiece { int chunkId, skip, take; };
+inline std::vector<FetchPiece> fetchPlan(const ChunkIndex& index, int from, int to) {
+    if (to < from) throw IllegalArgumentException("range cannot be empty");
+    auto first = index.findChunkForOriginalOffset(from);
+    if (!first) throw IllegalArgumentException("Invalid start position " + std::to_string(from) + " in segment path");
+    auto lastOpt = index.findChunkForOriginalOffset(to);
+    const Chunk last = lastOpt ? *lastOpt : index.chunks().back();
+    std::vector<FetchPiece> plan;
+    for (int id = first->id; id <= last.id; id++) {
+        const Chunk& c = index.chunks()[id];
+        int skip = 0, take = c.originalSize;
+        const bool atFirst = id == first->id, atLast = id == last.id;
+        if (atFirst && atLast) { skip = from - c.originalPosition; take = std::min(c.originalSize - skip, to - from + 1); }
+        else {
+            if (atFirst) { skip = from - c.originalPosition; take = c.originalSize - skip; }
+            if (atLast) take = std::min(c.originalSize, to - c.originalPosition + 1);
+        }
+        plan.push_back({id, skip, take});
+    }
+    return plan;
+}
+
+}  // namespace tieredstorage
