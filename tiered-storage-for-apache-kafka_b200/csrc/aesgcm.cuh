@@ -7,11 +7,11 @@
 // 128-bit tag, per-segment AAD).  Algorithm: NIST SP 800-38D.
 //
 // Decomposition (one launch handles a whole batch of chunks):
-//   gcm_key_setup_kernel   once per key: H = E_K(0), H^1..H^256, H^(2^k), and the 64 KiB Shoup table of H^256
-//   gcm_main_kernel        grid (ranges, chunks); each CTA takes a 256 KiB range of one chunk: 256 threads
+//   gcm_key_setup_kernel   once per key: H = E_K(0), H^1..H^512, H^(2^k), and the 64 KiB Shoup table of H^512
+//   gcm_main_kernel        grid (ranges, chunks); each CTA takes a 256 KiB range of one chunk: 512 threads
 //                          stride through its 16-byte blocks (coalesced 128-bit loads/stores), AES-CTR via a
-//                          bank-conflict-free Te0 table replicated per lane in shared memory, GHASH as a
-//                          256-way interleaved Horner scheme whose fixed multiplier H^256 is the TMA-staged
+//                          bank-conflict-free Te0/Te2 tables replicated per lane in shared memory, GHASH as a
+//                          512-way interleaved Horner scheme whose fixed multiplier H^512 is the TMA-staged
 //                          shared-memory table; emits one 16-byte partial per range
 //   gcm_finalize_kernel    one warp per chunk: combines the range partials with H-powers, adds AAD and the
 //                          length block, computes/verifies the tag, writes IV and TAG, sizes and status
@@ -22,11 +22,14 @@
 
 namespace ts {
 
-constexpr int GH_T = 256;                        // GHASH interleave = threads per CTA of gcm_main_kernel
+constexpr int GH_T = 512;                        // GHASH interleave = threads per CTA of gcm_main_kernel
 constexpr uint32_t GH_RANGE_BLOCKS = 16384;      // 16-byte blocks per CTA range (256 KiB)
 constexpr int GH_NSQ = 28;                       // H^(2^k), k < 28  (chunk.size < 2^30 => m+1 < 2^27)
 constexpr uint32_t GCM_IV = 12, GCM_TAG = 16;
-constexpr uint32_t GCM_SMEM_TE = 256 * 32 * 4;   // 32 KiB: Te0 replicated so lane l only touches bank l
+// Round tables: one 256-byte row per S-box input; words 0-31 = Te0[x] replicated per lane, words 32-63 = Te2[x]
+// (= Te0 rotated by 16 bits) replicated per lane.  Lane l only ever touches banks l (conflict-free), and the row
+// stride of 256 bytes lets ONE PRMT build the shared-memory offset (state byte -> bits 8-15, lane offset -> bits 0-7).
+constexpr uint32_t GCM_SMEM_TE = 256 * 64 * 4;   // 64 KiB
 constexpr uint32_t GCM_SMEM_HTAB = 16 * 256 * 16;  // 64 KiB
 constexpr uint32_t GCM_SMEM_BYTES = GCM_SMEM_TE + GCM_SMEM_HTAB;
 
@@ -97,35 +100,38 @@ __device__ __forceinline__ uint4 gf_mul_tab(const uint4* __restrict__ tab, uint4
 }
 
 // ------------------------------------------------------------------------------------------ AES-256
-// One block through the lane-replicated Te0 table: te_lane points at &te[lane], entry x lives at te_lane[x*32].
-#define TS_TE(x, sh) te_lane[(((x) >> (sh)) & 0xffu) << 5]
-__device__ __forceinline__ void aes256_encrypt_te(const Aes256RoundKeys& rk, const uint32_t* __restrict__ te_lane,
+// One block through the lane-replicated tables.  off0 = 4*lane selects the Te0 half of a row, off2 = 128 + 4*lane
+// the Te2 half; SEL(k) makes PRMT produce (byte k of x) << 8 | lane offset, i.e. the byte offset of the lookup.
+// Per column and round: 4 PRMT (addresses) + 4 LDS + 1 PRMT (one shared 8-bit rotation) + 3 XOR-class ops:
+//   t = Te0[a] ^ Te1[b] ^ Te2[c] ^ Te3[d] ^ rk = Te0[a] ^ Te2[c] ^ rk ^ rotl8(Te0[b] ^ Te2[d]).
+#define TS_SEL(k) (0x5504u | ((k) << 4))
+#define TS_T0(x, k) (*(const uint32_t*)(te + __byte_perm((x), off0, TS_SEL(k))))
+#define TS_T2(x, k) (*(const uint32_t*)(te + __byte_perm((x), off2, TS_SEL(k))))
+__device__ __forceinline__ void aes256_encrypt_te(const Aes256RoundKeys& rk, const uint8_t* __restrict__ te, uint32_t off0, uint32_t off2,
                                                   uint32_t& s0, uint32_t& s1, uint32_t& s2, uint32_t& s3) {
     s0 ^= rk.w[0]; s1 ^= rk.w[1]; s2 ^= rk.w[2]; s3 ^= rk.w[3];
 #pragma unroll
     for (int r = 1; r < 14; r++) {
-        uint32_t t0 = TS_TE(s0, 0) ^ __byte_perm(TS_TE(s1, 8), 0, 0x2103) ^ __byte_perm(TS_TE(s2, 16), 0, 0x1032) ^
-                      __byte_perm(TS_TE(s3, 24), 0, 0x0321) ^ rk.w[4 * r];
-        uint32_t t1 = TS_TE(s1, 0) ^ __byte_perm(TS_TE(s2, 8), 0, 0x2103) ^ __byte_perm(TS_TE(s3, 16), 0, 0x1032) ^
-                      __byte_perm(TS_TE(s0, 24), 0, 0x0321) ^ rk.w[4 * r + 1];
-        uint32_t t2 = TS_TE(s2, 0) ^ __byte_perm(TS_TE(s3, 8), 0, 0x2103) ^ __byte_perm(TS_TE(s0, 16), 0, 0x1032) ^
-                      __byte_perm(TS_TE(s1, 24), 0, 0x0321) ^ rk.w[4 * r + 2];
-        uint32_t t3 = TS_TE(s3, 0) ^ __byte_perm(TS_TE(s0, 8), 0, 0x2103) ^ __byte_perm(TS_TE(s1, 16), 0, 0x1032) ^
-                      __byte_perm(TS_TE(s2, 24), 0, 0x0321) ^ rk.w[4 * r + 3];
+        const uint32_t t0 = TS_T0(s0, 0u) ^ TS_T2(s2, 2u) ^ rk.w[4 * r]     ^ __byte_perm(TS_T0(s1, 1u) ^ TS_T2(s3, 3u), 0, 0x2103);
+        const uint32_t t1 = TS_T0(s1, 0u) ^ TS_T2(s3, 2u) ^ rk.w[4 * r + 1] ^ __byte_perm(TS_T0(s2, 1u) ^ TS_T2(s0, 3u), 0, 0x2103);
+        const uint32_t t2 = TS_T0(s2, 0u) ^ TS_T2(s0, 2u) ^ rk.w[4 * r + 2] ^ __byte_perm(TS_T0(s3, 1u) ^ TS_T2(s1, 3u), 0, 0x2103);
+        const uint32_t t3 = TS_T0(s3, 0u) ^ TS_T2(s1, 2u) ^ rk.w[4 * r + 3] ^ __byte_perm(TS_T0(s0, 1u) ^ TS_T2(s2, 3u), 0, 0x2103);
         s0 = t0; s1 = t1; s2 = t2; s3 = t3;
     }
-    // final round: SubBytes + ShiftRows only; S[x] is byte 1 (and 2) of Te0[x]
-    uint32_t a0 = TS_TE(s0, 0), a1 = TS_TE(s1, 8), a2 = TS_TE(s2, 16), a3 = TS_TE(s3, 24);
-    uint32_t b0 = TS_TE(s1, 0), b1 = TS_TE(s2, 8), b2 = TS_TE(s3, 16), b3 = TS_TE(s0, 24);
-    uint32_t c0 = TS_TE(s2, 0), c1 = TS_TE(s3, 8), c2 = TS_TE(s0, 16), c3 = TS_TE(s1, 24);
-    uint32_t d0 = TS_TE(s3, 0), d1 = TS_TE(s0, 8), d2 = TS_TE(s1, 16), d3 = TS_TE(s2, 24);
+    // final round: SubBytes + ShiftRows only; S[x] is byte 1 of Te0[x]
+    const uint32_t a0 = TS_T0(s0, 0u), a1 = TS_T0(s1, 1u), a2 = TS_T0(s2, 2u), a3 = TS_T0(s3, 3u);
+    const uint32_t b0 = TS_T0(s1, 0u), b1 = TS_T0(s2, 1u), b2 = TS_T0(s3, 2u), b3 = TS_T0(s0, 3u);
+    const uint32_t c0 = TS_T0(s2, 0u), c1 = TS_T0(s3, 1u), c2 = TS_T0(s0, 2u), c3 = TS_T0(s1, 3u);
+    const uint32_t d0 = TS_T0(s3, 0u), d1 = TS_T0(s0, 1u), d2 = TS_T0(s1, 2u), d3 = TS_T0(s2, 3u);
     // byte k of the result = byte 1 of the k-th lookup
     s0 = __byte_perm(__byte_perm(a0, a1, 0x0051), __byte_perm(a2, a3, 0x0051), 0x5410) ^ rk.w[56];
     s1 = __byte_perm(__byte_perm(b0, b1, 0x0051), __byte_perm(b2, b3, 0x0051), 0x5410) ^ rk.w[57];
     s2 = __byte_perm(__byte_perm(c0, c1, 0x0051), __byte_perm(c2, c3, 0x0051), 0x5410) ^ rk.w[58];
     s3 = __byte_perm(__byte_perm(d0, d1, 0x0051), __byte_perm(d2, d3, 0x0051), 0x5410) ^ rk.w[59];
 }
-#undef TS_TE
+#undef TS_T0
+#undef TS_T2
+#undef TS_SEL
 
 // Byte-oriented AES for the O(1)-per-chunk blocks (H = E_K(0), E_K(J0)); constant-memory S-box.
 __device__ TS_NOINLINE uint4 aes256_encrypt_slow(const Aes256RoundKeys& rk, uint4 in) {
@@ -154,7 +160,7 @@ __device__ TS_NOINLINE uint4 aes256_encrypt_slow(const Aes256RoundKeys& rk, uint
 }
 
 // ------------------------------------------------------------------------------------------ key set-up
-__global__ void __launch_bounds__(256) gcm_key_setup_kernel(const __grid_constant__ Aes256RoundKeys rk, GcmKeyCtx* kc) {
+__global__ void __launch_bounds__(GH_T) gcm_key_setup_kernel(const __grid_constant__ Aes256RoundKeys rk, GcmKeyCtx* kc) {
     __shared__ uint4 V[128];
     const int t = threadIdx.x;
     if (t == 0) {
@@ -204,7 +210,7 @@ __device__ __forceinline__ uint32_t ld_le32_bytes(const uint8_t* p) {
 
 // ------------------------------------------------------------------------------------------ main kernel
 template <bool ENC>
-__global__ void __launch_bounds__(GH_T, 2)
+__global__ void __launch_bounds__(GH_T, 1)
 gcm_main_kernel(const __grid_constant__ Aes256RoundKeys rk, const GcmKeyCtx* __restrict__ kc,
                 const __grid_constant__ GcmBatch B) {
     TS_DYN_SMEM(smem);
@@ -214,7 +220,7 @@ gcm_main_kernel(const __grid_constant__ Aes256RoundKeys rk, const GcmKeyCtx* __r
 #else
     uint64_t bar_dummy = 0; uint64_t* barp = &bar_dummy;
 #endif
-    uint32_t* te = (uint32_t*)smem;
+    const uint8_t* te = smem;
     uint4* htab = (uint4*)(smem + GCM_SMEM_TE);
 
     const uint32_t chunk = blockIdx.y, range = blockIdx.x, tid = threadIdx.x;
@@ -229,7 +235,10 @@ gcm_main_kernel(const __grid_constant__ Aes256RoundKeys rk, const GcmKeyCtx* __r
     if (tid == 0) mbar_init(&bar, 1);
     uint64_t* barp = &bar;
 #endif
-    for (uint32_t i = tid; i < 256 * 32; i += GH_T) te[i] = g_aes_tables.te0[i >> 5];
+    for (uint32_t i = tid; i < 256 * 64; i += GH_T) {
+        const uint32_t t0 = g_aes_tables.te0[i >> 6];
+        ((uint32_t*)smem)[i] = (i & 32) ? __byte_perm(t0, 0, 0x1032) : t0;       // second half of a row: Te2 = rotl16(Te0)
+    }
     __syncthreads();
     block_bulk_load(htab, kc->htab, GCM_SMEM_HTAB, barp, 0);   // TMA bulk copy of the H^256 table
     __syncthreads();
@@ -241,13 +250,13 @@ gcm_main_kernel(const __grid_constant__ Aes256RoundKeys rk, const GcmKeyCtx* __r
     uint8_t* dst = ENC ? out + GCM_IV : out;
     const uint32_t iv0 = ld_le32_bytes(ivp), iv1 = ld_le32_bytes(ivp + 4), iv2 = ld_le32_bytes(ivp + 8);
     const bool aligned = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0;
-    const uint32_t* te_lane = te + (tid & 31);
+    const uint32_t off0 = (tid & 31) * 4, off2 = 128 + off0;
 
     uint4 acc = make_uint4(0, 0, 0, 0);
     uint32_t last = 0xffffffffu;
     for (uint32_t i = b0 + tid; i < b1; i += GH_T) {
         uint32_t s0 = iv0, s1 = iv1, s2 = iv2, s3 = bswap32(i + 2);
-        aes256_encrypt_te(rk, te_lane, s0, s1, s2, s3);
+        aes256_encrypt_te(rk, te, off0, off2, s0, s1, s2, s3);
         const size_t off = (size_t)i << 4;
         const bool full = off + 16 <= n;
         uint4 d;

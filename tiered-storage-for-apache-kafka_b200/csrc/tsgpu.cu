@@ -43,7 +43,7 @@ static inline uint64_t frame_bound(uint64_t n) { return n + (n >> 8) + 64; }   /
 // ------------------------------------------------------------------------------------------ context
 namespace {
 
-constexpr int NSLOT = 2;
+constexpr int NSLOT = 4;
 constexpr uint32_t MAX_AAD = 4096;
 
 struct Desc {            // device-side descriptor block of one work slot (all arrays sized for max_batch)
@@ -56,7 +56,7 @@ struct Work {
     int device = 0;
     rt::stream_t stream{};
     rt::event_t ev_sizes{}, ev_done{};
-    bool busy = false;
+    bool busy = false, ready = false;
     uint8_t* d_orig = nullptr;     // max_batch * chunk_cap
     uint8_t* d_frames = nullptr;   // max_batch * frame_stride        (zstd frames, 16-byte aligned slots)
     uint8_t* d_xf = nullptr;       // max_batch * slot_stride         (transformed slots)
@@ -94,7 +94,7 @@ static void carve_desc(uint8_t* base, uint32_t nb, Desc& d, size_t* total) {
 }
 
 static int work_init(tsgpu_ctx* c, Work& w, int device) {
-    w.device = device;
+    w.device = device; w.ready = true;
     RT(rt::set_device(device));
     RT(rt::stream_create(&w.stream));
     RT(rt::event_create(&w.ev_sizes));
@@ -120,6 +120,7 @@ static int work_init(tsgpu_ctx* c, Work& w, int device) {
 }
 
 static void work_free(Work& w) {
+    if (!w.stream && !w.d_orig) return;                 // never initialised
     rt::set_device(w.device);
     if (w.stream) rt::stream_sync(w.stream);
     rt::free_device(w.d_orig); rt::free_device(w.d_frames); rt::free_device(w.d_xf);
@@ -167,7 +168,7 @@ extern "C" int tsgpu_create(const int* device_ids, int n_devices, uint32_t max_c
     c->lanes.resize(ids.size());
     for (size_t l = 0; l < ids.size(); l++) {
         c->lanes[l].device = ids[l];
-        for (int s = 0; s < NSLOT; s++) {
+        for (int s = 0; s < 1; s++) {                   // further slots are allocated on first use (work_ready)
             int rc = work_init(c, c->lanes[l].w[s], ids[l]);
             if (rc) { tsgpu_destroy(c); return rc; }
         }
@@ -206,7 +207,7 @@ static int gcm_stage(tsgpu_ctx* c, Work& w, rt::stream_t st, const Aes256RoundKe
                      const uint8_t* d_ivs, const uint8_t* d_aad, uint32_t aad_len, uint32_t* d_status,
                      uint32_t n_chunks, uint32_t max_payload, uint4* d_partials, uint32_t max_ranges) {
     if (!key_ready) {
-        TS_LAUNCH_P(c->prof, "gcm_key_setup", gcm_key_setup_kernel, dim3(1), dim3(256), 0, st, rk, w.d_keyctx);
+        TS_LAUNCH_P(c->prof, "gcm_key_setup", gcm_key_setup_kernel, dim3(1), dim3(GH_T), 0, st, rk, w.d_keyctx);
         CHECK_LAUNCH("gcm_key_setup_kernel");
     }
     GcmBatch B;
@@ -342,6 +343,7 @@ extern "C" int tsgpu_transform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src,
             if (e) { rc = fail(TSGPU_E_CUDA, "event_sync: %s", e); break; }
         }
         uint32_t c0 = b * c->max_batch, nb = std::min(c->max_batch, n - c0);
+        if (!work_of(b).ready) { rc = work_init(c, work_of(b), c->lanes[b % c->lanes.size()].device); if (rc) break; }
         rc = transform_issue(c, work_of(b), flags, src, src_len, cs, c0, nb, rk, aad, aad_len, ivs, inflight[b]);
     }
     while (rc == TSGPU_OK && drained < nbatches) rc = drain(drained++);
@@ -476,6 +478,7 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
             if (e) { rc = fail(TSGPU_E_CUDA, "event_sync: %s", e); break; }
         }
         uint32_t c0 = b * c->max_batch, nb = std::min(c->max_batch, n_chunks - c0);
+        if (!work_of(b).ready) { rc = work_init(c, work_of(b), c->lanes[b % c->lanes.size()].device); if (rc) break; }
         rc = detransform_issue(c, work_of(b), flags, src + in_pos[b], transformed_sizes, c0, nb, rk, aad, aad_len, inflight[b]);
     }
     while (rc == TSGPU_OK && drained < nbatches) rc = drain(drained++);
