@@ -1,6 +1,6 @@
 # quick perf probe: correctness subset + kernel breakdown (no e2e / cpu arms)
 set -x
-python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "aes or full_pipeline or grid" 2>&1 | tail -4
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "zstd or full_pipeline or grid or ranged" 2>&1 | tail -4
 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])

@@ -34,7 +34,7 @@ constexpr int ZE_WPB = 1;                      // warps (= blocks in flight) per
 constexpr uint32_t ZE_MAXSEQ = ZB / 8;         // sequences kept per block; beyond that the rest goes out as literals
 constexpr uint32_t ZE_LANE_EXT = 60;           // bytes a lane extends its own match beyond the first 4
 constexpr uint32_t ZE_BUF_PAD = 160;
-constexpr uint32_t ZE_SLOT = ZB + 64;          // per-block output slot: 3-byte header + payload (<= ZB when compressed)
+constexpr uint32_t ZE_SLOT = ZB + 512;         // per-block output slot: 3-byte header + payload (< ZB once accepted; table descriptions are written before that is known)
 constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 4 + 3 * 32 + 3 * 32 * 2 + 3 * 32;   // buf, ht, codes, stv, stn
 constexpr uint32_t ZE_SMEM_WARP_AL = (ZE_SMEM_WARP + 15) & ~15u;
 
@@ -98,23 +98,64 @@ static inline unsigned __match_any_sync(unsigned, unsigned v) {
 namespace ts {
 
 // ------------------------------------------------------------------------------------------ block compressor
-// Encodes the sequences section with the predefined FSE tables into the zeroed word buffer `bits`.
-// Returns the number of bytes of the bit stream (uniform across the warp).  N >= 1.
 struct ZeFseShared {      // per-CTA copy of the predefined encoding tables
     zf::PredefinedCTables t;
 };
 
-__device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict__ seqs, uint32_t N, uint32_t* bits,
+}  // namespace ts
+#include "zstd_fse_enc.cuh"
+namespace ts {
+
+// Encodes the sequences section (everything after the Number_of_Sequences field): the modes byte and table
+// descriptions go straight to `hdr_out` (global), the bit stream is staged in the word buffer `bits` (shared).
+// Returns the bit-stream bytes; *desc_bytes = 1 (modes byte) + table descriptions.  Warp-uniform, N >= 1.
+__device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict__ seqs, uint32_t N, uint32_t* bits, ZeCTab* ct,
                                                         uint8_t* codes /*[3][32]*/, uint16_t* stv /*[3][32]*/, uint8_t* stn /*[3][32]*/,
-                                                        const ZeFseShared* fs, uint32_t lane) {
+                                                        const ZeFseShared* fs, uint8_t* hdr_out, uint32_t* desc_bytes, uint32_t lane) {
+    // ---- pass 1: code histograms
+    for (uint32_t i = lane; i < ZE_NSYM_LL + ZE_NSYM_ML + ZE_NSYM_OF; i += 32) ct->cnt[i] = 0;
+    __syncwarp();
+    uint2 pre = lane < N ? seqs[lane] : make_uint2(0, 0);
+    for (uint32_t t0 = 0; t0 < N; t0 += 32) {
+        const uint32_t j = t0 + lane;
+        const uint2 s = pre;
+        if (j + 32 < N) pre = seqs[j + 32];                  // next tile in flight while this one is counted
+        if (j < N) {
+            atomicAdd(&ct->cnt[ze_ll_code(s.x & 0xffff)], 1u);
+            atomicAdd(&ct->cnt[ZE_NSYM_LL + ze_ml_code(s.x >> 16)], 1u);
+            atomicAdd(&ct->cnt[ZE_NSYM_LL + ZE_NSYM_ML + (uint32_t)zf::highbit32(s.y + 3)], 1u);
+        }
+    }
+    __syncwarp();
+    // ---- tables (descriptions in stream order LL, OF, ML); `bits` doubles as scratch until it is cleared
+    ZeKind kll, kof, kml;
+    uint8_t* desc = hdr_out + 1;
+    uint32_t dn = ze_build_kind(ct->cnt, ZE_NSYM_LL, N, zf::LL_MAX_LOG, zf::LL_DEFAULT_LOG, fs->t.ll.state, fs->t.ll.sym,
+                                ct->st_ll, ct->sy_ll, (uint8_t*)bits, desc, &kll, lane);
+    dn += ze_build_kind(ct->cnt + ZE_NSYM_LL + ZE_NSYM_ML, ZE_NSYM_OF, N, zf::OF_MAX_LOG, zf::OF_DEFAULT_LOG, fs->t.of.state, fs->t.of.sym,
+                        ct->st_of, ct->sy_of, (uint8_t*)bits, desc + dn, &kof, lane);
+    dn += ze_build_kind(ct->cnt + ZE_NSYM_LL, ZE_NSYM_ML, N, zf::ML_MAX_LOG, zf::ML_DEFAULT_LOG, fs->t.ml.state, fs->t.ml.sym,
+                        ct->st_ml, ct->sy_ml, (uint8_t*)bits, desc + dn, &kml, lane);
+    if (lane == 0) hdr_out[0] = (uint8_t)((kll.mode << 6) | (kof.mode << 4) | (kml.mode << 2));
+    *desc_bytes = 1 + dn;
+    __syncwarp();
+    for (uint32_t i = lane; i < (ZB + ZE_BUF_PAD) / 4; i += 32) bits[i] = 0;
+    __syncwarp();
+
+    // ---- pass 2: encode
     uint32_t bitpos = 0;
     uint32_t state = 0;                              // lanes 0..2: OF, ML, LL chains
+    const uint16_t* st_tab = lane == 0 ? ct->st_of : lane == 1 ? ct->st_ml : ct->st_ll;
+    const zf::FseCSym* sy = lane == 0 ? ct->sy_of : lane == 1 ? ct->sy_ml : ct->sy_ll;
+    const bool rle = (lane == 0 ? kof.mode : lane == 1 ? kml.mode : kll.mode) == 1;
+    pre = lane < N ? seqs[N - 1 - lane] : make_uint2(0, 0);
     for (uint32_t t0 = 0; t0 < N; t0 += 32) {
         const uint32_t j = t0 + lane;                // stream order: j = 0 is the LAST sequence
         const bool have = j < N;
         uint32_t ll = 0, mlb = 0, offb = 0, llc = 0, mlc = 0, ofc = 0;
+        const uint2 s = pre;
+        if (j + 32 < N) pre = seqs[N - 1 - (j + 32)];
         if (have) {
-            const uint2 s = seqs[N - 1 - j];
             ll = s.x & 0xffff; mlb = s.x >> 16; offb = s.y + 3;       // mlb = matchLength - 3, offb = offset + 3 (no repcodes)
             llc = ze_ll_code(ll); mlc = ze_ml_code(mlb); ofc = (uint32_t)zf::highbit32(offb);
             codes[lane] = (uint8_t)ofc; codes[32 + lane] = (uint8_t)mlc; codes[64 + lane] = (uint8_t)llc;
@@ -122,20 +163,24 @@ __device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict_
         __syncwarp();
         if (lane < 3) {
             const uint32_t cnt = min(32u, N - t0);
-            const uint16_t* st_tab = lane == 0 ? fs->t.of.state : lane == 1 ? fs->t.ml.state : fs->t.ll.state;
-            const zf::FseCSym* sy = lane == 0 ? fs->t.of.sym : lane == 1 ? fs->t.ml.sym : fs->t.ll.sym;
-            for (uint32_t i = 0; i < cnt; i++) {
-                const zf::FseCSym c = sy[codes[lane * 32 + i]];
-                if (t0 + i == 0) {                   // FSE_initCState2
-                    const uint32_t nb = (uint32_t)(c.delta_nb_bits + (1 << 15)) >> 16;
-                    const uint32_t v = (nb << 16) - (uint32_t)c.delta_nb_bits;
-                    state = st_tab[(int32_t)(v >> nb) + c.delta_find_state];
-                    stv[lane * 32 + i] = 0; stn[lane * 32 + i] = 0;
-                } else {                             // FSE_encodeSymbol
-                    const uint32_t nb = (state + (uint32_t)c.delta_nb_bits) >> 16;
-                    stv[lane * 32 + i] = (uint16_t)(state & ((1u << nb) - 1));
-                    stn[lane * 32 + i] = (uint8_t)nb;
-                    state = st_tab[(int32_t)(state >> nb) + c.delta_find_state];
+            if (rle) {
+                for (uint32_t i = 0; i < cnt; i++) { stv[lane * 32 + i] = 0; stn[lane * 32 + i] = 0; }
+            } else {
+                zf::FseCSym c = sy[codes[lane * 32]];
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const zf::FseCSym cn = sy[codes[lane * 32 + min(i + 1, cnt - 1)]];    // prefetch: independent of the state chain
+                    if (t0 + i == 0) {               // FSE_initCState2
+                        const uint32_t nb = (uint32_t)(c.delta_nb_bits + (1 << 15)) >> 16;
+                        const uint32_t v = (nb << 16) - (uint32_t)c.delta_nb_bits;
+                        state = st_tab[(int32_t)(v >> nb) + c.delta_find_state];
+                        stv[lane * 32 + i] = 0; stn[lane * 32 + i] = 0;
+                    } else {                         // FSE_encodeSymbol
+                        const uint32_t nb = (state + (uint32_t)c.delta_nb_bits) >> 16;
+                        stv[lane * 32 + i] = (uint16_t)(state & ((1u << nb) - 1));
+                        stn[lane * 32 + i] = (uint8_t)nb;
+                        state = st_tab[(int32_t)(state >> nb) + c.delta_find_state];
+                    }
+                    c = cn;
                 }
             }
         }
@@ -160,25 +205,22 @@ __device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict_
     const uint32_t st_of = __shfl_sync(TS_FULL, state, 0), st_ml = __shfl_sync(TS_FULL, state, 1),
                    st_ll = __shfl_sync(TS_FULL, state, 2);
     if (lane == 0) {
-        uint64_t f = st_ml & ((1u << zf::ML_DEFAULT_LOG) - 1);
-        uint32_t nb = zf::ML_DEFAULT_LOG;
-        f |= (uint64_t)(st_of & ((1u << zf::OF_DEFAULT_LOG) - 1)) << nb; nb += zf::OF_DEFAULT_LOG;
-        f |= (uint64_t)(st_ll & ((1u << zf::LL_DEFAULT_LOG) - 1)) << nb; nb += zf::LL_DEFAULT_LOG;
+        uint64_t f = st_ml & ((1u << kml.log) - 1);
+        uint32_t nb = kml.log;
+        f |= (uint64_t)(st_of & ((1u << kof.log) - 1)) << nb; nb += kof.log;
+        f |= (uint64_t)(st_ll & ((1u << kll.log) - 1)) << nb; nb += kll.log;
         f |= 1ull << nb; nb += 1;
         ze_put_bits(bits, bitpos, f, nb);
     }
-    bitpos += zf::ML_DEFAULT_LOG + zf::OF_DEFAULT_LOG + zf::LL_DEFAULT_LOG + 1;
+    bitpos += kml.log + kof.log + kll.log + 1;
     __syncwarp();
     return (bitpos + 7) >> 3;
 }
 
 __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __grid_constant__ ZstdEncArgs A) {
     TS_DYN_SMEM(smem);
-    __shared__ ZeFseShared fs;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < sizeof(ZeFseShared) / 4; i += blockDim.x)
-        ((uint32_t*)&fs)[i] = ((const uint32_t*)&g_pre_ctables)[i];
-    __syncthreads();
+    const ZeFseShared& fs = *(const ZeFseShared*)&g_pre_ctables;   // predefined tables stay in constant memory
 
     const uint32_t chunk = blockIdx.y;
     const uint32_t blk = blockIdx.x * ZE_WPB + warp;
@@ -289,10 +331,13 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
     uint32_t nlit = 0;
     {
         uint32_t src_pos = 0;
+        uint2 pre = lane < nseq ? seqs[lane] : make_uint2(0, 0);
         for (uint32_t t0 = 0; t0 < nseq; t0 += 32) {
             const uint32_t i = t0 + lane;
             uint32_t ll = 0, ml = 0;
-            if (i < nseq) { const uint2 sq = seqs[i]; ll = sq.x & 0xffff; ml = (sq.x >> 16) + 3; }
+            const uint2 sq = pre;
+            if (i + 32 < nseq) pre = seqs[i + 32];
+            if (i < nseq) { ll = sq.x & 0xffff; ml = (sq.x >> 16) + 3; }
             const uint32_t inc_l = warp_inclusive_scan_u32(ll, lane), inc_s = warp_inclusive_scan_u32(ll + ml, lane);
             const uint32_t lo = nlit + inc_l - ll, so = src_pos + inc_s - ll - ml;
             const uint32_t quick = min(ll, 16u);
@@ -321,20 +366,18 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
         uint8_t* body = out + 3;
         const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, (uint16_t*)ht, lane);   // header + payload
         __syncwarp();
-        for (uint32_t i = lane; i < (ZB + ZE_BUF_PAD) / 4; i += 32) ((uint32_t*)buf)[i] = 0;
-        __syncwarp();
-        const uint32_t sbytes = ze_encode_sequences(seqs, nseq, (uint32_t*)buf, codes, stv, stn, &fs, lane);
         const uint32_t shdr = nseq < 128 ? 1u : (nseq < 0x7f00 ? 2u : 3u);
-        const uint32_t total = lit_bytes + shdr + 1 + sbytes;
+        uint8_t* sp = body + lit_bytes;
+        uint32_t desc_bytes = 0;
+        const uint32_t sbytes = ze_encode_sequences(seqs, nseq, (uint32_t*)buf, (ZeCTab*)ht, codes, stv, stn, &fs, sp + shdr, &desc_bytes, lane);
+        const uint32_t total = lit_bytes + shdr + desc_bytes + sbytes;
         if (total < bn) {
-            uint8_t* sp = body + lit_bytes;
             if (lane == 0) {
                 if (shdr == 1) sp[0] = (uint8_t)nseq;
                 else if (shdr == 2) { sp[0] = (uint8_t)((nseq >> 8) + 0x80); sp[1] = (uint8_t)nseq; }
                 else { sp[0] = 0xff; sp[1] = (uint8_t)(nseq - 0x7f00); sp[2] = (uint8_t)((nseq - 0x7f00) >> 8); }
-                sp[shdr] = 0;                                      // LL/OF/ML all Predefined_Mode
             }
-            for (uint32_t i = lane; i < sbytes; i += 32) sp[shdr + 1 + i] = buf[i];
+            for (uint32_t i = lane; i < sbytes; i += 32) sp[shdr + desc_bytes + i] = buf[i];
             payload = total;
         }
     }
