@@ -76,20 +76,28 @@ __device__ __forceinline__ uint64_t zd_ld64(const uint8_t* p) {          // unal
     const uint32_t w2 = w[2];
     return (uint64_t)__funnelshift_r(w1, w2, sh) << 32 | __funnelshift_r(w0, w1, sh);
 }
-// Backward stream (FSE / Huffman): `bits` unread bits remain below the end mark.
-struct ZdBack { const uint8_t* p; int32_t bits; };
+// Backward stream (FSE / Huffman): `bits` unread bits remain below the end mark.  A 64-bit window of the stream
+// (bits [cbase, cbase+64), cbase a multiple of 8) is cached in registers and refilled about once per 57 bits.
+struct ZdBack { const uint8_t* p; int32_t bits; uint64_t C; int32_t cbase; };
 __device__ __forceinline__ bool zd_back_init(ZdBack& b, const uint8_t* p, uint32_t size) {
+    b.p = p; b.bits = 0; b.C = 0; b.cbase = 0x3fffffff;
     if (size == 0) return false;
     const uint32_t last = p[size - 1];
     if (last == 0) return false;
-    b.p = p; b.bits = (int32_t)(size - 1) * 8 + zf::highbit32(last);
+    b.bits = (int32_t)(size - 1) * 8 + zf::highbit32(last);
     return true;
 }
 // peek nb (<= 32) bits below the cursor without consuming; zero-extends past the start of the stream
-__device__ __forceinline__ uint32_t zd_back_peek(const ZdBack& b, uint32_t nb) {
+__device__ __forceinline__ uint32_t zd_back_peek(ZdBack& b, uint32_t nb) {
     if (nb == 0) return 0;
     const int32_t lo = b.bits - (int32_t)nb;
-    if (lo >= 0) return (uint32_t)(zd_ld64(b.p + (lo >> 3)) >> (lo & 7)) & (uint32_t)((1ull << nb) - 1);
+    if (lo >= 0) {
+        if (lo < b.cbase || b.bits > b.cbase + 64) {
+            b.cbase = max(0, ((b.bits + 7) & ~7) - 64);
+            b.C = zd_ld64(b.p + (b.cbase >> 3));
+        }
+        return (uint32_t)(b.C >> (lo - b.cbase)) & (uint32_t)((1ull << nb) - 1);
+    }
     if (b.bits <= 0) return 0;
     const uint32_t have = (uint32_t)b.bits;
     const uint32_t v = (uint32_t)zd_ld64(b.p) & (uint32_t)((1ull << have) - 1);
@@ -390,7 +398,7 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
 
     // ---- sequences: lane 0 decodes 32 at a time, the warp executes them
     uint32_t op = 0, lp = 0;                            // output / literal cursors (uniform)
-    ZdBack br; br.p = bs; br.bits = 0;
+    ZdBack br; br.p = bs; br.bits = 0; br.C = 0; br.cbase = 0x3fffffff;
     uint32_t st_ll = 0, st_of = 0, st_ml = 0;
     if (nseq) {
         if (lane == 0) {
@@ -439,30 +447,73 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
         }
         __syncwarp();
         if (cx->err) return 0;
-        for (uint32_t i = 0; i < cnt; i++) {
-            const uint32_t ll = cx->s_ll[i], ml = cx->s_ml[i], off = cx->s_off[i];
-            if (lp + ll > regen || (uint64_t)op + ll + ml > limit || (uint64_t)off > hist + op + ll) {
-                if (lane == 0) cx->err = ((uint64_t)off > hist + op + ll && fast_nonfirst) ? 1 : -1;
+        // ---- execute the batch: lane i owns sequence i.  Output/literal positions come from shuffle prefix sums;
+        // literal runs are independent; a match may start once its source range lies inside the completed prefix
+        // (multi-round resolution: far matches of a batch all copy at once, so their memory latency overlaps).
+        {
+            const bool mine = lane < cnt;
+            const uint32_t ll = mine ? cx->s_ll[lane] : 0, ml = mine ? cx->s_ml[lane] : 0, off = mine ? cx->s_off[lane] : 1;
+            const uint32_t inc_o = warp_inclusive_scan_u32(ll + ml, lane), inc_l = warp_inclusive_scan_u32(ll, lane);
+            const uint32_t tot_o = __shfl_sync(TS_FULL, inc_o, 31), tot_l = __shfl_sync(TS_FULL, inc_l, 31);
+            const uint32_t o_start = op + inc_o - ll - ml, l_start = lp + inc_l - ll, m_start = o_start + ll;
+            const bool bad_off = mine && (uint64_t)off > hist + m_start;
+            const uint32_t any_bad = __ballot_sync(TS_FULL, bad_off);
+            if (lp + tot_l > regen || (uint64_t)op + tot_o > limit || any_bad) {
+                if (lane == 0) cx->err = (any_bad && fast_nonfirst && lp + tot_l <= regen && (uint64_t)op + tot_o <= limit) ? 1 : -1;
                 __syncwarp();
                 return 0;
             }
-            if (rle_lit < 0x100) { for (uint32_t k = lane; k < ll; k += 32) dst[op + k] = (uint8_t)rle_lit; }
-            else { for (uint32_t k = lane; k < ll; k += 32) dst[op + k] = lit[lp + k]; }
-            op += ll; lp += ll;
-            __syncwarp();                                // the match may start inside the literals just written
-            uint8_t* d = dst + op;
-            const uint8_t* m = d - off;
-            if (off >= 32) {
-                for (uint32_t k0 = 0; k0 < ml; k0 += 32) {
-                    const uint32_t k = k0 + lane;
-                    if (k < ml) d[k] = m[k];
-                    if (off < ml) __syncwarp();          // later strides may read what this one wrote
+            // literals: short runs by their own lane, long runs by the whole warp
+            {
+                const uint32_t quick = min(ll, 32u);
+                if (rle_lit < 0x100) { for (uint32_t k = 0; k < quick; k++) dst[o_start + k] = (uint8_t)rle_lit; }
+                else { for (uint32_t k = 0; k < quick; k++) dst[o_start + k] = lit[l_start + k]; }
+                uint32_t longs = __ballot_sync(TS_FULL, ll > 32);
+                while (longs) {
+                    const uint32_t f = (uint32_t)__ffs((int)longs) - 1;
+                    longs &= longs - 1;
+                    const uint32_t fo = __shfl_sync(TS_FULL, o_start, f), fl = __shfl_sync(TS_FULL, l_start, f), fn = __shfl_sync(TS_FULL, ll, f);
+                    if (rle_lit < 0x100) { for (uint32_t k = 32 + lane; k < fn; k += 32) dst[fo + k] = (uint8_t)rle_lit; }
+                    else { for (uint32_t k = 32 + lane; k < fn; k += 32) dst[fo + k] = lit[fl + k]; }
                 }
-            } else {
-                for (uint32_t k = lane; k < ml; k += 32) d[k] = m[k % off];   // periodic source entirely before d
             }
-            op += ml;
             __syncwarp();
+            // matches
+            bool done = !mine || ml == 0;
+            const int64_t src_end = (int64_t)m_start - (int64_t)off + (int64_t)ml;      // relative to dst
+            while (true) {
+                const uint32_t pending = __ballot_sync(TS_FULL, !done);
+                if (!pending) break;
+                const uint32_t first = (uint32_t)__ffs((int)pending) - 1;
+                const uint32_t frontier = __shfl_sync(TS_FULL, m_start, first);
+                const bool ready = !done && (lane == first || src_end <= (int64_t)frontier);
+                uint8_t* d = dst + m_start;
+                const uint8_t* m = d - off;
+                if (ready && ml <= 64) {
+                    for (uint32_t k = 0; k < ml; k++) d[k] = m[k];                       // byte-serial: overlap (off < ml) is fine
+                    done = true;
+                }
+                uint32_t big = __ballot_sync(TS_FULL, ready && ml > 64);
+                while (big) {                                                            // long matches: 32 lanes per match
+                    const uint32_t f = (uint32_t)__ffs((int)big) - 1;
+                    big &= big - 1;
+                    const uint32_t fm = __shfl_sync(TS_FULL, m_start, f), fl = __shfl_sync(TS_FULL, ml, f), fo = __shfl_sync(TS_FULL, off, f);
+                    uint8_t* dd = dst + fm;
+                    const uint8_t* mm = dd - fo;
+                    if (fo >= 32) {
+                        for (uint32_t k0 = 0; k0 < fl; k0 += 32) {
+                            const uint32_t k = k0 + lane;
+                            if (k < fl) dd[k] = mm[k];
+                            if (fo < fl) __syncwarp();                                   // later strides may read what this one wrote
+                        }
+                    } else {
+                        for (uint32_t k = lane; k < fl; k += 32) dd[k] = mm[k % fo];     // periodic source entirely before dd
+                    }
+                    if (lane == f) done = true;
+                }
+                __syncwarp();
+            }
+            op += tot_o; lp += tot_l;
         }
     }
     // ---- trailing literals
@@ -539,13 +590,18 @@ __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------ kernel 2: per-block fast path
-__global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_blocks_kernel(const __grid_constant__ ZstdDecArgs A) {
+// The block's output is assembled in shared memory (matches then read shared memory instead of paying an L2 round
+// trip per dependent copy) and flushed to HBM once, coalesced.
+constexpr int ZD_WPB_FAST = 1;
+constexpr uint32_t ZD_FAST_WARP_BYTES = (uint32_t)((sizeof(ZdWarpCtx) + 15) & ~15u) + ZB;
+__global__ void __launch_bounds__(ZD_WPB_FAST * 32) zstd_dec_blocks_kernel(const __grid_constant__ ZstdDecArgs A) {
     TS_DYN_SMEM(smem);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.y, b = blockIdx.x * ZD_WPB + warp;
+    const uint32_t chunk = blockIdx.y, b = blockIdx.x * ZD_WPB_FAST + warp;
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
     if (!info[2] || info[3] == 2 || b >= info[1]) return;
-    ZdWarpCtx* cx = (ZdWarpCtx*)(smem + (size_t)warp * sizeof(ZdWarpCtx));
+    ZdWarpCtx* cx = (ZdWarpCtx*)(smem + (size_t)warp * ZD_FAST_WARP_BYTES);
+    uint8_t* obuf = (uint8_t*)cx + ((sizeof(ZdWarpCtx) + 15) & ~15u);
     const uint32_t fcs = info[0];
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t n = A.in_len[chunk];
@@ -568,7 +624,16 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_blocks_kernel(const __gr
         else { const uint8_t v = p[pos + 3]; for (uint32_t k = lane; k < bsz; k += 32) dst[k] = v; produced = bsz; }
     } else {
         uint8_t* litbuf = A.lits_fast + ((size_t)chunk * A.blocks_per_chunk + b) * (ZB + 64);
-        produced = zd_compressed_block(p + pos + 3, bsz, dst, 0, expect, cx, litbuf, ZB, b != 0, lane);
+        produced = zd_compressed_block(p + pos + 3, bsz, obuf, 0, expect, cx, litbuf, ZB, b != 0, lane);
+        __syncwarp();
+        if (cx->err == 0 && produced == expect) {        // flush: 128-bit stores when the destination allows
+            if ((((uintptr_t)dst) & 15) == 0) {
+                for (uint32_t k = lane * 16; k + 16 <= produced; k += 512) *(uint4*)(dst + k) = *(const uint4*)(obuf + k);
+                for (uint32_t k = (produced & ~15u) + lane; k < produced; k += 32) dst[k] = obuf[k];
+            } else {
+                for (uint32_t k = lane; k < produced; k += 32) dst[k] = obuf[k];
+            }
+        }
     }
     __syncwarp();
     if (lane == 0 && (cx->err != 0 || produced != expect)) atomicOr(&info[3], 1u);   // let the general path decide
@@ -650,7 +715,7 @@ constexpr uint32_t ZD_SMEM_BYTES = ZD_WPB * sizeof(ZdWarpCtx);
 inline const char* zstd_kernels_configure() {
     const char* e;
     if ((e = rt::allow_smem(zstd_enc_blocks_kernel, ZE_SMEM_BYTES))) return e;
-    if ((e = rt::allow_smem(zstd_dec_blocks_kernel, ZD_SMEM_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_dec_blocks_kernel, ZD_WPB_FAST * ZD_FAST_WARP_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_frames_kernel, ZD_SMEM_BYTES))) return e;
     return nullptr;
 }
@@ -677,8 +742,8 @@ inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8
         if ((e = rt::d2d(d_out_off, s.pos_tmp, 8ull * n_chunks, st))) { g_zstd_err = e; return -7; }
     }
     const uint32_t bpc = (chunk_cap + ZB - 1) / ZB;
-    TS_LAUNCH_P(prof, "zstd_dec_blocks", zstd_dec_blocks_kernel, dim3((bpc + ZD_WPB - 1) / ZD_WPB, n_chunks), dim3(ZD_WPB * 32),
-                ZD_SMEM_BYTES, st, A);
+    TS_LAUNCH_P(prof, "zstd_dec_blocks", zstd_dec_blocks_kernel, dim3((bpc + ZD_WPB_FAST - 1) / ZD_WPB_FAST, n_chunks), dim3(ZD_WPB_FAST * 32),
+                ZD_WPB_FAST * ZD_FAST_WARP_BYTES, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     TS_LAUNCH_P(prof, "zstd_dec_frames", zstd_dec_frames_kernel, dim3((n_chunks + ZD_WPB - 1) / ZD_WPB), dim3(ZD_WPB * 32),
                 ZD_SMEM_BYTES, st, A);

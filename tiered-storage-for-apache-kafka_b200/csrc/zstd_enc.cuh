@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
     // handful of instructions per taken match; sequences are then written by their own lanes in parallel and
     // literals are gathered in one pass afterwards.
     uint32_t anchor = 0, cur = 0, nseq = 0;
-    while (cur + 4 <= bn && nseq < ZE_MAXSEQ) {
+    while (cur + 4 <= bn && nseq + 8 <= ZE_MAXSEQ) {                // a step adds at most 8 sequences (min match 4)
         const uint32_t p = cur + lane;
         const bool valid = p + 4 <= bn;
         const uint32_t v = ld_u32_unaligned(buf + p);
@@ -282,9 +282,9 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
             len = min(len, lim);
         }
         const uint32_t mask = __ballot_sync(TS_FULL, ok);
-        uint32_t taken = 0, pos = 0, budget = ZE_MAXSEQ - nseq;
-        while (pos < 32 && budget) {
-            const uint32_t m2 = (mask >> pos) << pos;
+        uint32_t taken = 0, pos = 0;
+        while (pos < 32) {
+            const uint32_t m2 = mask & (0xffffffffu << pos);
             if (!m2) break;
             const uint32_t f = (uint32_t)__ffs((int)m2) - 1;
             uint32_t L = __shfl_sync(TS_FULL, len, f);
@@ -310,7 +310,6 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
             }
             taken |= 1u << f;
             pos = f + L;
-            budget--;
         }
         if (taken) {
             const uint32_t my_end = p + len;                       // meaningful on taken lanes
