@@ -39,6 +39,11 @@ struct ZdWarpCtx {                        // per-warp shared-memory working set 
     uint8_t symbol_of[512];
     uint16_t next[64];
     int16_t norm[64];
+    int16_t norm3[3][64];                 // FSE_Compressed tables waiting for the warp-parallel build
+    uint32_t pend_log[3], pend_nsym[3];
+    uint32_t cum[65];
+    uint16_t hstart[256];                 // first table cell of each Huffman symbol (filled by all lanes)
+    uint32_t huf_nw;
     uint8_t weights[256];
     zf::FseDEntry wt[1 << zf::HUFW_MAX_LOG];
     uint32_t rank_start[16];
@@ -220,13 +225,23 @@ __device__ TS_NOINLINE uint32_t zd_read_huf_table(const uint8_t* src, uint32_t s
     for (uint32_t s = 0; s < nw; s++) {
         const uint32_t w = W[s];
         if (!w) continue;
-        const uint32_t len = 1u << (w - 1), at = cx->rank_start[w];
-        const uint16_t e = (uint16_t)(s | ((max_bits + 1 - w) << 8));
-        for (uint32_t k = 0; k < len; k++) cx->huf[at + k] = e;
-        cx->rank_start[w] = at + len;
+        cx->hstart[s] = (uint16_t)cx->rank_start[w];
+        cx->rank_start[w] += 1u << (w - 1);
     }
-    cx->huf_log = max_bits; cx->huf_valid = 1;
+    cx->huf_log = max_bits; cx->huf_valid = 1; cx->huf_nw = nw;
     return used;
+}
+// All lanes: fill the decoding table from the per-symbol start cells computed above.
+__device__ __forceinline__ void zd_fill_huf_warp(ZdWarpCtx* cx, uint32_t lane) {
+    const uint32_t nw = cx->huf_nw, max_bits = cx->huf_log;
+    for (uint32_t s = 0; s < nw; s++) {
+        const uint32_t w = cx->weights[s];
+        if (!w) continue;
+        const uint32_t len = 1u << (w - 1), at = cx->hstart[s];
+        const uint16_t e = (uint16_t)(s | ((max_bits + 1 - w) << 8));
+        for (uint32_t k = lane; k < len; k += 32) cx->huf[at + k] = e;
+    }
+    __syncwarp();
 }
 
 // One Huffman stream: `count` symbols from src[0..size) into dst.  Any lane; returns false on corruption.
@@ -244,7 +259,49 @@ __device__ __forceinline__ bool zd_huf_stream(const uint16_t* __restrict__ huf, 
 }
 
 // Sequence table of one kind according to its compression mode.  Lane 0.  Returns bytes consumed, -1 on error.
-__device__ TS_NOINLINE int32_t zd_seq_table(uint32_t mode, int kind, const uint8_t* src, uint32_t size, ZdWarpCtx* cx, bool fast_nonfirst) {
+// Warp-parallel build of a sequence decoding table whose distribution has no "less than one" symbols (what this
+// library's writer emits): the spread then has the closed form pos(i) = i*step & mask, a cell's symbol is found by
+// binary search in the cumulative counts, and cells of a symbol are numbered in position order with match_any.
+__device__ __forceinline__ void zd_build_dtable_warp(int kind, ZdWarpCtx* cx, uint32_t lane) {
+    zf::FseDEntry* T = kind == 0 ? cx->ll : kind == 1 ? cx->of : cx->ml;
+    const int16_t* nm = cx->norm3[kind];
+    const uint32_t log = cx->pend_log[kind], nsym = cx->pend_nsym[kind];
+    const uint32_t size = 1u << log, mask = size - 1, step = (size >> 1) + (size >> 3) + 3;
+    const uint32_t p0 = lane < nsym ? (uint32_t)nm[lane] : 0u, p1 = lane + 32 < nsym ? (uint32_t)nm[lane + 32] : 0u;
+    const uint32_t inc0 = warp_inclusive_scan_u32(p0, lane);
+    const uint32_t inc1 = warp_inclusive_scan_u32(p1, lane) + __shfl_sync(TS_FULL, inc0, 31);
+    cx->cum[lane] = inc0 - p0; cx->cum[32 + lane] = inc1 - p1;
+    if (lane == 0) cx->cum[64] = size;
+    cx->next[lane] = (uint16_t)p0; cx->next[32 + lane] = (uint16_t)p1;
+    __syncwarp();
+    for (uint32_t i = lane; i < size; i += 32) {
+        uint32_t lo = 0, hi = 64;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (cx->cum[mid] <= i) lo = mid; else hi = mid; }
+        cx->symbol_of[(i * step) & mask] = (uint8_t)lo;
+    }
+    __syncwarp();
+    for (uint32_t u0 = 0; u0 < size; u0 += 32) {
+        const uint32_t u = u0 + lane;
+        const uint32_t sym = cx->symbol_of[u];
+        const uint32_t same = __match_any_sync(TS_FULL, sym);
+        const uint32_t rank = (uint32_t)__popc(same & ((1u << lane) - 1));
+        const uint32_t base = cx->next[sym];
+        const uint32_t ns = base + rank;
+        const int nb = (int)log - zf::highbit32(ns);
+        zf::FseDEntry e;
+        e.nb_bits = (uint8_t)nb;
+        e.next_base = (uint16_t)((ns << nb) - size);
+        if (kind == 0) { e.nb_extra = g_seq_tables.ll_bits[sym]; e.base = g_seq_tables.ll_base[sym]; }
+        else if (kind == 2) { e.nb_extra = g_seq_tables.ml_bits[sym]; e.base = g_seq_tables.ml_base[sym]; }
+        else { e.nb_extra = (uint8_t)sym; e.base = 1u << sym; }
+        T[u] = e;
+        __syncwarp();
+        if (rank == 0) cx->next[sym] = (uint16_t)(base + (uint32_t)__popc(same));
+        __syncwarp();
+    }
+}
+
+__device__ TS_NOINLINE int32_t zd_seq_table(uint32_t mode, int kind, const uint8_t* src, uint32_t size, ZdWarpCtx* cx, bool fast_nonfirst, uint32_t* pending) {
     zf::FseDEntry* T = kind == 0 ? cx->ll : kind == 1 ? cx->of : cx->ml;
     uint32_t* logp = kind == 0 ? &cx->ll_log : kind == 1 ? &cx->of_log : &cx->ml_log;
     uint32_t* validp = kind == 0 ? &cx->ll_valid : kind == 1 ? &cx->of_valid : &cx->ml_valid;
@@ -266,9 +323,13 @@ __device__ TS_NOINLINE int32_t zd_seq_table(uint32_t mode, int kind, const uint8
     }
     if (mode == 2) {                                    // FSE_Compressed_Mode
         uint32_t lg; int ns;
-        const uint32_t h = zd_read_ncount(src, size, cx->norm, max_sym, max_log, &lg, &ns);
+        int16_t* nm = cx->norm3[kind];
+        const uint32_t h = zd_read_ncount(src, size, nm, max_sym, max_log, &lg, &ns);
         if (!h) return -1;
-        zf::fse_build_dtable(cx->norm, ns, (int)lg, kind, g_seq_tables, T, cx->symbol_of, cx->next);
+        bool low = false;
+        for (int q = 0; q < ns; q++) low |= nm[q] < 0;
+        if (low) zf::fse_build_dtable(nm, ns, (int)lg, kind, g_seq_tables, T, cx->symbol_of, cx->next);   // libzstd-style table: serial
+        else { cx->pend_log[kind] = lg; cx->pend_nsym[kind] = (uint32_t)ns; *pending |= 1u << kind; }  // built by all lanes later
         *logp = lg; *validp = 1;
         return (int32_t)h;
     }
@@ -327,6 +388,7 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
     if (ltype == 0) lit = blk + lhs;
     else if (ltype == 1) rle_lit = blk[lhs];
     else {
+        if (ltype == 2) zd_fill_huf_warp(cx, lane);
         const uint8_t* hsrc = blk + lhs + tree;
         const uint32_t hsize = lcomp - tree;
         bool ok = true;
@@ -371,7 +433,7 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
                 if (nseq == 255) { if (ssize < 3) break; nseq = sp[1] + ((uint32_t)sp[2] << 8) + 0x7f00; hs = 3; }
                 else { if (ssize < 2) break; nseq = ((nseq - 128) << 8) + sp[1]; hs = 2; }
             }
-            uint32_t pos = hs;
+            uint32_t pos = hs, pend = 0;
             if (nseq) {
                 if (ssize < hs + 1) break;
                 const uint32_t modes = sp[hs];
@@ -380,12 +442,12 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
                 bool bad = false;
                 const uint32_t m3[3] = { modes >> 6, (modes >> 4) & 3, (modes >> 2) & 3 };   // LL, OF, ML
                 for (int k = 0; k < 3 && !bad; k++) {
-                    const int32_t used = zd_seq_table(m3[k], k, sp + pos, ssize - pos, cx, fast_nonfirst);
+                    const int32_t used = zd_seq_table(m3[k], k, sp + pos, ssize - pos, cx, fast_nonfirst, &pend);
                     if (used < 0) bad = true; else pos += (uint32_t)used;
                 }
                 if (bad || pos > ssize) break;
             }
-            t[1] = nseq; t[2] = pos;
+            t[1] = nseq; t[2] = pos; t[3] = pend;
             t[0] = 1;
         } while (false);
     }
@@ -393,6 +455,11 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
     if (!cx->tmp[0]) { if (lane == 0 && cx->err == 0) cx->err = -1; __syncwarp(); return 0; }
     if (cx->err) return 0;
     const uint32_t nseq = cx->tmp[1];
+    {
+        const uint32_t pend = cx->tmp[3];
+        for (int k = 0; k < 3; k++) if (pend & (1u << k)) zd_build_dtable_warp(k, cx, lane);
+        __syncwarp();
+    }
     const uint8_t* bs = sp + cx->tmp[2];
     const uint32_t bs_size = ssize - cx->tmp[2];
 
@@ -418,10 +485,42 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
             uint32_t r0 = cx->rep[0], r1 = cx->rep[1], r2 = cx->rep[2];
             for (uint32_t i = 0; i < cnt; i++) {
                 const zf::FseDEntry eo = cx->of[st_of], em = cx->ml[st_ml], el = cx->ll[st_ll];
-                // extra bits: offset, match length, literal length (in this order)
-                uint32_t ofv = eo.base + (eo.nb_extra ? zd_back_read(br, eo.nb_extra) : 0);
-                const uint32_t ml = em.base + (em.nb_extra ? zd_back_read(br, em.nb_extra) : 0);
-                const uint32_t ll = el.base + (el.nb_extra ? zd_back_read(br, el.nb_extra) : 0);
+                // Bits of one sequence, first read first: offset extra, match-length extra, literal-length extra, then
+                // (unless it is the last sequence) the LL, ML, OF state updates.  All six widths are known from the three
+                // table entries, so the fields are cut out of ONE cached 64-bit window instead of six dependent reads.
+                const bool upd = s0 + i + 1 < nseq;
+                const uint32_t u_ll = upd ? el.nb_bits : 0u, u_ml = upd ? em.nb_bits : 0u, u_of = upd ? eo.nb_bits : 0u;
+                const uint32_t total = (uint32_t)eo.nb_extra + em.nb_extra + el.nb_extra + u_ll + u_ml + u_of;
+                uint32_t ofv, ml, ll;
+                if (total <= 57 && br.bits >= (int32_t)total) {
+                    const int32_t lo = br.bits - (int32_t)total;
+                    if (lo < br.cbase || br.bits > br.cbase + 64) {
+                        br.cbase = max(0, ((br.bits + 7) & ~7) - 64);
+                        br.C = zd_ld64(br.p + (br.cbase >> 3));
+                    }
+                    const uint64_t W = br.C >> (lo - br.cbase);
+                    uint32_t sh = total - eo.nb_extra;
+                    ofv = eo.base + ((uint32_t)(W >> sh) & (uint32_t)((1ull << eo.nb_extra) - 1));
+                    sh -= em.nb_extra;
+                    ml = em.base + ((uint32_t)(W >> sh) & ((1u << em.nb_extra) - 1));
+                    sh -= el.nb_extra;
+                    ll = el.base + ((uint32_t)(W >> sh) & ((1u << el.nb_extra) - 1));
+                    if (upd) {
+                        st_ll = el.next_base + ((uint32_t)(W >> (u_ml + u_of)) & ((1u << u_ll) - 1));
+                        st_ml = em.next_base + ((uint32_t)(W >> u_of) & ((1u << u_ml) - 1));
+                        st_of = eo.next_base + ((uint32_t)W & ((1u << u_of) - 1));
+                    }
+                    br.bits = lo;
+                } else {                                 // wide sequences (long offsets) or the tail of the stream: field by field
+                    ofv = eo.base + (eo.nb_extra ? zd_back_read(br, eo.nb_extra) : 0);
+                    ml = em.base + (em.nb_extra ? zd_back_read(br, em.nb_extra) : 0);
+                    ll = el.base + (el.nb_extra ? zd_back_read(br, el.nb_extra) : 0);
+                    if (upd) {
+                        st_ll = el.next_base + zd_back_read(br, el.nb_bits);
+                        st_ml = em.next_base + zd_back_read(br, em.nb_bits);
+                        st_of = eo.next_base + zd_back_read(br, eo.nb_bits);
+                    }
+                }
                 uint32_t off;
                 if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
                 else {
@@ -436,11 +535,6 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
                     }
                 }
                 cx->s_ll[i] = ll; cx->s_ml[i] = ml; cx->s_off[i] = off;
-                if (s0 + i + 1 < nseq) {                // state updates: LL, ML, OF
-                    st_ll = el.next_base + zd_back_read(br, el.nb_bits);
-                    st_ml = em.next_base + zd_back_read(br, em.nb_bits);
-                    st_of = eo.next_base + zd_back_read(br, eo.nb_bits);
-                }
                 if (br.bits < 0) { cx->err = -1; break; }
             }
             cx->rep[0] = r0; cx->rep[1] = r1; cx->rep[2] = r2;
