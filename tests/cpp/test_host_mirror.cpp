@@ -63,6 +63,31 @@ static void builderTests() {
     CHECK(throwsWith<IllegalArgumentException>([&] { fetchPlan(f, 30, 31); }, "Invalid start position 30"));
 }
 
+static void manifestTests() {
+    // golden strings: core/T/manifest/SegmentManifestV1SerdeTest.java:82-133
+    const std::string META = "{\"remoteLogSegmentId\":{\"topicIdPartition\":{\"topicId\":\"lZ6vvmajTWKDBUTV6SQAtQ\",\"topicPartition\":"
+        "{\"topic\":\"topic1\",\"partition\":42}},\"id\":\"adh9f8BMS4anaUnD8KWfWg\"},\"startOffset\":0,\"endOffset\":1000,"
+        "\"maxTimestampMs\":1000000000,\"brokerId\":2,\"eventTimestampMs\":2000000000,\"segmentLeaderEpochs\":{\"0\":100,\"1\":200,\"2\":300}}";
+    const std::string HEAD = "{\"version\":\"1\",\"chunkIndex\":{\"type\":\"fixed\",\"originalChunkSize\":100,\"originalFileSize\":1000,"
+        "\"transformedChunkSize\":110,\"finalTransformedChunkSize\":110},\"segmentIndexes\":{\"offset\":{\"position\":0,\"size\":1},"
+        "\"timestamp\":{\"position\":1,\"size\":1},\"producerSnapshot\":{\"position\":2,\"size\":1},\"leaderEpoch\":{\"position\":3,\"size\":1},";
+    RemoteLogSegmentMetadataJson m{"lZ6vvmajTWKDBUTV6SQAtQ", "topic1", 42, "adh9f8BMS4anaUnD8KWfWg", 0, 1000, 1000000000LL, 2, 2000000000LL,
+                                   {{0, 100}, {1, 200}, {2, 300}}};
+    FixedSizeChunkIndex idx(100, 1000, 110, 110);
+    SegmentIndexesV1 with{{0, 1}, {1, 1}, {2, 1}, {3, 1}, SegmentIndexV1{4, 1}}, without{{0, 1}, {1, 1}, {2, 1}, {3, 1}, std::nullopt};
+    Bytes aad{10, 11, 12, 13};
+    CHECK(segmentManifestV1Json(idx, with, false, std::nullopt, nullptr, m) ==
+          HEAD + "\"transaction\":{\"position\":4,\"size\":1}},\"compression\":false,\"remoteLogSegmentMetadata\":" + META + "}");
+    CHECK(segmentManifestV1Json(idx, without, false, std::nullopt, nullptr, m) ==
+          HEAD + "\"transaction\":null},\"compression\":false,\"remoteLogSegmentMetadata\":" + META + "}");
+    CHECK(segmentManifestV1Json(idx, with, false, std::nullopt, &aad, m) ==
+          HEAD + "\"transaction\":{\"position\":4,\"size\":1}},\"compression\":false,\"encryption\":{\"aad\":\"CgsMDQ==\"},\"remoteLogSegmentMetadata\":" + META + "}");
+    CHECK(segmentManifestV1Json(idx, with, true, std::string("key1:AAEC"), &aad, m).find("\"compression\":true,\"encryption\":{\"dataKey\":\"key1:AAEC\",\"aad\":\"CgsMDQ==\"}") != std::string::npos);
+    // core/IT/RemoteStorageManagerTest.java:117-120 style key
+    CHECK(objectKey("test/", m, Suffix::LOG) == "test/topic1-lZ6vvmajTWKDBUTV6SQAtQ/42/00000000000000000000-adh9f8BMS4anaUnD8KWfWg.log");
+    CHECK(objectKey("", m, Suffix::MANIFEST) == "topic1-lZ6vvmajTWKDBUTV6SQAtQ/42/00000000000000000000-adh9f8BMS4anaUnD8KWfWg.rsm-manifest");
+}
+
 static void baseAndFinisherTests() {
     std::istringstream in(std::string("0123456789"));
     BaseTransformChunkEnumeration base(&in, 3);                       // BaseTransformChunkEnumerationTest: "012" "345" "678" "9"
@@ -138,6 +163,7 @@ static void gpuChainTests(tsgpu_ctx* ctx) {
 
 int main(int argc, char** argv) {
     builderTests();
+    manifestTests();
     baseAndFinisherTests();
     if (argc > 1 && !strcmp(argv[1], "--device")) {
         tsgpu_ctx* ctx = nullptr;

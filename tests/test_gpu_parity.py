@@ -218,3 +218,21 @@ def test_empty_segment_and_argument_errors(ctx):
     with pytest.raises(tsgpu.TsgpuError) as e:
         ctx.transform(A, np.zeros(10, np.uint8), 8 * MIB + 1, bytes(32), b"", bytes(12))
     assert e.value.code == binding.E_ARG
+
+
+def test_single_process_multi_device_context():
+    # the JVM case: one process, several GPUs; batches are dealt round-robin to (device, slot) pairs
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    c = tsgpu.Context(max_chunk_bytes=MIB, max_batch=4, devices=[0, 1])
+    n, cs = 37 * MIB + 999, MIB                      # 38 chunks -> 10 batches over 2 devices x 4 slots
+    src = corpus.gen_segment("K", 8, n, cs)
+    key, aad, ivs = corpus.fixed_key_material(38)
+    got, gs = c.transform(Z | A, src, cs, key, aad, ivs)
+    one = tsgpu.Context(max_chunk_bytes=MIB, max_batch=4, devices=[0])
+    want, ws = one.transform(Z | A, src, cs, key, aad, ivs)
+    assert gs == ws and np.array_equal(got, want)     # same bytes whichever device handled a batch
+    back, _ = c.detransform(Z | A, got, gs, n, key, aad)
+    assert np.array_equal(back, src)
+    c.close(); one.close()

@@ -15,6 +15,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
 #include <functional>
 #include <istream>
 #include <memory>
@@ -403,6 +404,64 @@ inline std::vector<FetchPiece> fetchPlan(const ChunkIndex& index, int from, int 
         plan.push_back({id, skip, take});
     }
     return plan;
+}
+
+// ------------------------------------------------------------------ SegmentManifestV1 JSON
+// Writer for the exact on-disk form of core/M/manifest/SegmentManifestV1.java:37-91 with the property order Jackson
+// produces (golden strings: core/T/manifest/SegmentManifestV1SerdeTest.java:82-133).  The wrapped data key string
+// "<keyId>:<base64 RSA-OAEP(dek)>" is produced by the host's RsaEncryptionProvider and passed through untouched.
+struct SegmentIndexV1 { int position, size; };
+struct SegmentIndexesV1 {                            // core/M/manifest/SegmentIndexesV1.java, builder :27-60
+    SegmentIndexV1 offset, timestamp, producerSnapshot, leaderEpoch;
+    std::optional<SegmentIndexV1> transaction;
+};
+struct RemoteLogSegmentMetadataJson {                // the mixin of core/M/manifest/serde/KafkaTypeSerdeModule.java:63-115
+    std::string topicId, topic; int partition; std::string id;
+    long long startOffset, endOffset, maxTimestampMs; int brokerId; long long eventTimestampMs;
+    std::vector<std::pair<int, long long>> segmentLeaderEpochs;
+};
+inline std::string base64Std(const uint8_t* in, size_t n) {
+    static const char A[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    std::string o;
+    for (size_t i = 0; i < n; i += 3) {
+        const uint32_t v = (uint32_t)in[i] << 16 | (i + 1 < n ? (uint32_t)in[i + 1] << 8 : 0) | (i + 2 < n ? in[i + 2] : 0);
+        o += A[v >> 18]; o += A[(v >> 12) & 63]; o += i + 1 < n ? A[(v >> 6) & 63] : '='; o += i + 2 < n ? A[v & 63] : '=';
+    }
+    return o;
+}
+inline std::string segmentManifestV1Json(const ChunkIndex& chunkIndex, const SegmentIndexesV1& idx, bool compression,
+                                         const std::optional<std::string>& wrappedDataKey, const Bytes* aad,
+                                         const RemoteLogSegmentMetadataJson& m) {
+    auto one = [](const char* name, const SegmentIndexV1& i) {
+        return std::string("\"") + name + "\":{\"position\":" + std::to_string(i.position) + ",\"size\":" + std::to_string(i.size) + "}";
+    };
+    std::string s = "{\"version\":\"1\",\"chunkIndex\":" + chunkIndex.toJson() + ",\"segmentIndexes\":{";
+    s += one("offset", idx.offset) + "," + one("timestamp", idx.timestamp) + "," + one("producerSnapshot", idx.producerSnapshot) + "," +
+         one("leaderEpoch", idx.leaderEpoch) + ",";
+    s += idx.transaction ? one("transaction", *idx.transaction) : std::string("\"transaction\":null");
+    s += std::string("},\"compression\":") + (compression ? "true" : "false");
+    if (aad) {                                       // SegmentEncryptionMetadataV1.java:35-61
+        s += ",\"encryption\":{";
+        if (wrappedDataKey) s += "\"dataKey\":\"" + *wrappedDataKey + "\",";
+        s += "\"aad\":\"" + base64Std(aad->data(), aad->size()) + "\"}";
+    }
+    s += ",\"remoteLogSegmentMetadata\":{\"remoteLogSegmentId\":{\"topicIdPartition\":{\"topicId\":\"" + m.topicId +
+         "\",\"topicPartition\":{\"topic\":\"" + m.topic + "\",\"partition\":" + std::to_string(m.partition) + "}},\"id\":\"" + m.id + "\"}," +
+         "\"startOffset\":" + std::to_string(m.startOffset) + ",\"endOffset\":" + std::to_string(m.endOffset) +
+         ",\"maxTimestampMs\":" + std::to_string(m.maxTimestampMs) + ",\"brokerId\":" + std::to_string(m.brokerId) +
+         ",\"eventTimestampMs\":" + std::to_string(m.eventTimestampMs) + ",\"segmentLeaderEpochs\":{";
+    for (size_t i = 0; i < m.segmentLeaderEpochs.size(); i++)
+        s += (i ? "," : "") + std::string("\"") + std::to_string(m.segmentLeaderEpochs[i].first) + "\":" + std::to_string(m.segmentLeaderEpochs[i].second);
+    return s + "}}}";
+}
+
+// Object keys (core/M/ObjectKeyFactory.java:43-53, 81-124): "<prefix><topic>-<topicId>/<partition>/<startOffset %020d>-<segmentId>.<suffix>"
+enum class Suffix { LOG, INDEXES, MANIFEST };
+inline std::string objectKey(const std::string& prefix, const RemoteLogSegmentMetadataJson& m, Suffix suffix) {
+    char off[32];
+    snprintf(off, sizeof off, "%020lld", m.startOffset);
+    const char* sfx = suffix == Suffix::LOG ? "log" : suffix == Suffix::INDEXES ? "indexes" : "rsm-manifest";
+    return prefix + m.topic + "-" + m.topicId + "/" + std::to_string(m.partition) + "/" + off + "-" + m.id + "." + sfx;
 }
 
 }  // namespace tieredstorage
