@@ -32,7 +32,8 @@ constexpr int ZE_HLOG = 10;                    // per-warp hash table: 2^10 x u3
 constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
 constexpr int ZE_WPB = 1;                      // warps (= blocks in flight) per CTA
 constexpr uint32_t ZE_MAXSEQ = ZB / 8;         // sequences kept per block; beyond that the rest goes out as literals
-constexpr uint32_t ZE_LANE_EXT = 60;           // bytes a lane extends its own match beyond the first 4
+constexpr uint32_t ZE_MIN_MATCH = 5;           // a 4-byte match costs more bits than four Huffman-coded literals (libzstd level 3 also uses 5)
+constexpr uint32_t ZE_LANE_EXT = 12;           // bytes a lane extends its own match beyond the first 4
 constexpr uint32_t ZE_BUF_PAD = 160;
 constexpr uint32_t ZE_SLOT = ZB + 512;         // per-block output slot: 3-byte header + payload (< ZB once accepted; table descriptions are written before that is known)
 constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 4 + 3 * 32 + 3 * 32 * 2 + 3 * 32;   // buf, ht, codes, stv, stn
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
             }
             len = min(len, lim);
         }
-        const uint32_t mask = __ballot_sync(TS_FULL, ok);
+        const uint32_t mask = __ballot_sync(TS_FULL, ok && len >= ZE_MIN_MATCH);
         uint32_t taken = 0, pos = 0;
         while (pos < 32) {
             const uint32_t m2 = mask & (0xffffffffu << pos);
