@@ -221,6 +221,23 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(torch, index):
+    """Pin this rank to the CPUs next to its GPU so the pinned staging buffers are first-touched on the local NUMA
+    node (matters for the PCIe-bound e2e number when 8 ranks share one host).  Best effort: any failure is ignored."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        cpus = open("/sys/bus/pci/devices/%s/local_cpulist" % bdf).read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        if ids:
+            os.sched_setaffinity(0, ids)
+    except Exception:
+        pass
+
+
 def main_tsgpu(args):
     import torch
     import torch.distributed as dist
@@ -234,6 +251,7 @@ def main_tsgpu(args):
         raise SystemExit("bench.py --impl tsgpu needs a GPU: libtsgpu has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     flags = flags_of(args.workload)

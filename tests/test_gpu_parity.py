@@ -236,3 +236,21 @@ def test_single_process_multi_device_context():
     back, _ = c.detransform(Z | A, got, gs, n, key, aad)
     assert np.array_equal(back, src)
     c.close(); one.close()
+
+
+def test_large_chunk_multi_pass_assembly():
+    # chunk.size is configurable up to 2^30-1 (RemoteStorageManagerConfig.java:123-130): a 20 MiB chunk has 2560 zstd
+    # blocks (the frame assembler scans 1024 block sizes per pass) and 80 AES ranges
+    c = tsgpu.Context(max_chunk_bytes=20 * MIB, max_batch=2)
+    n, cs = 2 * 20 * MIB + 54321, 20 * MIB
+    src = corpus.gen_segment("K", 10, n, 4 * MIB)
+    key, aad, ivs = corpus.fixed_key_material(3)
+    got, gs = c.transform(Z | A, src, cs, key, aad, ivs)
+    back_ref, _ = ora.detransform_chunks(Z | A, got, gs, n, key, aad)
+    assert np.array_equal(back_ref, src)
+    back, _ = c.detransform(Z | A, got, gs, n, key, aad)
+    assert np.array_equal(back, src)
+    ref, rs = ora.transform_segment(Z | A, src, cs, key, aad, ivs)
+    back, _ = c.detransform(Z | A, ref, rs, n, key, aad)
+    assert np.array_equal(back, src)
+    c.close()
