@@ -335,12 +335,11 @@ extern "C" int tsgpu_transform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src,
     };
     uint32_t drained = 0;
     for (uint32_t b = 0; b < nbatches && rc == TSGPU_OK; b++) {
-        if (b >= nwork) {                      // the slot is reused: its previous batch must be fully copied out
+        if (b >= nwork) {
+            // The slot is reused.  Its previous batch has been drained (sizes read on the host, copies-out enqueued);
+            // the new batch is enqueued on the same stream, so stream order keeps it behind those copies — the host
+            // does not wait, which keeps all slots' queues full.
             if (drained <= b - nwork) { rc = drain(drained++); if (rc) break; }
-            Work& pw = work_of(b);
-            rt::set_device(pw.device);
-            const char* e = rt::event_sync(pw.ev_done);
-            if (e) { rc = fail(TSGPU_E_CUDA, "event_sync: %s", e); break; }
         }
         uint32_t c0 = b * c->max_batch, nb = std::min(c->max_batch, n - c0);
         if (!work_of(b).ready) { rc = work_init(c, work_of(b), c->lanes[b % c->lanes.size()].device); if (rc) break; }
@@ -472,10 +471,6 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     for (uint32_t b = 0; b < nbatches && rc == TSGPU_OK; b++) {
         if (b >= nwork) {
             if (drained <= b - nwork) { rc = drain(drained++); if (rc) break; }
-            Work& pw = work_of(b);
-            rt::set_device(pw.device);
-            const char* e = rt::event_sync(pw.ev_done);
-            if (e) { rc = fail(TSGPU_E_CUDA, "event_sync: %s", e); break; }
         }
         uint32_t c0 = b * c->max_batch, nb = std::min(c->max_batch, n_chunks - c0);
         if (!work_of(b).ready) { rc = work_init(c, work_of(b), c->lanes[b % c->lanes.size()].device); if (rc) break; }
