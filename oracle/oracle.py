@@ -60,6 +60,8 @@ def lib():
         for f in (L.ora_zstd_compress_chunk, L.ora_zstd_decompress_chunk):
             f.restype = C.c_int64
             f.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t]
+        L.ora_zstd_compress_level.restype = C.c_int64
+        L.ora_zstd_compress_level.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.c_int]
         L.ora_zstd_content_size.restype = C.c_int64
         L.ora_zstd_content_size.argtypes = [u8p, C.c_size_t]
         L.ora_aesgcm_encrypt_chunk.argtypes = [u8p, u8p, u8p, C.c_size_t, u8p, C.c_size_t, u8p]
@@ -115,6 +117,15 @@ def zstd_compress_chunk(data):
     d = _u8(data)
     out = np.empty(lib().ora_zstd_bound(d.size) + 64, dtype=np.uint8)
     r = lib().ora_zstd_compress_chunk(_p(d), d.size, _p(out), out.size)
+    if r < 0:
+        _err(r)
+    return out[:r].tobytes()
+
+
+def zstd_compress_level(data, level):
+    d = _u8(data)
+    out = np.empty(lib().ora_zstd_bound(d.size) + 64, dtype=np.uint8)
+    r = lib().ora_zstd_compress_level(_p(d), d.size, _p(out), out.size, level)
     if r < 0:
         _err(r)
     return out[:r].tobytes()

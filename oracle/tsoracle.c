@@ -68,6 +68,20 @@ int64_t ora_zstd_compress_chunk(const uint8_t* src, size_t n, uint8_t* dst, size
     if (Z.isError(r)) return fail(ORA_E_SHORT, "zstd compress: %s", Z.getErrorName(r));
     return (int64_t)r;
 }
+/* Same call sequence at another compression level: only used to widen the decoder's test coverage (the reference
+ * itself always runs the default level). */
+int64_t ora_zstd_compress_level(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int level) {
+    if (zload()) return ORA_E_NOLIB;
+    ZSTD_CCtx* c = Z.createCCtx();
+    if (!c) return fail(ORA_E_ARG, "ZSTD_createCCtx failed");
+    Z.setPledgedSrcSize(c, n);
+    Z.setParameter(c, ZSTD_c_contentSizeFlag, 1);
+    Z.setParameter(c, 100 /* ZSTD_c_compressionLevel */, level);
+    size_t r = Z.compress2(c, dst, cap, src, n);
+    Z.freeCCtx(c);
+    if (Z.isError(r)) return fail(ORA_E_SHORT, "zstd compress: %s", Z.getErrorName(r));
+    return (int64_t)r;
+}
 /* Zstd.decompressedSize (DecompressionChunkEnumeration.java:41): <0 => "Invalid decompressed size" */
 int64_t ora_zstd_content_size(const uint8_t* frame, size_t n) {
     if (zload()) return ORA_E_NOLIB;
