@@ -69,8 +69,15 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (arrival time, csv line)
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
 
     def start(self):
         try:
@@ -84,7 +91,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.monotonic(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -94,8 +101,12 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        # samples that arrived inside the timed region; if the region was shorter than the sampling period, the samples
+        # taken under the same load right before it (warm-up runs the identical step) are used and counted separately
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t)]
+        rows = inside if inside else [r for (t, r) in self.rows][-5:]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -107,7 +118,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
 def load_peaks():
@@ -279,20 +290,22 @@ def main_tsgpu(args):
         torch.cuda.synchronize()
 
     # ---- value: device-resident, CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                    # started before warm-up so nvidia-smi is already streaming
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.begin()
     e0.record()
     for _ in range(args.steps):
         step_device()
     e1.record()
     barrier()
+    sampler.end()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
