@@ -263,33 +263,48 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
     while (cur + 4 <= bn && nseq + 8 <= ZE_MAXSEQ) {                // a step adds at most 8 sequences (min match 4)
         const uint32_t p = cur + lane;
         const bool valid = p + 4 <= bn;
-        const uint32_t v = ld_u32_unaligned(buf + p);
+        // unaligned 4-byte reads as a rolling pair of aligned words per stream: one new LDS per stream and step
+        const uint32_t* wp = (const uint32_t*)(buf + (p & ~3u));
+        const uint32_t shp = (p & 3) * 8;
+        uint32_t a0 = wp[0], a1 = wp[1];
+        const uint32_t v = __funnelshift_r(a0, a1, shp);
         const uint32_t h = ze_hash(v);
         const uint32_t slot = valid ? ht[h] : 0u;                  // position + 1, 0 = empty
         __syncwarp();
         if (valid) atomicMax(&ht[h], p + 1);                       // newest position wins, deterministically
         __syncwarp();
-        const uint32_t cand = slot - 1;
-        const bool ok = slot != 0 && ld_u32_unaligned(buf + cand) == v;
+        const uint32_t cand = slot ? slot - 1 : 0u;
+        const uint32_t* wc = (const uint32_t*)(buf + (cand & ~3u));
+        const uint32_t shc = (cand & 3) * 8;
+        uint32_t c0 = wc[0], c1 = wc[1];
+        const bool ok = slot != 0 && __funnelshift_r(c0, c1, shc) == v;
         uint32_t len = 0;
         if (ok) {
             len = 4;
             const uint32_t lim = min(bn - p, 4 + ZE_LANE_EXT);
-            while (len < lim) {
-                const uint32_t c = ze_common_bytes(ld_u32_unaligned(buf + p + len) ^ ld_u32_unaligned(buf + cand + len));
+            for (uint32_t k = 2; len < lim; k++) {
+                a0 = a1; a1 = wp[k]; c0 = c1; c1 = wc[k];
+                const uint32_t c = ze_common_bytes(__funnelshift_r(a0, a1, shp) ^ __funnelshift_r(c0, c1, shc));
                 len += c;
                 if (c < 4) break;
             }
             len = min(len, lim);
         }
         const uint32_t mask = __ballot_sync(TS_FULL, ok && len >= ZE_MIN_MATCH);
+        // Greedy selection, left to right.  Every lane precomputes where its match would end and which candidate would
+        // come next, so one shuffle per taken match walks the chain (the only serial part of the parse).
+        const uint32_t e = lane + len;
+        const uint32_t mnext = e < 32 ? mask & (0xffffffffu << e) : 0u;
+        const uint32_t nxt = mnext ? (uint32_t)__ffs((int)mnext) - 1 : 32u;
+        const bool capped = ok && len == 4 + ZE_LANE_EXT && p + len < bn;
+        const uint32_t packed = e | (nxt << 8) | (capped ? 1u << 16 : 0u);
         uint32_t taken = 0, pos = 0;
-        while (pos < 32) {
-            const uint32_t m2 = mask & (0xffffffffu << pos);
-            if (!m2) break;
-            const uint32_t f = (uint32_t)__ffs((int)m2) - 1;
-            uint32_t L = __shfl_sync(TS_FULL, len, f);
-            if (L == 4 + ZE_LANE_EXT && cur + f + L < bn) {        // warp-wide extension of a long match
+        uint32_t f = mask ? (uint32_t)__ffs((int)mask) - 1 : 32u;
+        while (f < 32) {
+            const uint32_t info = __shfl_sync(TS_FULL, packed, f);
+            uint32_t end = info & 0xffu, nf = (info >> 8) & 0xffu;
+            if (info >> 16) {                                      // warp-wide extension of a long match
+                uint32_t L = 4 + ZE_LANE_EXT;
                 const uint32_t off = __shfl_sync(TS_FULL, p - cand, f);
                 const uint32_t mpos = cur + f;
                 while (true) {
@@ -308,9 +323,13 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
                     L += 128;
                 }
                 if (lane == f) len = L;
+                end = f + L;
+                const uint32_t m2 = end < 32 ? mask & (0xffffffffu << end) : 0u;
+                nf = m2 ? (uint32_t)__ffs((int)m2) - 1 : 32u;
             }
             taken |= 1u << f;
-            pos = f + L;
+            pos = end;
+            f = nf;
         }
         if (taken) {
             const uint32_t my_end = p + len;                       // meaningful on taken lanes
