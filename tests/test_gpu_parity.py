@@ -238,6 +238,23 @@ def test_single_process_multi_device_context():
     c.close(); one.close()
 
 
+def test_index_files_ride_one_ragged_batch(ctx):
+    # RemoteStorageManager.transformIndex (RemoteStorageManager.java:455-490): each Kafka index file is ONE chunk,
+    # encryption only; fetchIndexBytes (:624-652) reads one back
+    rng = np.random.default_rng(77)
+    blobs = [rng.integers(0, 256, n, dtype=np.uint8) for n in (10 * MIB // 8, 10 * MIB // 12, 37, 126, 20480)]
+    src = np.concatenate(blobs)
+    key, aad, ivs = rng.bytes(32), rng.bytes(32), rng.bytes(12 * 5)
+    out, sizes = ctx.transform_chunks(A, src, [b.size for b in blobs], key, aad, ivs)
+    assert sizes == [b.size + 28 for b in blobs]
+    pos = 0
+    for i, b in enumerate(blobs):
+        assert bytes(out[pos:pos + sizes[i]]) == ora.aesgcm_encrypt_chunk(key, ivs[12 * i:12 * i + 12], aad, b)
+        pos += sizes[i]
+    back, osz = ctx.detransform(A, out, sizes, src.size, key, aad)
+    assert np.array_equal(back, src) and osz == [b.size for b in blobs]
+
+
 def test_large_chunk_multi_pass_assembly():
     # chunk.size is configurable up to 2^30-1 (RemoteStorageManagerConfig.java:123-130): a 20 MiB chunk has 2560 zstd
     # blocks (the frame assembler scans 1024 block sizes per pass) and 80 AES ranges

@@ -120,3 +120,23 @@ def test_simt_reference_written_index_deserializes(ctx):
     assert ctx.transformed_chunks_deserialize("KLUv/SAPeQAAAAAAAwAAAAoBAAoAAAAe") == [10, 20, 30]
     pos = ctx.chunk_positions(sizes)
     assert [int(p) for p in pos[:-1]] == [c[3] for c in ora.ChunkIndex.variable(1 << 20, 599 * (1 << 20) + 1, sizes).chunks()]
+
+
+def test_simt_index_files_ride_one_ragged_batch(ctx):
+    # RemoteStorageManager.transformIndex (RemoteStorageManager.java:455-490): each Kafka index is ONE chunk, encryption
+    # only; the object is their concatenation and SegmentIndexesV1 records (position, size) of each transformed blob
+    rng = np.random.default_rng(77)
+    blobs = [rng.integers(0, 256, n, dtype=np.uint8) for n in (10485, 9000, 37, 126, 2048)]   # offset, time, snapshot, epoch, txn
+    src = np.concatenate(blobs)
+    key, aad, ivs = rng.bytes(32), rng.bytes(32), rng.bytes(12 * 5)
+    out, sizes = ctx.transform_chunks(A, src, [b.size for b in blobs], key, aad, ivs)
+    assert sizes == [b.size + 28 for b in blobs]
+    pos = 0
+    for i, b in enumerate(blobs):
+        want = ora.aesgcm_encrypt_chunk(key, ivs[12 * i:12 * i + 12], aad, b)
+        assert bytes(out[pos:pos + sizes[i]]) == want            # bit-exact with the reference-side cipher
+        pos += sizes[i]
+    back, osz = ctx.detransform(A, out, sizes, src.size, key, aad)      # fetchIndexBytes direction
+    assert np.array_equal(back, src) and osz == [b.size for b in blobs]
+    with pytest.raises(tsgpu.TsgpuError):
+        ctx.transform_chunks(A, src, [10, 0, 5], key, aad, ivs)

@@ -20,7 +20,7 @@ OK, E_ARG, E_STATE, E_AUTH, E_CORRUPT, E_SHORT, E_NODEVICE, E_CUDA, E_NOMEM = 0,
 
 SYMBOLS = [
     "tsgpu_last_error", "tsgpu_version", "tsgpu_create", "tsgpu_destroy", "tsgpu_host_alloc", "tsgpu_host_free",
-    "tsgpu_transform_bound", "tsgpu_transform", "tsgpu_detransform", "tsgpu_slot_stride",
+    "tsgpu_transform_bound", "tsgpu_transform", "tsgpu_transform_chunks", "tsgpu_detransform", "tsgpu_slot_stride",
     "tsgpu_transform_device", "tsgpu_detransform_device", "tsgpu_launch_count", "tsgpu_chunk_positions",
     "tsgpu_chunk_sizes_encode", "tsgpu_chunk_sizes_decode", "tsgpu_transformed_chunks_serialize",
     "tsgpu_transformed_chunks_deserialize", "tsgpu_chunk_index_json", "tsgpu_profile_enable", "tsgpu_profile_report",
@@ -59,6 +59,7 @@ def load(path=None):
     L.tsgpu_slot_stride.restype = u64
     L.tsgpu_slot_stride.argtypes = [u32, u32]
     L.tsgpu_transform.argtypes = [vp, u32, vp, u64, u32, vp, vp, u32, vp, vp, u64, vp, vp]
+    L.tsgpu_transform_chunks.argtypes = [vp, u32, vp, vp, u32, vp, vp, u32, vp, vp, u64, vp]
     L.tsgpu_detransform.argtypes = [vp, u32, vp, u64, vp, u32, vp, vp, u32, vp, u64, vp]
     L.tsgpu_transform_device.argtypes = [vp, C.c_int, u32, vp, u64, u32, vp, vp, u32, vp, vp, u64, vp, vp]
     L.tsgpu_detransform_device.argtypes = [vp, C.c_int, u32, vp, u64, vp, u32, u32, vp, vp, u32, vp, vp, vp, vp]
@@ -148,6 +149,19 @@ class Context:
         self._check(self.lib.tsgpu_transform(self._h, flags, _p(s), s.size, chunk_size, _p(k), _p(a), a.size, _p(iv),
                                              dst.ctypes.data, dst.size, sizes.ctypes.data, C.addressof(n)))
         sizes = sizes[:n.value]
+        return dst[:int(sizes.sum(dtype=np.uint64))], [int(x) for x in sizes]
+
+    def transform_chunks(self, flags, src, chunk_lens, key=None, aad=b"", ivs=None):
+        """Ragged chunks (e.g. the index files of a segment): returns (transformed bytes, [transformed sizes])."""
+        s = _u8(src)
+        lens = np.ascontiguousarray(chunk_lens, dtype=np.uint32)
+        cap = int(sum(int(self.lib.tsgpu_transform_bound(flags, int(x), int(x))) for x in lens)) + 64
+        dst = np.empty(cap, dtype=np.uint8)
+        sizes = np.zeros(max(lens.size, 1), dtype=np.uint32)
+        k, a, iv = _u8(key), _u8(aad), _u8(ivs)
+        self._check(self.lib.tsgpu_transform_chunks(self._h, flags, _p(s), _p(lens), lens.size, _p(k), _p(a), a.size, _p(iv),
+                                                    dst.ctypes.data, dst.size, sizes.ctypes.data))
+        sizes = sizes[:lens.size]
         return dst[:int(sizes.sum(dtype=np.uint64))], [int(x) for x in sizes]
 
     def detransform(self, flags, src, transformed_sizes, dst_cap, key=None, aad=b"", dst=None):

@@ -236,19 +236,19 @@ struct XfBatch {            // one in-flight transform batch
 };
 }
 
-static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t* src, uint64_t src_len,
+// `off`/`len`: position and size of every chunk inside src (chunks are contiguous); `cs` = largest chunk of the call.
+static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t* src, const uint64_t* off, const uint32_t* len,
                            uint32_t cs, uint32_t c0, uint32_t nb, const Aes256RoundKeys& rk,
                            const uint8_t* aad, uint32_t aad_len, const uint8_t* ivs, XfBatch& xb) {
     RT(rt::set_device(w.device));
     rt::stream_t st = w.stream;
-    const uint64_t byte0 = (uint64_t)c0 * cs;
-    const uint64_t byte1 = std::min<uint64_t>(src_len, (uint64_t)(c0 + nb) * cs);
+    const uint64_t byte0 = off[c0];
+    const uint64_t byte1 = off[c0 + nb - 1] + len[c0 + nb - 1];
     RT(rt::h2d(w.d_orig, src + byte0, byte1 - byte0, st));
     // descriptor block: a = original chunks, b = frames, c = transformed slots
     for (uint32_t i = 0; i < nb; i++) {
-        uint64_t o = (uint64_t)i * cs;
-        w.hd.a_off[i] = o;
-        w.hd.a_len[i] = (uint32_t)std::min<uint64_t>(cs, (byte1 - byte0) - o);
+        w.hd.a_off[i] = off[c0 + i] - byte0;
+        w.hd.a_len[i] = len[c0 + i];
         w.hd.b_off[i] = (uint64_t)i * c->frame_stride;
         w.hd.c_off[i] = (uint64_t)i * c->slot_stride + TSGPU_SLOT_HEAD;
     }
@@ -281,9 +281,12 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
     return TSGPU_OK;
 }
 
-extern "C" int tsgpu_transform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, uint64_t src_len, uint32_t chunk_size,
-                               const uint8_t key[32], const uint8_t* aad, uint32_t aad_len, const uint8_t* ivs,
-                               uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes, uint32_t* n_chunks) {
+static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, uint64_t src_len, const std::vector<uint64_t>& off,
+                            const std::vector<uint32_t>& len, uint32_t cs, const uint8_t key[32], const uint8_t* aad, uint32_t aad_len,
+                            const uint8_t* ivs, uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes, uint32_t* n_chunks);
+
+static int transform_args_ok(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, uint64_t src_len, const uint8_t* key, const uint8_t* aad,
+                             uint32_t aad_len, const uint8_t* ivs, uint32_t* transformed_sizes, uint32_t* n_chunks) {
     if (!c) return fail(TSGPU_E_ARG, "ctx cannot be null");
     if (!n_chunks || !transformed_sizes) return fail(TSGPU_E_ARG, "transformed_sizes/n_chunks cannot be null");
     if (src_len && !src) return fail(TSGPU_E_ARG, "inputStream cannot be null");
@@ -291,6 +294,14 @@ extern "C" int tsgpu_transform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src,
     if ((flags & TSGPU_FLAG_AES) && (!key || !ivs)) return fail(TSGPU_E_ARG, "key and ivs are required for encryption");
     if ((flags & TSGPU_FLAG_AES) && aad_len > MAX_AAD) return fail(TSGPU_E_ARG, "aad longer than %u bytes", MAX_AAD);
     if ((flags & TSGPU_FLAG_AES) && aad_len && !aad) return fail(TSGPU_E_ARG, "aad cannot be null");
+    return TSGPU_OK;
+}
+
+extern "C" int tsgpu_transform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, uint64_t src_len, uint32_t chunk_size,
+                               const uint8_t key[32], const uint8_t* aad, uint32_t aad_len, const uint8_t* ivs,
+                               uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes, uint32_t* n_chunks) {
+    int rc = transform_args_ok(c, flags, src, src_len, key, aad, aad_len, ivs, transformed_sizes, n_chunks);
+    if (rc) return rc;
     // BaseTransformChunkEnumeration: originalChunkSize 0 disables chunking (one chunk = whole stream)
     uint64_t cs64 = chunk_size ? chunk_size : src_len;
     if (src_len == 0) { *n_chunks = 0; return TSGPU_OK; }
@@ -298,14 +309,45 @@ extern "C" int tsgpu_transform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src,
     const uint32_t cs = (uint32_t)cs64;
     const uint64_t n64 = (src_len + cs - 1) / cs;
     if (n64 > *n_chunks) return fail(TSGPU_E_SHORT, "transformed_sizes too small: %llu chunks", (unsigned long long)n64);
-    const uint32_t n = (uint32_t)n64;
+    std::vector<uint64_t> off(n64);
+    std::vector<uint32_t> len(n64);
+    for (uint64_t i = 0; i < n64; i++) { off[i] = i * cs; len[i] = (uint32_t)std::min<uint64_t>(cs, src_len - i * cs); }
+    return transform_common(c, flags, src, src_len, off, len, cs, key, aad, aad_len, ivs, dst, dst_cap, transformed_sizes, n_chunks);
+}
+
+// Ragged variant: chunk i is the next chunk_lens[i] bytes of src.  This is what RemoteStorageManager.transformIndex
+// (RemoteStorageManager.java:455-490) needs: every Kafka index file is ONE chunk (chunking disabled), AES only, and the
+// five of them ride in a single batch.
+extern "C" int tsgpu_transform_chunks(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, const uint32_t* chunk_lens, uint32_t n,
+                                      const uint8_t key[32], const uint8_t* aad, uint32_t aad_len, const uint8_t* ivs,
+                                      uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes) {
+    uint32_t cap = n;
+    if (n && !chunk_lens) return fail(TSGPU_E_ARG, "chunk_lens cannot be null");
+    uint64_t total = 0; uint32_t mx = 0;
+    std::vector<uint64_t> off(n);
+    std::vector<uint32_t> len(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if (chunk_lens[i] == 0) return fail(TSGPU_E_ARG, "chunk %u is empty", i);
+        off[i] = total; len[i] = chunk_lens[i]; total += chunk_lens[i]; mx = std::max(mx, chunk_lens[i]);
+    }
+    int rc = transform_args_ok(c, flags, src, total, key, aad, aad_len, ivs, transformed_sizes, &cap);
+    if (rc) return rc;
+    if (n == 0) return TSGPU_OK;
+    if (mx > c->chunk_cap) return fail(TSGPU_E_ARG, "chunk size %u exceeds the context's max_chunk_bytes %u", mx, c->chunk_cap);
+    return transform_common(c, flags, src, total, off, len, mx, key, aad, aad_len, ivs, dst, dst_cap, transformed_sizes, &cap);
+}
+
+static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, uint64_t src_len, const std::vector<uint64_t>& off,
+                            const std::vector<uint32_t>& len, uint32_t cs, const uint8_t key[32], const uint8_t* aad, uint32_t aad_len,
+                            const uint8_t* ivs, uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes, uint32_t* n_chunks) {
+    const uint32_t n = (uint32_t)len.size();
     if (!dst) return fail(TSGPU_E_ARG, "dst cannot be null");
 
     std::lock_guard<std::mutex> lock(c->mu);
     if (flags == 0) {       // TransformFinisher no-transform fast path (TransformFinisher.java:135-140): bytes unchanged
         if (dst_cap < src_len) return fail(TSGPU_E_SHORT, "dst too small");
         memcpy(dst, src, src_len);
-        for (uint32_t i = 0; i < n; i++) transformed_sizes[i] = (uint32_t)std::min<uint64_t>(cs, src_len - (uint64_t)i * cs);
+        for (uint32_t i = 0; i < n; i++) transformed_sizes[i] = len[i];
         *n_chunks = n;
         return TSGPU_OK;
     }
@@ -343,7 +385,7 @@ extern "C" int tsgpu_transform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src,
         }
         uint32_t c0 = b * c->max_batch, nb = std::min(c->max_batch, n - c0);
         if (!work_of(b).ready) { rc = work_init(c, work_of(b), c->lanes[b % c->lanes.size()].device); if (rc) break; }
-        rc = transform_issue(c, work_of(b), flags, src, src_len, cs, c0, nb, rk, aad, aad_len, ivs, inflight[b]);
+        rc = transform_issue(c, work_of(b), flags, src, off.data(), len.data(), cs, c0, nb, rk, aad, aad_len, ivs, inflight[b]);
     }
     while (rc == TSGPU_OK && drained < nbatches) rc = drain(drained++);
     for (auto& l : c->lanes) for (auto& w : l.w) if (w.busy) {   // always leave the context idle
