@@ -36,7 +36,12 @@ constexpr uint32_t ZE_MIN_MATCH = 5;           // a 4-byte match costs more bits
 constexpr uint32_t ZE_LANE_EXT = 12;           // bytes a lane extends its own match beyond the first 4
 constexpr uint32_t ZE_BUF_PAD = 160;
 constexpr uint32_t ZE_SLOT = ZB + 512;         // per-block output slot: 3-byte header + payload (< ZB once accepted; table descriptions are written before that is known)
-constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 4 + 3 * 32 + 3 * 32 * 2 + 3 * 32;   // buf, ht, codes, stv, stn
+constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 4;   // buf, ht
+// per-tile FSE scratch (codes, state bits) lives in the tail of `buf`: the sequence bit stream staged there is at most
+// ZE_MAXSEQ * 58 bits, which ends below this offset
+constexpr uint32_t ZE_SEQ_AUX_OFF = ZB - 512;
+static_assert(ZE_MAXSEQ * 58 / 8 + 16 <= ZE_SEQ_AUX_OFF, "sequence bit stream would overlap the FSE tile scratch");
+static_assert(ZE_SEQ_AUX_OFF + 3 * 32 + 3 * 32 * 2 + 3 * 32 <= ZB + ZE_BUF_PAD, "FSE tile scratch must fit the block buffer");
 constexpr uint32_t ZE_SMEM_WARP_AL = (ZE_SMEM_WARP + 15) & ~15u;
 
 __constant__ zf::SeqTables g_seq_tables = zf::make_seq_tables();
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
     uint8_t* wbase = smem + warp * ZE_SMEM_WARP_AL;
     uint8_t* buf = wbase;
     uint32_t* ht = (uint32_t*)(wbase + ZB + ZE_BUF_PAD);
-    uint8_t* codes = (uint8_t*)(ht + ZE_HSIZE);
+    uint8_t* codes = buf + ZE_SEQ_AUX_OFF;
     uint16_t* stv = (uint16_t*)(codes + 96);
     uint8_t* stn = (uint8_t*)(stv + 96);
 
