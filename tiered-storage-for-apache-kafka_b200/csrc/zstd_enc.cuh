@@ -99,6 +99,7 @@ static inline unsigned __match_any_sync(unsigned, unsigned v) {
 
 }  // namespace ts
 
+#include "zstd_fse_enc.cuh"
 #include "zstd_huf_enc.cuh"
 
 namespace ts {
@@ -108,9 +109,6 @@ struct ZeFseShared {      // per-CTA copy of the predefined encoding tables
     zf::PredefinedCTables t;
 };
 
-}  // namespace ts
-#include "zstd_fse_enc.cuh"
-namespace ts {
 
 // Encodes the sequences section (everything after the Number_of_Sequences field): the modes byte and table
 // descriptions go straight to `hdr_out` (global), the bit stream is staged in the word buffer `bits` (shared).
@@ -137,11 +135,11 @@ __device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict_
     ZeKind kll, kof, kml;
     uint8_t* desc = hdr_out + 1;
     uint32_t dn = ze_build_kind(ct->cnt, ZE_NSYM_LL, N, zf::LL_MAX_LOG, zf::LL_DEFAULT_LOG, fs->t.ll.state, fs->t.ll.sym,
-                                ct->st_ll, ct->sy_ll, (uint8_t*)bits, desc, &kll, lane);
+                                ct->st_ll, ct->sy_ll, (uint8_t*)bits, desc, &kll, true, lane);
     dn += ze_build_kind(ct->cnt + ZE_NSYM_LL + ZE_NSYM_ML, ZE_NSYM_OF, N, zf::OF_MAX_LOG, zf::OF_DEFAULT_LOG, fs->t.of.state, fs->t.of.sym,
-                        ct->st_of, ct->sy_of, (uint8_t*)bits, desc + dn, &kof, lane);
+                        ct->st_of, ct->sy_of, (uint8_t*)bits, desc + dn, &kof, true, lane);
     dn += ze_build_kind(ct->cnt + ZE_NSYM_LL, ZE_NSYM_ML, N, zf::ML_MAX_LOG, zf::ML_DEFAULT_LOG, fs->t.ml.state, fs->t.ml.sym,
-                        ct->st_ml, ct->sy_ml, (uint8_t*)bits, desc + dn, &kml, lane);
+                        ct->st_ml, ct->sy_ml, (uint8_t*)bits, desc + dn, &kml, true, lane);
     if (lane == 0) hdr_out[0] = (uint8_t)((kll.mode << 6) | (kof.mode << 4) | (kml.mode << 2));
     *desc_bytes = 1 + dn;
     __syncwarp();
@@ -385,7 +383,16 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
 
     // ---- phase B: entropy stage into the (now free) shared block buffer, then emit
     uint32_t payload = 0xffffffffu;                                // "not compressible"
-    if (nseq > 0) {
+    if (nseq == 0) {
+        // no match at all: the block may still be worth a compressed block with entropy-coded literals and zero sequences
+        uint8_t* body = out + 3;
+        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, (uint16_t*)ht, lane);
+        __syncwarp();
+        if (lit_bytes + 1 < bn) {
+            if (lane == 0) body[lit_bytes] = 0;                    // Number_of_Sequences = 0: the sequences section ends here
+            payload = lit_bytes + 1;
+        }
+    } else {
         // literals section first (into `out` directly), then the sequences bit stream staged in `buf`
         uint8_t* body = out + 3;
         const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, (uint16_t*)ht, lane);   // header + payload

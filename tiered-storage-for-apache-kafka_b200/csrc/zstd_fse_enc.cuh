@@ -74,7 +74,7 @@ __device__ TS_NOINLINE uint32_t ze_write_ncount(uint8_t* out, const uint32_t* no
 // Returns the bytes of table description written at desc (global).
 __device__ __forceinline__ uint32_t ze_build_kind(uint32_t* cnt, uint32_t alphabet, uint32_t N, uint32_t max_log, uint32_t default_log,
                                                   const uint16_t* pre_state, const zf::FseCSym* pre_sym, uint16_t* st, zf::FseCSym* sy,
-                                                  uint8_t* scratch, uint8_t* desc, ZeKind* kind, uint32_t lane) {
+                                                  uint8_t* scratch, uint8_t* desc, ZeKind* kind, bool allow_predefined, uint32_t lane) {
     const uint32_t c0 = lane < alphabet ? cnt[lane] : 0, c1 = lane + 32 < alphabet ? cnt[lane + 32] : 0;
     const uint32_t used0 = __ballot_sync(TS_FULL, c0 != 0), used1 = __ballot_sync(TS_FULL, c1 != 0);
     const uint32_t nused = (uint32_t)__popc(used0) + (uint32_t)__popc(used1);
@@ -84,7 +84,7 @@ __device__ __forceinline__ uint32_t ze_build_kind(uint32_t* cnt, uint32_t alphab
         kind->mode = 1; kind->log = 0;
         return 1;
     }
-    if (N < ZE_PREDEF_BELOW) {                               // Predefined_Mode
+    if (allow_predefined && N < ZE_PREDEF_BELOW) {           // Predefined_Mode
         const uint32_t size = 1u << default_log;
         for (uint32_t i = lane; i < size; i += 32) st[i] = pre_state[i];
         for (uint32_t i = lane; i < alphabet; i += 32) sy[i] = pre_sym[i];

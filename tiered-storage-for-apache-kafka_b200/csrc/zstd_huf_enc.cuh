@@ -10,6 +10,7 @@
 #include "ts_common.cuh"
 #include "zstd_format.h"
 #include "index_scan.cuh"
+#include "zstd_fse_enc.cuh"
 
 namespace ts {
 
@@ -34,6 +35,9 @@ __device__ __forceinline__ uint32_t ze_rle_literals(uint8_t v, uint32_t n, uint8
 }
 
 constexpr uint32_t ZE_HUF_MIN = 64;            // below this many literals a table cannot pay for itself
+// FSE-compressed weights also shave ~1.5 % off text-like blocks (tree description 62 -> ~25 bytes per 8 KiB block) but cost
+// ~5 % of the block's time; by default they are used only where direct weights cannot describe the tree (symbols > 128).
+constexpr bool ZE_FSE_WEIGHTS_ALWAYS = false;
 
 // Returns the bytes written at `body`.  `work`: >= ZB + 160 bytes of shared memory (tree scratch, then the
 // stream staging area); `aux`: 4 KiB of shared memory (histogram + code table).
@@ -65,8 +69,20 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
     }
     __syncwarp();
     if (m == 1) return ze_rle_literals((uint8_t)(keys[0] & 0xff), n, body, lane);
+    {   // Shannon estimate in 1/16 bit units: sum c * (log2(n) - log2(c)), log2 by leading zeros + a linear fraction
+        uint32_t cost = 0;
+        for (uint32_t k = 0; k < 8; k++) {
+            const uint32_t c = hist[lane * 8 + k];
+            if (c) {
+                const uint32_t hb = (uint32_t)zf::highbit32(c);
+                const uint32_t lg16 = (hb << 4) + (((c << (31 - hb)) >> 27) & 15);       // ~ 16 * log2(c)
+                cost += c * (((uint32_t)zf::highbit32(n) << 4) + (((n << (31 - zf::highbit32(n))) >> 27) & 15) + 1 - lg16);
+            }
+        }
+        const uint32_t bits16 = __reduce_add_sync(TS_FULL, cost);
+        if ((bits16 >> 7) + m / 2 + 16 >= n) return ze_raw_literals(lits, n, body, lane);   // >= n bytes even before rounding losses
+    }
     const uint32_t last_sym = keys[m - 1] & 0xff;
-    if (last_sym > 128) return ze_raw_literals(lits, n, body, lane);      // would need FSE-compressed weights
 
     // ---- code lengths: rebuild with halved counts until the tree is at most 11 deep
     uint32_t max_len = 0;
@@ -131,7 +147,67 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
     }
     __syncwarp();
     const uint32_t nweights = last_sym;                                   // symbols 0 .. last_sym-1 are listed
-    const uint32_t tree_bytes = 1 + (nweights + 1) / 2;
+    // Tree description: direct 4-bit weights (at most 128 of them) or FSE-compressed weights (RFC 8878 §4.2.1.1);
+    // the shorter wins.  The FSE form is what lets alphabets above byte value 128 (binary payloads) be Huffman-coded.
+    uint32_t tree_bytes = nweights <= 128 ? 1 + (nweights + 1) / 2 : 0xffffffffu;
+    uint8_t* wdesc = (uint8_t*)(keys + 256);                              // 1 KiB tail of `aux`: header byte + FSE description
+    {
+        uint8_t* wts = (uint8_t*)(work + 1536);                           // weights, then FSE tables, in dead tree scratch
+        uint32_t* wcnt = (uint32_t*)(wts + 256);                          // [16]
+        uint16_t* wst = (uint16_t*)(wcnt + 16);                           // [64]
+        zf::FseCSym* wsy = (zf::FseCSym*)(wst + 64);                      // [16]
+        uint8_t* wscratch = (uint8_t*)(wsy + 16);                         // >= 772 bytes
+        if (lane < 16) wcnt[lane] = 0;
+        __syncwarp();
+        for (uint32_t s2 = lane; s2 < nweights; s2 += 32) {
+            const uint32_t l = ctab[s2] >> 16;
+            const uint32_t w = l ? max_len + 1 - l : 0;
+            wts[s2] = (uint8_t)w;
+            atomicAdd(&wcnt[w], 1u);
+        }
+        __syncwarp();
+        if (nweights >= 2 && (ZE_FSE_WEIGHTS_ALWAYS || nweights > 128)) {
+            ZeKind wk;
+            const uint32_t dsz = ze_build_kind(wcnt, 13, nweights, zf::HUFW_MAX_LOG, zf::HUFW_MAX_LOG, nullptr, nullptr, wst, wsy,
+                                               wscratch, wdesc + 1, &wk, false, lane);
+            if (wk.mode == 2) {
+                if (lane == 0) {                                          // two interleaved states, last weight first
+                    uint8_t* o = wdesc + 1 + dsz;
+                    uint64_t acc = 0; uint32_t nb = 0, ob = 0;
+                    uint32_t st[2];
+                    for (uint32_t q = 0; q < 2; q++) {                    // FSE_initCState2 for the two last weights
+                        const uint32_t i = nweights - 1 - q;
+                        const zf::FseCSym c = wsy[wts[i]];
+                        const uint32_t nbo = (uint32_t)(c.delta_nb_bits + (1 << 15)) >> 16;
+                        const uint32_t v = (nbo << 16) - (uint32_t)c.delta_nb_bits;
+                        st[i & 1] = wst[(int32_t)(v >> nbo) + c.delta_find_state];
+                    }
+                    for (int32_t i = (int32_t)nweights - 3; i >= 0; i--) {
+                        const zf::FseCSym c = wsy[wts[i]];
+                        const uint32_t sv = st[i & 1];
+                        const uint32_t nbo = (sv + (uint32_t)c.delta_nb_bits) >> 16;
+                        acc |= (uint64_t)(sv & ((1u << nbo) - 1)) << nb; nb += nbo;
+                        st[i & 1] = wst[(int32_t)(sv >> nbo) + c.delta_find_state];
+                        while (nb >= 8) { o[ob++] = (uint8_t)acc; acc >>= 8; nb -= 8; }
+                    }
+                    acc |= (uint64_t)(st[1] & ((1u << wk.log) - 1)) << nb; nb += wk.log;      // flush odd chain, then even chain
+                    acc |= (uint64_t)(st[0] & ((1u << wk.log) - 1)) << nb; nb += wk.log;
+                    acc |= 1ull << nb; nb += 1;                                                // end mark
+                    while (nb > 0) { o[ob++] = (uint8_t)acc; acc >>= 8; nb = nb >= 8 ? nb - 8 : 0; }
+                    meta[2] = dsz + ob;
+                }
+                __syncwarp();
+                const uint32_t fsz = meta[2];
+                if (fsz < 128 && 1 + fsz < tree_bytes) {
+                    if (lane == 0) wdesc[0] = (uint8_t)fsz;
+                    tree_bytes = 1 + fsz;
+                } else if (lane == 0) wdesc[0] = 0xff;
+            } else if (lane == 0) wdesc[0] = 0xff;
+        } else if (lane == 0) wdesc[0] = 0xff;
+        __syncwarp();
+    }
+    if (tree_bytes == 0xffffffffu) return ze_raw_literals(lits, n, body, lane);   // neither form can describe this tree
+    const bool fse_weights = wdesc[0] != 0xff;
     const uint32_t est = tree_bytes + 6 + (meta[1] >> 3) + 8;
     if (est + 5 >= n) return ze_raw_literals(lits, n, body, lane);        // Huffman would not pay
 
@@ -180,11 +256,15 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
         else h = 2u | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 22);
         for (uint32_t k = 0; k < hsz; k++) body[k] = (uint8_t)(h >> (8 * k));
         uint8_t* t = body + hsz;
-        t[0] = (uint8_t)(127 + nweights);
-        for (uint32_t i = 0; i < nweights; i += 2) {
-            const uint32_t l0 = ctab[i] >> 16, l1 = i + 1 < nweights ? ctab[i + 1] >> 16 : 0;
-            const uint32_t w0 = l0 ? max_len + 1 - l0 : 0, w1 = l1 ? max_len + 1 - l1 : 0;
-            t[1 + i / 2] = (uint8_t)((w0 << 4) | w1);
+        if (fse_weights) {
+            for (uint32_t i = 0; i < tree_bytes; i++) t[i] = wdesc[i];
+        } else {
+            t[0] = (uint8_t)(127 + nweights);
+            for (uint32_t i = 0; i < nweights; i += 2) {
+                const uint32_t l0 = ctab[i] >> 16, l1 = i + 1 < nweights ? ctab[i + 1] >> 16 : 0;
+                const uint32_t w0 = l0 ? max_len + 1 - l0 : 0, w1 = l1 ? max_len + 1 - l1 : 0;
+                t[1 + i / 2] = (uint8_t)((w0 << 4) | w1);
+            }
         }
         uint8_t* j = t + tree_bytes;
         j[0] = (uint8_t)ssz[0]; j[1] = (uint8_t)(ssz[0] >> 8);
