@@ -238,6 +238,36 @@ def test_single_process_multi_device_context():
     c.close(); one.close()
 
 
+@pytest.mark.parametrize("shape", ["skewed_high_bytes", "gauss_around_128", "alphabet_200", "period_1000", "long_runs"])
+def test_zstd_binary_payload_shapes(ctx, shape):
+    # binary Kafka payloads: alphabets above byte value 128 (FSE-compressed Huffman weights), literal-only blocks
+    # (zero sequences), long-distance repeats and long runs (warp-wide match extension)
+    rng = np.random.default_rng(42)
+    n, cs = 2 * 4 * MIB + 4097, 4 * MIB
+    if shape == "skewed_high_bytes":
+        src = (255 - np.minimum(rng.geometric(0.15, n), 120)).astype(np.uint8)
+    elif shape == "gauss_around_128":
+        src = np.clip(rng.normal(128, 20, n), 0, 255).astype(np.uint8)
+    elif shape == "alphabet_200":
+        src = rng.integers(0, 200, n).astype(np.uint8)
+    elif shape == "period_1000":
+        src = np.tile(rng.integers(0, 256, 1000, dtype=np.uint8), n // 1000 + 1)[:n].copy()
+    else:
+        src = np.repeat(rng.integers(0, 256, n // 3000 + 1, dtype=np.uint8), 3000)[:n].copy()
+    got, gs = ctx.transform(Z, src, cs)
+    pos = 0
+    for i, s in enumerate(gs):
+        assert ora.zstd_decompress_chunk(got[pos:pos + s]) == src[i * cs:min(n, (i + 1) * cs)].tobytes()
+        pos += s
+    if shape in ("skewed_high_bytes", "gauss_around_128", "period_1000", "long_runs"):
+        assert sum(gs) < 0.9 * n
+    back, _ = ctx.detransform(Z, got, gs, n)
+    assert np.array_equal(back, src)
+    ref, rs = ora.transform_segment(Z, src, cs)
+    back, _ = ctx.detransform(Z, ref, rs, n)
+    assert np.array_equal(back, src)
+
+
 def test_index_files_ride_one_ragged_batch(ctx):
     # RemoteStorageManager.transformIndex (RemoteStorageManager.java:455-490): each Kafka index file is ONE chunk,
     # encryption only; fetchIndexBytes (:624-652) reads one back
