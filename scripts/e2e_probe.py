@@ -12,7 +12,7 @@ src = corpus.gen_segment(kind, 0, seg, cs)
 h_src = torch.empty(seg, dtype=torch.uint8).pin_memory(); h_src.numpy()[:] = src
 key, aad, ivs = corpus.fixed_key_material(nch)
 for flags in (3, 2):
-    for mb in (8, 16, 32):
+    for mb in (2, 4, 8):
         ctx = tsgpu.Context(max_chunk_bytes=cs, max_batch=mb)
         cap = int(ctx.lib.tsgpu_transform_bound(flags, seg, cs)) + 64
         h_dst = torch.empty(cap, dtype=torch.uint8).pin_memory(); d = h_dst.numpy()

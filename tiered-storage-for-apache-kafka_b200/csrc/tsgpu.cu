@@ -57,6 +57,7 @@ struct Work {
     rt::stream_t stream{};
     rt::event_t ev_sizes{}, ev_done{};
     bool busy = false, ready = false;
+    uint64_t key_epoch = 0;        // host call whose key this slot's GcmKeyCtx currently holds
     uint8_t* d_orig = nullptr;     // max_batch * chunk_cap
     uint8_t* d_frames = nullptr;   // max_batch * frame_stride        (zstd frames, 16-byte aligned slots)
     uint8_t* d_xf = nullptr;       // max_batch * slot_stride         (transformed slots)
@@ -81,6 +82,7 @@ struct tsgpu_ctx {
     uint32_t chunk_cap = 0, max_batch = 0;
     uint64_t frame_stride = 0, slot_stride = 0;
     LaunchProf prof;
+    uint64_t call_epoch = 0;       // one key per host call: a slot builds its H tables once per call, not once per batch
 };
 
 static void carve_desc(uint8_t* base, uint32_t nb, Desc& d, size_t* total) {
@@ -268,7 +270,9 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
         xb.final_base = w.d_frames; xb.final_stride = c->frame_stride; xb.final_head = 0;
     }
     if (flags & TSGPU_FLAG_AES) {
-        int rc = gcm_stage<true>(c, w, st, rk, false, cur_base, cur_off, cur_len, w.d_xf, w.dd.c_off, w.dd.c_len,
+        const bool key_ready = w.key_epoch == c->call_epoch;
+        w.key_epoch = c->call_epoch;
+        int rc = gcm_stage<true>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, w.d_xf, w.dd.c_off, w.dd.c_len,
                                  w.dd.ivs, w.dd.aad, aad_len, w.dd.status, nb, cur_max, w.d_partials, w.max_ranges);
         if (rc) return rc;
         cur_len = w.dd.c_len;
@@ -353,6 +357,7 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
     }
     Aes256RoundKeys rk{};
     if (flags & TSGPU_FLAG_AES) rk = aes256_expand_key(key);
+    c->call_epoch++;
 
     const uint32_t nbatches = (n + c->max_batch - 1) / c->max_batch;
     const uint32_t nwork = (uint32_t)c->lanes.size() * NSLOT;
@@ -433,7 +438,9 @@ static int detransform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_
         uint8_t* ob = z ? w.d_frames : w.d_orig;
         const uint64_t* oo = z ? w.dd.b_off : w.dd.a_off;
         uint32_t* ol = z ? w.dd.b_len : w.dd.a_len;
-        int rc = gcm_stage<false>(c, w, st, rk, false, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
+        const bool key_ready = w.key_epoch == c->call_epoch;
+        w.key_epoch = c->call_epoch;
+        int rc = gcm_stage<false>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
                                   w.dd.status, nb, max_t, w.d_partials, w.max_ranges);
         if (rc) return rc;
         cur_base = ob; cur_off = oo; cur_len = ol;
@@ -476,6 +483,7 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     }
     Aes256RoundKeys rk{};
     if (flags & TSGPU_FLAG_AES) rk = aes256_expand_key(key);
+    c->call_epoch++;
 
     const uint32_t nbatches = (n_chunks + c->max_batch - 1) / c->max_batch;
     const uint32_t nwork = (uint32_t)c->lanes.size() * NSLOT;
