@@ -7,6 +7,7 @@ NVCCFLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -X
 HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h $(CSRC)/*.hpp) include/tsgpu.h
 
 all: $(PKG)/libtsgpu.so oracle tests/simt/libtsgpu_simt.so
+libtsgpu.so: $(PKG)/libtsgpu.so
 
 $(PKG)/libtsgpu.so: $(CSRC)/tsgpu.cu $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/tsgpu.cu -lcudart 2> build_ptxas.log || (cat build_ptxas.log; false)
@@ -23,7 +24,7 @@ tests/simt/libtsgpu_simt.so: $(CSRC)/tsgpu.cu $(HDRS) tests/simt/simt.h tests/si
 clean:
 	rm -f $(PKG)/libtsgpu.so tests/simt/libtsgpu_simt.so build_ptxas.log
 	$(MAKE) -C oracle clean
-.PHONY: all oracle clean
+.PHONY: all oracle clean libtsgpu.so
 
 # C++ host-mirror tests: `_simt` links the test-only emulator build (CPU box), `_gpu` links the product library.
 tests/cpp/test_host_mirror_simt: tests/cpp/test_host_mirror.cpp $(PKG)/host/chunk_transform.hpp tests/simt/libtsgpu_simt.so oracle

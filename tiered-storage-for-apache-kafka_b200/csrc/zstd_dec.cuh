@@ -113,6 +113,13 @@ __device__ __forceinline__ uint32_t zd_back_read(ZdBack& b, uint32_t nb) {
     b.bits -= (int32_t)nb;
     return v;
 }
+// stateless: bits [end - nb, end) of a backward stream, nb <= 32, end - nb >= 0
+__device__ __forceinline__ uint32_t zd_bits_at(const uint8_t* p, int32_t end, uint32_t nb) {
+    if (nb == 0) return 0;
+    const int32_t base = max(0, ((end + 7) & ~7) - 64);
+    const uint64_t C = zd_ld64(p + (base >> 3));
+    return (uint32_t)(C >> (end - (int32_t)nb - base)) & (uint32_t)((1ull << nb) - 1);
+}
 // Forward LSB-first reader for FSE table descriptions
 struct ZdFwd { const uint8_t* p; uint32_t size; uint32_t bit; };
 __device__ __forceinline__ uint32_t zd_fwd_peek(const ZdFwd& f, uint32_t nb) {
@@ -188,7 +195,9 @@ __device__ TS_NOINLINE uint32_t zd_read_huf_table(const uint8_t* src, uint32_t s
             const int s = cx->symbol_of[u];
             const uint32_t ns = cx->next[s]++;
             const int nb = (int)log - zf::highbit32(ns);
-            T[u].nb_bits = (uint8_t)nb; T[u].next_base = (uint16_t)((ns << nb) - (1u << log)); T[u].nb_extra = (uint8_t)s; T[u].base = 0;
+            zf::FseDEntry e{};
+            e.nb_bits = (uint32_t)nb; e.next_base = (ns << nb) - (1u << log); e.nb_extra = (uint32_t)s;
+            T[u] = e;
         }
         ZdBack b;
         if (!zd_back_init(b, src + 1 + h, hb - h)) return 0;
@@ -288,12 +297,11 @@ __device__ __forceinline__ void zd_build_dtable_warp(int kind, ZdWarpCtx* cx, ui
         const uint32_t base = cx->next[sym];
         const uint32_t ns = base + rank;
         const int nb = (int)log - zf::highbit32(ns);
-        zf::FseDEntry e;
-        e.nb_bits = (uint8_t)nb;
-        e.next_base = (uint16_t)((ns << nb) - size);
-        if (kind == 0) { e.nb_extra = g_seq_tables.ll_bits[sym]; e.base = g_seq_tables.ll_base[sym]; }
-        else if (kind == 2) { e.nb_extra = g_seq_tables.ml_bits[sym]; e.base = g_seq_tables.ml_base[sym]; }
-        else { e.nb_extra = (uint8_t)sym; e.base = 1u << sym; }
+        zf::FseDEntry e{};
+        e.nb_bits = (uint32_t)nb;
+        e.next_base = (ns << nb) - size;
+        e.sym = sym;
+        e.nb_extra = kind == 0 ? g_seq_tables.ll_bits[sym] : kind == 2 ? g_seq_tables.ml_bits[sym] : sym;
         T[u] = e;
         __syncwarp();
         if (rank == 0) cx->next[sym] = (uint16_t)(base + (uint32_t)__popc(same));
@@ -481,72 +489,95 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
     }
     for (uint32_t s0 = 0; s0 < nseq; s0 += 32) {
         const uint32_t cnt = min(32u, nseq - s0);
+        // (1) lane 0 walks ONLY the state chain: per sequence three table entries, the bit count, three state updates.
+        //     It records where each sequence's bits end and which states it was decoded from.
         if (lane == 0) {
-            uint32_t r0 = cx->rep[0], r1 = cx->rep[1], r2 = cx->rep[2];
             for (uint32_t i = 0; i < cnt; i++) {
                 const zf::FseDEntry eo = cx->of[st_of], em = cx->ml[st_ml], el = cx->ll[st_ll];
+                cx->s_ll[i] = st_of | (st_ml << 10) | (st_ll << 20);
+                cx->s_ml[i] = (uint32_t)br.bits;
                 // Bits of one sequence, first read first: offset extra, match-length extra, literal-length extra, then
-                // (unless it is the last sequence) the LL, ML, OF state updates.  All six widths are known from the three
-                // table entries, so the fields are cut out of ONE cached 64-bit window instead of six dependent reads.
+                // (unless it is the last sequence) the LL, ML, OF state updates.
                 const bool upd = s0 + i + 1 < nseq;
                 const uint32_t u_ll = upd ? el.nb_bits : 0u, u_ml = upd ? em.nb_bits : 0u, u_of = upd ? eo.nb_bits : 0u;
-                const uint32_t total = (uint32_t)eo.nb_extra + em.nb_extra + el.nb_extra + u_ll + u_ml + u_of;
-                uint32_t ofv, ml, ll;
-                if (total <= 57 && br.bits >= (int32_t)total) {
-                    const int32_t lo = br.bits - (int32_t)total;
+                const uint32_t extra = (uint32_t)eo.nb_extra + em.nb_extra + el.nb_extra;
+                const uint32_t ubits = u_ll + u_ml + u_of;
+                br.bits -= (int32_t)extra;
+                if (br.bits < (int32_t)ubits) { if (br.bits < 0 || upd) { cx->err = -1; break; } }
+                if (upd) {
+                    const int32_t lo = br.bits - (int32_t)ubits;           // ubits <= 27: one cached window
                     if (lo < br.cbase || br.bits > br.cbase + 64) {
                         br.cbase = max(0, ((br.bits + 7) & ~7) - 64);
                         br.C = zd_ld64(br.p + (br.cbase >> 3));
                     }
-                    const uint64_t W = br.C >> (lo - br.cbase);
-                    uint32_t sh = total - eo.nb_extra;
-                    ofv = eo.base + ((uint32_t)(W >> sh) & (uint32_t)((1ull << eo.nb_extra) - 1));
-                    sh -= em.nb_extra;
-                    ml = em.base + ((uint32_t)(W >> sh) & ((1u << em.nb_extra) - 1));
-                    sh -= el.nb_extra;
-                    ll = el.base + ((uint32_t)(W >> sh) & ((1u << el.nb_extra) - 1));
-                    if (upd) {
-                        st_ll = el.next_base + ((uint32_t)(W >> (u_ml + u_of)) & ((1u << u_ll) - 1));
-                        st_ml = em.next_base + ((uint32_t)(W >> u_of) & ((1u << u_ml) - 1));
-                        st_of = eo.next_base + ((uint32_t)W & ((1u << u_of) - 1));
-                    }
+                    const uint32_t W = (uint32_t)(br.C >> (lo - br.cbase));
+                    st_ll = el.next_base + ((W >> (u_ml + u_of)) & ((1u << u_ll) - 1));
+                    st_ml = em.next_base + ((W >> u_of) & ((1u << u_ml) - 1));
+                    st_of = eo.next_base + (W & ((1u << u_of) - 1));
                     br.bits = lo;
-                } else {                                 // wide sequences (long offsets) or the tail of the stream: field by field
-                    ofv = eo.base + (eo.nb_extra ? zd_back_read(br, eo.nb_extra) : 0);
-                    ml = em.base + (em.nb_extra ? zd_back_read(br, em.nb_extra) : 0);
-                    ll = el.base + (el.nb_extra ? zd_back_read(br, el.nb_extra) : 0);
-                    if (upd) {
-                        st_ll = el.next_base + zd_back_read(br, el.nb_bits);
-                        st_ml = em.next_base + zd_back_read(br, em.nb_bits);
-                        st_of = eo.next_base + zd_back_read(br, eo.nb_bits);
-                    }
                 }
-                uint32_t off;
-                if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
-                else {
-                    if (fast_nonfirst) { cx->err = 1; break; }       // repeat offsets carried into the block
-                    const uint32_t idx = ofv - 1 + (ll == 0 ? 1 : 0);    // 0: rep1, 1: rep2, 2: rep3, 3: rep1 - 1
-                    if (idx == 0) off = r0;
-                    else {
-                        uint32_t t = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
-                        if (t == 0) { cx->err = -1; break; }
-                        if (idx != 1) r2 = r1;
-                        r1 = r0; r0 = t; off = t;
-                    }
-                }
-                cx->s_ll[i] = ll; cx->s_ml[i] = ml; cx->s_off[i] = off;
-                if (br.bits < 0) { cx->err = -1; break; }
             }
-            cx->rep[0] = r0; cx->rep[1] = r1; cx->rep[2] = r2;
         }
         __syncwarp();
         if (cx->err) return 0;
+        // (2) every lane cuts the three values of its own sequence out of the stream
+        const bool mine = lane < cnt;
+        uint32_t ll = 0, ml = 0, off = 1, ofv = 4;
+        if (mine) {
+            const uint32_t st = cx->s_ll[lane];
+            const int32_t end = (int32_t)cx->s_ml[lane];
+            const zf::FseDEntry eo = cx->of[st & 1023], em = cx->ml[(st >> 10) & 1023], el = cx->ll[st >> 20];
+            ofv = (1u << eo.sym) + zd_bits_at(bs, end, eo.nb_extra);
+            const uint32_t v = zd_bits_at(bs, end - (int32_t)eo.nb_extra, (uint32_t)em.nb_extra + el.nb_extra);
+            ml = g_seq_tables.ml_base[em.sym] + (v >> el.nb_extra);
+            ll = g_seq_tables.ll_base[el.sym] + (v & ((1u << el.nb_extra) - 1));
+            off = ofv - 3;
+        }
+        // (3) repeat offsets: batches without any (all of this compressor's) need no serial pass
+        const uint32_t rep_mask = __ballot_sync(TS_FULL, mine && ofv <= 3);
+        if (rep_mask == 0) {
+            const uint32_t o1 = __shfl_sync(TS_FULL, off, cnt - 1), o2 = __shfl_sync(TS_FULL, off, cnt >= 2 ? cnt - 2 : 0),
+                           o3 = __shfl_sync(TS_FULL, off, cnt >= 3 ? cnt - 3 : 0);
+            if (lane == 0) {
+                const uint32_t r0 = cx->rep[0], r1 = cx->rep[1];
+                cx->rep[2] = cnt >= 3 ? o3 : cnt == 2 ? r0 : r1;
+                cx->rep[1] = cnt >= 2 ? o2 : r0;
+                cx->rep[0] = o1;
+            }
+        } else {
+            if (fast_nonfirst) { if (lane == 0) cx->err = 1; __syncwarp(); return 0; }    // repeat offsets carried into the block
+            __syncwarp();
+            cx->s_off[lane] = ofv; cx->s_ml[lane] = ll;
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t r0 = cx->rep[0], r1 = cx->rep[1], r2 = cx->rep[2];
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const uint32_t v = cx->s_off[i];
+                    uint32_t o;
+                    if (v > 3) { o = v - 3; r2 = r1; r1 = r0; r0 = o; }
+                    else {
+                        const uint32_t idx = v - 1 + (cx->s_ml[i] == 0 ? 1 : 0);     // 0: rep1, 1: rep2, 2: rep3, 3: rep1 - 1
+                        if (idx == 0) o = r0;
+                        else {
+                            const uint32_t t = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
+                            if (t == 0) { cx->err = -1; break; }
+                            if (idx != 1) r2 = r1;
+                            r1 = r0; r0 = t; o = t;
+                        }
+                    }
+                    cx->s_off[i] = o;
+                }
+                cx->rep[0] = r0; cx->rep[1] = r1; cx->rep[2] = r2;
+            }
+            __syncwarp();
+            if (cx->err) return 0;
+            off = mine ? cx->s_off[lane] : 1;
+        }
+        __syncwarp();
         // ---- execute the batch: lane i owns sequence i.  Output/literal positions come from shuffle prefix sums;
         // literal runs are independent; a match may start once its source range lies inside the completed prefix
         // (multi-round resolution: far matches of a batch all copy at once, so their memory latency overlaps).
         {
-            const bool mine = lane < cnt;
-            const uint32_t ll = mine ? cx->s_ll[lane] : 0, ml = mine ? cx->s_ml[lane] : 0, off = mine ? cx->s_off[lane] : 1;
             const uint32_t inc_o = warp_inclusive_scan_u32(ll + ml, lane), inc_l = warp_inclusive_scan_u32(ll, lane);
             const uint32_t tot_o = __shfl_sync(TS_FULL, inc_o, 31), tot_l = __shfl_sync(TS_FULL, inc_l, 31);
             const uint32_t o_start = op + inc_o - ll - ml, l_start = lp + inc_l - ll, m_start = o_start + ll;

@@ -63,12 +63,16 @@ __host__ __device__ inline int highbit32(uint32_t v) {       // v != 0
 }
 
 // ---- FSE decoding table entry (sequence flavour: carries the code's base value and extra-bit count) ----
+// One 32-bit word per cell: the state chain needs next_base / nb_bits / nb_extra only; the code's base value is looked
+// up from `sym` by whoever cuts the extra bits out of the stream (ll_base / ml_base / 1 << ofCode).
 struct FseDEntry {
-    uint16_t next_base;     // new state = next_base + read(nb_bits)
-    uint8_t nb_bits;
-    uint8_t nb_extra;       // additional bits of the code (LL_bits / ML_bits / offset code)
-    uint32_t base;          // base value of the code (literal length / match length / 1<<ofCode)
+    uint32_t next_base : 10;    // new state = next_base + read(nb_bits)
+    uint32_t nb_bits : 4;
+    uint32_t nb_extra : 5;      // additional bits of the code (LL_bits / ML_bits / offset code)
+    uint32_t sym : 6;           // the code itself
+    uint32_t pad : 7;
 };
+static_assert(sizeof(FseDEntry) == 4, "FSE decoding cell is one word");
 
 // Spread + state assignment of RFC 8878 §4.1.1 (same procedure libzstd's FSE_buildDTable follows).
 // symbol_of[] is scratch of table_size bytes; next[] scratch of nsym uint16.
@@ -98,22 +102,19 @@ __host__ __device__ inline void fse_build_dtable(const int16_t* norm, int nsym, 
         const int s = symbol_of[u];
         const uint32_t ns = next[s]++;
         const int nb = log - highbit32(ns);
-        FseDEntry e;
-        e.nb_bits = (uint8_t)nb;
-        e.next_base = (uint16_t)((ns << nb) - size);
-        if (kind == 0) { e.nb_extra = st.ll_bits[s]; e.base = st.ll_base[s]; }
-        else if (kind == 2) { e.nb_extra = st.ml_bits[s]; e.base = st.ml_base[s]; }
-        else { e.nb_extra = (uint8_t)s; e.base = 1u << s; }
+        FseDEntry e{};
+        e.nb_bits = (uint32_t)nb;
+        e.next_base = (ns << nb) - size;
+        e.sym = (uint32_t)s;
+        e.nb_extra = kind == 0 ? st.ll_bits[s] : kind == 2 ? st.ml_bits[s] : (uint32_t)s;
         table[u] = e;
     }
 }
 // RLE mode: a single-entry table
 __host__ __device__ inline void fse_build_rle(int sym, int kind, const SeqTables& st, FseDEntry* table) {
-    FseDEntry e;
-    e.nb_bits = 0; e.next_base = 0;
-    if (kind == 0) { e.nb_extra = st.ll_bits[sym]; e.base = st.ll_base[sym]; }
-    else if (kind == 2) { e.nb_extra = st.ml_bits[sym]; e.base = st.ml_base[sym]; }
-    else { e.nb_extra = (uint8_t)sym; e.base = 1u << sym; }
+    FseDEntry e{};
+    e.sym = (uint32_t)sym;
+    e.nb_extra = kind == 0 ? st.ll_bits[sym] : kind == 2 ? st.ml_bits[sym] : (uint32_t)sym;
     table[0] = e;
 }
 
