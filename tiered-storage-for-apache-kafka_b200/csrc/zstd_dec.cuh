@@ -492,31 +492,41 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
         // (1) lane 0 walks ONLY the state chain: per sequence three table entries, the bit count, three state updates.
         //     It records where each sequence's bits end and which states it was decoded from.
         if (lane == 0) {
-            for (uint32_t i = 0; i < cnt; i++) {
-                const zf::FseDEntry eo = cx->of[st_of], em = cx->ml[st_ml], el = cx->ll[st_ll];
+            const uint32_t* tof = (const uint32_t*)cx->of; const uint32_t* tml = (const uint32_t*)cx->ml; const uint32_t* tll = (const uint32_t*)cx->ll;
+            const uint32_t n_upd = min(cnt, nseq - 1 - s0);          // sequences of this batch that are followed by another one
+            int32_t bits = br.bits;
+            bool bad = false;
+            uint32_t i = 0;
+            for (; i < n_upd; i++) {
+                // Bits of one sequence, first read first: offset extra, match-length extra, literal-length extra, then the
+                // LL, ML, OF state updates (<= 27 bits: one cached window).
+                const uint32_t eo = tof[st_of], em = tml[st_ml], el = tll[st_ll];
                 cx->s_ll[i] = st_of | (st_ml << 10) | (st_ll << 20);
-                cx->s_ml[i] = (uint32_t)br.bits;
-                // Bits of one sequence, first read first: offset extra, match-length extra, literal-length extra, then
-                // (unless it is the last sequence) the LL, ML, OF state updates.
-                const bool upd = s0 + i + 1 < nseq;
-                const uint32_t u_ll = upd ? el.nb_bits : 0u, u_ml = upd ? em.nb_bits : 0u, u_of = upd ? eo.nb_bits : 0u;
-                const uint32_t extra = (uint32_t)eo.nb_extra + em.nb_extra + el.nb_extra;
-                const uint32_t ubits = u_ll + u_ml + u_of;
-                br.bits -= (int32_t)extra;
-                if (br.bits < (int32_t)ubits) { if (br.bits < 0 || upd) { cx->err = -1; break; } }
-                if (upd) {
-                    const int32_t lo = br.bits - (int32_t)ubits;           // ubits <= 27: one cached window
-                    if (lo < br.cbase || br.bits > br.cbase + 64) {
-                        br.cbase = max(0, ((br.bits + 7) & ~7) - 64);
-                        br.C = zd_ld64(br.p + (br.cbase >> 3));
-                    }
-                    const uint32_t W = (uint32_t)(br.C >> (lo - br.cbase));
-                    st_ll = el.next_base + ((W >> (u_ml + u_of)) & ((1u << u_ll) - 1));
-                    st_ml = em.next_base + ((W >> u_of) & ((1u << u_ml) - 1));
-                    st_of = eo.next_base + (W & ((1u << u_of) - 1));
-                    br.bits = lo;
+                cx->s_ml[i] = (uint32_t)bits;
+                const uint32_t t = eo + em + el;                     // bits 0..5: state-update bits, bits 6..11: extra bits
+                bits -= (int32_t)((t >> 6) & 63);
+                const int32_t lo = bits - (int32_t)(t & 63);
+                if (lo < 0) { bad = true; break; }
+                if (lo < br.cbase || bits > br.cbase + 64) {
+                    br.cbase = max(0, ((bits + 7) & ~7) - 64);
+                    br.C = zd_ld64(br.p + (br.cbase >> 3));
                 }
+                uint32_t W = (uint32_t)(br.C >> (lo - br.cbase));
+                const uint32_t u_of = eo & 63, u_ml = em & 63, u_ll = el & 63;
+                st_of = (eo >> 18) + (W & ((1u << u_of) - 1)); W >>= u_of;
+                st_ml = (em >> 18) + (W & ((1u << u_ml) - 1)); W >>= u_ml;
+                st_ll = (el >> 18) + (W & ((1u << u_ll) - 1));
+                bits = lo;
             }
+            if (!bad && i < cnt) {                                   // the block's last sequence: values only
+                const uint32_t t = tof[st_of] + tml[st_ml] + tll[st_ll];
+                cx->s_ll[i] = st_of | (st_ml << 10) | (st_ll << 20);
+                cx->s_ml[i] = (uint32_t)bits;
+                bits -= (int32_t)((t >> 6) & 63);
+                if (bits < 0) bad = true;
+            }
+            br.bits = bits;
+            if (bad) cx->err = -1;
         }
         __syncwarp();
         if (cx->err) return 0;
@@ -592,7 +602,15 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
             {
                 const uint32_t quick = min(ll, 32u);
                 if (rle_lit < 0x100) { for (uint32_t k = 0; k < quick; k++) dst[o_start + k] = (uint8_t)rle_lit; }
-                else { for (uint32_t k = 0; k < quick; k++) dst[o_start + k] = lit[l_start + k]; }
+                else {                                       // four loads in flight per step (lit and dst never alias)
+                    const uint8_t* ls = lit + l_start; uint8_t* ld = dst + o_start;
+                    uint32_t k = 0;
+                    for (; k + 4 <= quick; k += 4) {
+                        const uint8_t b0 = ls[k], b1 = ls[k + 1], b2 = ls[k + 2], b3 = ls[k + 3];
+                        ld[k] = b0; ld[k + 1] = b1; ld[k + 2] = b2; ld[k + 3] = b3;
+                    }
+                    for (; k < quick; k++) ld[k] = ls[k];
+                }
                 uint32_t longs = __ballot_sync(TS_FULL, ll > 32);
                 while (longs) {
                     const uint32_t f = (uint32_t)__ffs((int)longs) - 1;
@@ -615,7 +633,14 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
                 uint8_t* d = dst + m_start;
                 const uint8_t* m = d - off;
                 if (ready && ml <= 64) {
-                    for (uint32_t k = 0; k < ml; k++) d[k] = m[k];                       // byte-serial: overlap (off < ml) is fine
+                    uint32_t k = 0;
+                    if (off >= 4) {                              // the four source bytes of a step all precede its first store
+                        for (; k + 4 <= ml; k += 4) {
+                            const uint8_t b0 = m[k], b1 = m[k + 1], b2 = m[k + 2], b3 = m[k + 3];
+                            d[k] = b0; d[k + 1] = b1; d[k + 2] = b2; d[k + 3] = b3;
+                        }
+                    }
+                    for (; k < ml; k++) d[k] = m[k];             // byte-serial: overlap (off < ml) is fine
                     done = true;
                 }
                 uint32_t big = __ballot_sync(TS_FULL, ready && ml > 64);

@@ -65,12 +65,12 @@ __host__ __device__ inline int highbit32(uint32_t v) {       // v != 0
 // ---- FSE decoding table entry (sequence flavour: carries the code's base value and extra-bit count) ----
 // One 32-bit word per cell: the state chain needs next_base / nb_bits / nb_extra only; the code's base value is looked
 // up from `sym` by whoever cuts the extra bits out of the stream (ll_base / ml_base / 1 << ofCode).
-struct FseDEntry {
+struct FseDEntry {              // field order is the bit layout (LSB first) the decoder's state chain relies on:
+    uint32_t nb_bits : 6;       //   the sum of three cells' words carries sum(nb_bits) in bits 0..5 (<= 27) and
+    uint32_t nb_extra : 6;      //   sum(nb_extra) in bits 6..11 (<= 63); next_base needs no mask (word >> 18)
+    uint32_t sym : 6;           // the code itself; nb_extra = additional bits of the code (LL_bits / ML_bits / offset code)
     uint32_t next_base : 10;    // new state = next_base + read(nb_bits)
-    uint32_t nb_bits : 4;
-    uint32_t nb_extra : 5;      // additional bits of the code (LL_bits / ML_bits / offset code)
-    uint32_t sym : 6;           // the code itself
-    uint32_t pad : 7;
+    uint32_t pad : 4;
 };
 static_assert(sizeof(FseDEntry) == 4, "FSE decoding cell is one word");
 
