@@ -355,7 +355,7 @@ def main_tsgpu(args):
     # ---- e2e: the host-buffer C-ABI call (pinned src/dst), H2D + kernels + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
-        ectx = tsgpu.Context(max_chunk_bytes=cs, max_batch=8, devices=[local])
+        ectx = tsgpu.Context(max_chunk_bytes=cs, max_batch=4, devices=[local])
         cap = int(ectx.lib.tsgpu_transform_bound(flags, seg, cs)) + 64
         h_dst = torch.empty(cap, dtype=torch.uint8).pin_memory()
         dst_np = h_dst.numpy()

@@ -11,16 +11,18 @@ kind = sys.argv[1] if len(sys.argv) > 1 else 'K'
 src = corpus.gen_segment(kind, 0, seg, cs)
 h_src = torch.empty(seg, dtype=torch.uint8).pin_memory(); h_src.numpy()[:] = src
 key, aad, ivs = corpus.fixed_key_material(nch)
-for flags in (3, 2):
-    for mb in (2, 4, 8):
+import os
+for flags, slots, split, mb in ((3, 8, 1, 4), (3, 16, 1, 4), (3, 16, 1, 2), (3, 12, 1, 4), (3, 8, 1, 2), (3, 16, 1, 1), (3, 8, 0, 4), (1, 8, 1, 4), (2, 8, 1, 4), (2, 16, 1, 2)):
+    if True:
+        os.environ['TSGPU_SLOTS'] = str(slots); os.environ['TSGPU_SPLIT_OUT'] = str(split)
         ctx = tsgpu.Context(max_chunk_bytes=cs, max_batch=mb)
         cap = int(ctx.lib.tsgpu_transform_bound(flags, seg, cs)) + 64
         h_dst = torch.empty(cap, dtype=torch.uint8).pin_memory(); d = h_dst.numpy()
         for _ in range(2): ctx.transform(flags, h_src.numpy(), cs, key, aad, ivs, dst=d)
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        for _ in range(3): out, sizes = ctx.transform(flags, h_src.numpy(), cs, key, aad, ivs, dst=d)
-        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 3
-        print('flags', flags, 'batch', mb, 'e2e %.1f GiB/s' % (1.0 / dt), 'out MiB', sum(sizes) // MIB, flush=True)
+        for _ in range(4): out, sizes = ctx.transform(flags, h_src.numpy(), cs, key, aad, ivs, dst=d)
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 4
+        print('flags', flags, 'slots', slots, 'split', split, 'batch', mb, 'e2e %.1f GiB/s' % (1.0 / dt), 'out MiB', sum(sizes) // MIB, flush=True)
         ctx.close(); del h_dst
 # raw copy ceilings
 d_buf = torch.empty(seg, dtype=torch.uint8, device='cuda')

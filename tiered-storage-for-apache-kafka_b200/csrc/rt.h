@@ -30,6 +30,7 @@ inline const char* event_create(event_t* e) { *e = 0; return nullptr; }
 inline void event_destroy(event_t) {}
 inline const char* event_record(event_t, stream_t) { return nullptr; }
 inline const char* event_sync(event_t) { return nullptr; }
+inline const char* stream_wait_event(stream_t, event_t) { return nullptr; }
 inline const char* last_error() { return nullptr; }
 typedef int tevent_t;
 inline void tevent_create(tevent_t*) {}
@@ -64,6 +65,7 @@ inline const char* event_create(event_t* e) { return err(cudaEventCreateWithFlag
 inline void event_destroy(event_t e) { if (e) cudaEventDestroy(e); }
 inline const char* event_record(event_t e, stream_t s) { return err(cudaEventRecord(e, s)); }
 inline const char* event_sync(event_t e) { return err(cudaEventSynchronize(e)); }
+inline const char* stream_wait_event(stream_t s, event_t e) { return err(cudaStreamWaitEvent(s, e, 0)); }
 inline const char* last_error() { return err(cudaGetLastError()); }
 typedef cudaEvent_t tevent_t;
 inline void tevent_create(tevent_t* e) { cudaEventCreate(e); }

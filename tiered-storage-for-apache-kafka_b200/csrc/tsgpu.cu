@@ -43,7 +43,7 @@ static inline uint64_t frame_bound(uint64_t n) { return n + (n >> 8) + 64; }   /
 // ------------------------------------------------------------------------------------------ context
 namespace {
 
-constexpr int NSLOT = 4;
+constexpr int NSLOT_MAX = 16;       // work slots per device; tsgpu_ctx::nslot of them are used
 constexpr uint32_t MAX_AAD = 4096;
 
 struct Desc {            // device-side descriptor block of one work slot (all arrays sized for max_batch)
@@ -54,8 +54,9 @@ struct Desc {            // device-side descriptor block of one work slot (all a
 
 struct Work {
     int device = 0;
-    rt::stream_t stream{};
+    rt::stream_t stream{}, out_stream{};   // out_stream: copies of finished chunks back to the host
     rt::event_t ev_sizes{}, ev_done{};
+    bool out_pending = false;              // a copy-out on out_stream still reads this slot's final buffer
     bool busy = false, ready = false;
     uint64_t key_epoch = 0;        // host call whose key this slot's GcmKeyCtx currently holds
     uint8_t* d_orig = nullptr;     // max_batch * chunk_cap
@@ -72,7 +73,7 @@ struct Work {
     uint32_t c0 = 0, nb = 0;
 };
 
-struct Lane { int device = 0; Work w[NSLOT]; };
+struct Lane { int device = 0; Work w[NSLOT_MAX]; };
 
 }  // namespace
 
@@ -82,6 +83,8 @@ struct tsgpu_ctx {
     uint32_t chunk_cap = 0, max_batch = 0;
     uint64_t frame_stride = 0, slot_stride = 0;
     LaunchProf prof;
+    uint32_t nslot = 8;            // work slots per device in flight (TSGPU_SLOTS overrides; measured best with batches of 4 x 4 MiB)
+    bool split_out = true;         // copies-out ride their own stream (the slot's next batch starts behind an event, not behind them)
     uint64_t call_epoch = 0;       // one key per host call: a slot builds its H tables once per call, not once per batch
 };
 
@@ -99,6 +102,7 @@ static int work_init(tsgpu_ctx* c, Work& w, int device) {
     w.device = device; w.ready = true;
     RT(rt::set_device(device));
     RT(rt::stream_create(&w.stream));
+    RT(rt::stream_create(&w.out_stream));
     RT(rt::event_create(&w.ev_sizes));
     RT(rt::event_create(&w.ev_done));
     const uint64_t nb = c->max_batch;
@@ -125,12 +129,13 @@ static void work_free(Work& w) {
     if (!w.stream && !w.d_orig) return;                 // never initialised
     rt::set_device(w.device);
     if (w.stream) rt::stream_sync(w.stream);
+    if (w.out_stream) rt::stream_sync(w.out_stream);
     rt::free_device(w.d_orig); rt::free_device(w.d_frames); rt::free_device(w.d_xf);
     rt::free_device(w.d_desc); rt::free_host(w.h_desc);
     rt::free_device(w.d_partials); rt::free_device(w.d_keyctx); rt::free_host(w.h_sizes);
     zstd_enc_scratch_free(w.zenc); zstd_dec_scratch_free(w.zdec);
     rt::event_destroy(w.ev_sizes); rt::event_destroy(w.ev_done);
-    rt::stream_destroy(w.stream);
+    rt::stream_destroy(w.stream); rt::stream_destroy(w.out_stream);
 }
 
 extern "C" uint64_t tsgpu_slot_stride(uint32_t flags, uint32_t chunk_size) {
@@ -165,6 +170,8 @@ extern "C" int tsgpu_create(const int* device_ids, int n_devices, uint32_t max_c
     tsgpu_ctx* c = new (std::nothrow) tsgpu_ctx();
     if (!c) return fail(TSGPU_E_NOMEM, "out of memory");
     c->chunk_cap = max_chunk_bytes; c->max_batch = max_batch;
+    if (const char* e = getenv("TSGPU_SLOTS")) { int v = atoi(e); if (v >= 1 && v <= NSLOT_MAX) c->nslot = (uint32_t)v; }       // tuning knobs
+    if (const char* e = getenv("TSGPU_SPLIT_OUT")) c->split_out = atoi(e) != 0;
     c->frame_stride = align_up(frame_bound(max_chunk_bytes), 16) + 16;
     c->slot_stride = tsgpu_slot_stride(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES, max_chunk_bytes);
     c->lanes.resize(ids.size());
@@ -230,6 +237,13 @@ static int gcm_stage(tsgpu_ctx* c, Work& w, rt::stream_t st, const Aes256RoundKe
     return TSGPU_OK;
 }
 
+// A slot's next batch may start (copy-in, early kernels) while the previous batch's chunks are still going out on
+// out_stream; the first kernel that overwrites the buffer they are read from waits for them here.
+static int wait_copies_out(Work& w, rt::stream_t st) {
+    if (w.out_pending) { RT(rt::stream_wait_event(st, w.ev_done)); w.out_pending = false; }
+    return TSGPU_OK;
+}
+
 // ------------------------------------------------------------------------------------------ transform (host)
 namespace {
 struct XfBatch {            // one in-flight transform batch
@@ -264,6 +278,7 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
     uint32_t cur_max = cs;
     xb.final_base = w.d_orig; xb.final_stride = cs; xb.final_head = 0;
     if (flags & TSGPU_FLAG_ZSTD) {
+        if (!(flags & TSGPU_FLAG_AES)) { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }   // d_frames is the final buffer
         int rc = zstd_compress_batch(w.zenc, st, cur_base, cur_off, cur_len, nb, cs, w.d_frames, w.dd.b_off, w.dd.b_len, c->prof);
         if (rc) return fail(rc, "zstd compress: %s", zstd_last_error());
         cur_base = w.d_frames; cur_off = w.dd.b_off; cur_len = w.dd.b_len; cur_max = (uint32_t)frame_bound(cs);
@@ -272,6 +287,7 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
     if (flags & TSGPU_FLAG_AES) {
         const bool key_ready = w.key_epoch == c->call_epoch;
         w.key_epoch = c->call_epoch;
+        { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }                                  // d_xf is the final buffer
         int rc = gcm_stage<true>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, w.d_xf, w.dd.c_off, w.dd.c_len,
                                  w.dd.ivs, w.dd.aad, aad_len, w.dd.status, nb, cur_max, w.d_partials, w.max_ranges);
         if (rc) return rc;
@@ -360,24 +376,26 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
     c->call_epoch++;
 
     const uint32_t nbatches = (n + c->max_batch - 1) / c->max_batch;
-    const uint32_t nwork = (uint32_t)c->lanes.size() * NSLOT;
+    const uint32_t nwork = (uint32_t)c->lanes.size() * c->nslot;
     std::vector<XfBatch> inflight(nbatches);
     uint64_t dst_off = 0;
     int rc = TSGPU_OK;
-    auto work_of = [&](uint32_t b) -> Work& { return c->lanes[b % c->lanes.size()].w[(b / c->lanes.size()) % NSLOT]; };
+    auto work_of = [&](uint32_t b) -> Work& { return c->lanes[b % c->lanes.size()].w[(b / c->lanes.size()) % c->nslot]; };
     auto drain = [&](uint32_t b) -> int {        // sizes of batch b are ready -> copy its chunks out, in order
         XfBatch& xb = inflight[b];
         Work& w = *xb.w;
         RT(rt::set_device(w.device));
         RT(rt::event_sync(w.ev_sizes));
+        rt::stream_t os = c->split_out ? w.out_stream : w.stream;    // the sizes event has completed: nothing to order on out_stream
         for (uint32_t i = 0; i < xb.nb; i++) {
             uint32_t sz = w.h_sizes[i];
             if (dst_off + sz > dst_cap) return fail(TSGPU_E_SHORT, "dst too small");
-            RT(rt::d2h(dst + dst_off, xb.final_base + (uint64_t)i * xb.final_stride + xb.final_head, sz, w.stream));
+            RT(rt::d2h(dst + dst_off, xb.final_base + (uint64_t)i * xb.final_stride + xb.final_head, sz, os));
             transformed_sizes[xb.c0 + i] = sz;
             dst_off += sz;
         }
-        RT(rt::event_record(w.ev_done, w.stream));
+        RT(rt::event_record(w.ev_done, os));
+        w.out_pending = c->split_out;
         return TSGPU_OK;
     };
     uint32_t drained = 0;
@@ -396,8 +414,9 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
     for (auto& l : c->lanes) for (auto& w : l.w) if (w.busy) {   // always leave the context idle
         rt::set_device(w.device);
         const char* e = rt::stream_sync(w.stream);
+        if (!e) e = rt::stream_sync(w.out_stream);
         if (e && rc == TSGPU_OK) rc = fail(TSGPU_E_CUDA, "stream_sync: %s", e);
-        w.busy = false;
+        w.busy = false; w.out_pending = false;
     }
     if (rc) return rc;
     *n_chunks = n;
@@ -440,12 +459,14 @@ static int detransform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_
         uint32_t* ol = z ? w.dd.b_len : w.dd.a_len;
         const bool key_ready = w.key_epoch == c->call_epoch;
         w.key_epoch = c->call_epoch;
+        if (!z) { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }                          // d_orig is the final buffer
         int rc = gcm_stage<false>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
                                   w.dd.status, nb, max_t, w.d_partials, w.max_ranges);
         if (rc) return rc;
         cur_base = ob; cur_off = oo; cur_len = ol;
     }
     if (flags & TSGPU_FLAG_ZSTD) {
+        { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }
         int rc = zstd_decompress_batch(w.zdec, st, cur_base, cur_off, cur_len, nb, c->chunk_cap,
                                        w.d_orig, w.dd.a_off, w.dd.a_len, w.dd.status, /*compute_offsets=*/true, c->prof);
         if (rc) return fail(rc, "zstd decompress: %s", zstd_last_error());
@@ -486,7 +507,7 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     c->call_epoch++;
 
     const uint32_t nbatches = (n_chunks + c->max_batch - 1) / c->max_batch;
-    const uint32_t nwork = (uint32_t)c->lanes.size() * NSLOT;
+    const uint32_t nwork = (uint32_t)c->lanes.size() * c->nslot;
     std::vector<DxBatch> inflight(nbatches);
     std::vector<uint64_t> in_pos(nbatches + 1, 0);
     for (uint32_t b = 0; b < nbatches; b++) {
@@ -496,7 +517,7 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     }
     uint64_t dst_off = 0;
     int rc = TSGPU_OK, soft = TSGPU_OK;
-    auto work_of = [&](uint32_t b) -> Work& { return c->lanes[b % c->lanes.size()].w[(b / c->lanes.size()) % NSLOT]; };
+    auto work_of = [&](uint32_t b) -> Work& { return c->lanes[b % c->lanes.size()].w[(b / c->lanes.size()) % c->nslot]; };
     auto drain = [&](uint32_t b) -> int {
         DxBatch& db = inflight[b];
         Work& w = *db.w;
@@ -512,9 +533,11 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
         }
         if (soft != TSGPU_OK) return soft;
         if (dst_off + total > dst_cap) return fail(TSGPU_E_SHORT, "dst too small");
-        if (total) RT(rt::d2h(dst + dst_off, w.d_orig, total, w.stream));
+        rt::stream_t os = c->split_out ? w.out_stream : w.stream;
+        if (total) RT(rt::d2h(dst + dst_off, w.d_orig, total, os));
         dst_off += total;
-        RT(rt::event_record(w.ev_done, w.stream));
+        RT(rt::event_record(w.ev_done, os));
+        w.out_pending = c->split_out;
         return TSGPU_OK;
     };
     uint32_t drained = 0;
@@ -530,8 +553,9 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     for (auto& l : c->lanes) for (auto& w : l.w) if (w.busy) {
         rt::set_device(w.device);
         const char* e = rt::stream_sync(w.stream);
+        if (!e) e = rt::stream_sync(w.out_stream);
         if (e && rc == TSGPU_OK) rc = fail(TSGPU_E_CUDA, "stream_sync: %s", e);
-        w.busy = false;
+        w.busy = false; w.out_pending = false;
     }
     if (rc == TSGPU_E_AUTH || rc == TSGPU_E_CORRUPT) {
         // JCE releases no plaintext when the tag check fails: do not leave partial output behind
