@@ -28,7 +28,7 @@
 namespace ts {
 
 constexpr uint32_t ZB = 8192;                  // bytes of original data per zstd block
-constexpr int ZE_HLOG = 10;                    // per-warp hash table: 2^10 x u32 (position + 1)
+constexpr int ZE_HLOG = 10;                    // per-warp hash table: 2^10 x u16 (position + 1)
 constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
 constexpr int ZE_WPB = 1;                      // warps (= blocks in flight) per CTA
 constexpr uint32_t ZE_MAXSEQ = ZB / 8;         // sequences kept per block; beyond that the rest goes out as literals
@@ -36,7 +36,8 @@ constexpr uint32_t ZE_MIN_MATCH = 5;           // a 4-byte match costs more bits
 constexpr uint32_t ZE_LANE_EXT = 12;           // bytes a lane extends its own match beyond the first 4
 constexpr uint32_t ZE_BUF_PAD = 160;
 constexpr uint32_t ZE_SLOT = ZB + 512;         // per-block output slot: 3-byte header + payload (< ZB once accepted; table descriptions are written before that is known)
-constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 4;   // buf, ht
+constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 2;   // buf, ht
+static_assert(ZB < 65535 && ZE_MAXSEQ <= 1024, "16-bit hash slots / 7-bit FSE tables assume small blocks");
 // per-tile FSE scratch (codes, state bits) lives in the tail of `buf`: the sequence bit stream staged there is at most
 // ZE_MAXSEQ * 58 bits, which ends below this offset
 constexpr uint32_t ZE_SEQ_AUX_OFF = ZB - 512;
@@ -116,8 +117,9 @@ struct ZeFseShared {      // per-CTA copy of the predefined encoding tables
 __device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict__ seqs, uint32_t N, uint32_t* bits, ZeCTab* ct,
                                                         uint8_t* codes /*[3][32]*/, uint16_t* stv /*[3][32]*/, uint8_t* stn /*[3][32]*/,
                                                         const ZeFseShared* fs, uint8_t* hdr_out, uint32_t* desc_bytes, uint32_t lane) {
-    // ---- pass 1: code histograms
-    for (uint32_t i = lane; i < ZE_NSYM_LL + ZE_NSYM_ML + ZE_NSYM_OF; i += 32) ct->cnt[i] = 0;
+    // ---- pass 1: code histograms (then normalised counts), in the word buffer beyond ze_build_kind's own scratch
+    uint32_t* cnt = bits + 256;
+    for (uint32_t i = lane; i < ZE_NSYM_LL + ZE_NSYM_ML + ZE_NSYM_OF; i += 32) cnt[i] = 0;
     __syncwarp();
     uint2 pre = lane < N ? seqs[lane] : make_uint2(0, 0);
     for (uint32_t t0 = 0; t0 < N; t0 += 32) {
@@ -125,20 +127,20 @@ __device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict_
         const uint2 s = pre;
         if (j + 32 < N) pre = seqs[j + 32];                  // next tile in flight while this one is counted
         if (j < N) {
-            atomicAdd(&ct->cnt[ze_ll_code(s.x & 0xffff)], 1u);
-            atomicAdd(&ct->cnt[ZE_NSYM_LL + ze_ml_code(s.x >> 16)], 1u);
-            atomicAdd(&ct->cnt[ZE_NSYM_LL + ZE_NSYM_ML + (uint32_t)zf::highbit32(s.y + 3)], 1u);
+            atomicAdd(&cnt[ze_ll_code(s.x & 0xffff)], 1u);
+            atomicAdd(&cnt[ZE_NSYM_LL + ze_ml_code(s.x >> 16)], 1u);
+            atomicAdd(&cnt[ZE_NSYM_LL + ZE_NSYM_ML + (uint32_t)zf::highbit32(s.y + 3)], 1u);
         }
     }
     __syncwarp();
     // ---- tables (descriptions in stream order LL, OF, ML); `bits` doubles as scratch until it is cleared
     ZeKind kll, kof, kml;
     uint8_t* desc = hdr_out + 1;
-    uint32_t dn = ze_build_kind(ct->cnt, ZE_NSYM_LL, N, zf::LL_MAX_LOG, zf::LL_DEFAULT_LOG, fs->t.ll.state, fs->t.ll.sym,
+    uint32_t dn = ze_build_kind(cnt, ZE_NSYM_LL, N, zf::LL_MAX_LOG, zf::LL_DEFAULT_LOG, fs->t.ll.state, fs->t.ll.sym,
                                 ct->st_ll, ct->sy_ll, (uint8_t*)bits, desc, &kll, true, lane);
-    dn += ze_build_kind(ct->cnt + ZE_NSYM_LL + ZE_NSYM_ML, ZE_NSYM_OF, N, zf::OF_MAX_LOG, zf::OF_DEFAULT_LOG, fs->t.of.state, fs->t.of.sym,
+    dn += ze_build_kind(cnt + ZE_NSYM_LL + ZE_NSYM_ML, ZE_NSYM_OF, N, zf::OF_MAX_LOG, zf::OF_DEFAULT_LOG, fs->t.of.state, fs->t.of.sym,
                         ct->st_of, ct->sy_of, (uint8_t*)bits, desc + dn, &kof, true, lane);
-    dn += ze_build_kind(ct->cnt + ZE_NSYM_LL, ZE_NSYM_ML, N, zf::ML_MAX_LOG, zf::ML_DEFAULT_LOG, fs->t.ml.state, fs->t.ml.sym,
+    dn += ze_build_kind(cnt + ZE_NSYM_LL, ZE_NSYM_ML, N, zf::ML_MAX_LOG, zf::ML_DEFAULT_LOG, fs->t.ml.state, fs->t.ml.sym,
                         ct->st_ml, ct->sy_ml, (uint8_t*)bits, desc + dn, &kml, true, lane);
     if (lane == 0) hdr_out[0] = (uint8_t)((kll.mode << 6) | (kof.mode << 4) | (kml.mode << 2));
     *desc_bytes = 1 + dn;
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
 
     uint8_t* wbase = smem + warp * ZE_SMEM_WARP_AL;
     uint8_t* buf = wbase;
-    uint32_t* ht = (uint32_t*)(wbase + ZB + ZE_BUF_PAD);
+    uint16_t* ht = (uint16_t*)(wbase + ZB + ZE_BUF_PAD);
     uint8_t* codes = buf + ZE_SEQ_AUX_OFF;
     uint16_t* stv = (uint16_t*)(codes + 96);
     uint8_t* stn = (uint8_t*)(stv + 96);
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
         for (uint32_t i = lane; i < bn; i += 32) buf[i] = src[i];
     }
     for (uint32_t i = bn + lane; i < ZB + ZE_BUF_PAD; i += 32) buf[i] = 0;
-    for (uint32_t i = lane; i < ZE_HSIZE; i += 32) ht[i] = 0;
+    for (uint32_t i = lane; i < ZE_HSIZE / 2; i += 32) ((uint32_t*)ht)[i] = 0;
     __syncwarp();
 
     // ---- phase A: greedy LZ parse, 32 positions per step
@@ -274,7 +276,9 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
         const uint32_t h = ze_hash(v);
         const uint32_t slot = valid ? ht[h] : 0u;                  // position + 1, 0 = empty
         __syncwarp();
-        if (valid) atomicMax(&ht[h], p + 1);                       // newest position wins, deterministically
+        // Lanes of this step that share a slot all store; the CUDA model lets any one of them win.  Every outcome is a
+        // valid parse (candidates are verified before use), so frames may differ in bytes, never in what they decode to.
+        if (valid) ht[h] = (uint16_t)(p + 1);
         __syncwarp();
         const uint32_t cand = slot ? slot - 1 : 0u;
         const uint32_t* wc = (const uint32_t*)(buf + (cand & ~3u));
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
     if (nseq == 0) {
         // no match at all: the block may still be worth a compressed block with entropy-coded literals and zero sequences
         uint8_t* body = out + 3;
-        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, (uint16_t*)ht, lane);
+        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, ht, lane);
         __syncwarp();
         if (lit_bytes + 1 < bn) {
             if (lane == 0) body[lit_bytes] = 0;                    // Number_of_Sequences = 0: the sequences section ends here
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
     } else {
         // literals section first (into `out` directly), then the sequences bit stream staged in `buf`
         uint8_t* body = out + 3;
-        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, (uint16_t*)ht, lane);   // header + payload
+        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, ht, lane);   // header + payload
         __syncwarp();
         const uint32_t shdr = nseq < 128 ? 1u : (nseq < 0x7f00 ? 2u : 3u);
         uint8_t* sp = body + lit_bytes;

@@ -40,13 +40,13 @@ constexpr uint32_t ZE_HUF_MIN = 64;            // below this many literals a tab
 constexpr bool ZE_FSE_WEIGHTS_ALWAYS = false;
 
 // Returns the bytes written at `body`.  `work`: >= ZB + 160 bytes of shared memory (tree scratch, then the
-// stream staging area); `aux`: 4 KiB of shared memory (histogram + code table).
+// stream staging area); `aux16`: 2 KiB of shared memory (histogram + code table).
 __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict__ lits, uint32_t n, uint8_t* body,
                                                        uint32_t* work, uint16_t* aux16, uint32_t lane) {
     if (n < ZE_HUF_MIN) return ze_raw_literals(lits, n, body, lane);
     uint32_t* hist = (uint32_t*)aux16;         // [256]
     uint32_t* ctab = hist + 256;               // [256] code | len << 16
-    uint32_t* keys = ctab + 256;               // [256] used symbols: count << 8 | symbol
+    uint32_t* keys = work + 1280;              // [256] used symbols: count << 8 | symbol
     uint32_t* sorted = work;                   // [256]
     uint32_t* nodew = work + 256;              // [512]
     uint16_t* parent = (uint16_t*)(work + 768);   // [512]
@@ -150,7 +150,7 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
     // Tree description: direct 4-bit weights (at most 128 of them) or FSE-compressed weights (RFC 8878 §4.2.1.1);
     // the shorter wins.  The FSE form is what lets alphabets above byte value 128 (binary payloads) be Huffman-coded.
     uint32_t tree_bytes = nweights <= 128 ? 1 + (nweights + 1) / 2 : 0xffffffffu;
-    uint8_t* wdesc = (uint8_t*)(keys + 256);                              // 1 KiB tail of `aux`: header byte + FSE description
+    uint8_t* wdesc = (uint8_t*)hist;                                      // the histogram is dead: header byte + FSE description
     {
         uint8_t* wts = (uint8_t*)(work + 1536);                           // weights, then FSE tables, in dead tree scratch
         uint32_t* wcnt = (uint32_t*)(wts + 256);                          // [16]
