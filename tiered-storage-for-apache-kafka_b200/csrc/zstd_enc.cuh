@@ -254,8 +254,10 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
             else for (uint32_t k = i; k < bn; k++) buf[k] = src[k];
         }
     } else {
+        _Pragma("unroll 2")
         for (uint32_t i = lane; i < bn; i += 32) buf[i] = src[i];
     }
+    _Pragma("unroll 1")
     for (uint32_t i = bn + lane; i < ZB + ZE_BUF_PAD; i += 32) buf[i] = 0;
     for (uint32_t i = lane; i < ZE_HSIZE / 2; i += 32) ((uint32_t*)ht)[i] = 0;
     __syncwarp();
@@ -379,6 +381,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
             src_pos += __shfl_sync(TS_FULL, inc_s, 31);
         }
         const uint32_t ll = bn - anchor;                           // trailing literals
+        _Pragma("unroll 2")
         for (uint32_t k = lane; k < ll; k += 32) lits[nlit + k] = buf[anchor + k];
         nlit += ll;
     }
@@ -387,36 +390,37 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
 
     // ---- phase B: entropy stage into the (now free) shared block buffer, then emit
     uint32_t payload = 0xffffffffu;                                // "not compressible"
-    if (nseq == 0) {
-        // no match at all: the block may still be worth a compressed block with entropy-coded literals and zero sequences
-        uint8_t* body = out + 3;
-        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, ht, lane);
-        __syncwarp();
-        if (lit_bytes + 1 < bn) {
-            if (lane == 0) body[lit_bytes] = 0;                    // Number_of_Sequences = 0: the sequences section ends here
-            payload = lit_bytes + 1;
-        }
-    } else {
+    {
         // literals section first (into `out` directly), then the sequences bit stream staged in `buf`
         uint8_t* body = out + 3;
         const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, ht, lane);   // header + payload
         __syncwarp();
-        const uint32_t shdr = nseq < 128 ? 1u : (nseq < 0x7f00 ? 2u : 3u);
-        uint8_t* sp = body + lit_bytes;
-        uint32_t desc_bytes = 0;
-        const uint32_t sbytes = ze_encode_sequences(seqs, nseq, (uint32_t*)buf, (ZeCTab*)ht, codes, stv, stn, &fs, sp + shdr, &desc_bytes, lane);
-        const uint32_t total = lit_bytes + shdr + desc_bytes + sbytes;
-        if (total < bn) {
-            if (lane == 0) {
-                if (shdr == 1) sp[0] = (uint8_t)nseq;
-                else if (shdr == 2) { sp[0] = (uint8_t)((nseq >> 8) + 0x80); sp[1] = (uint8_t)nseq; }
-                else { sp[0] = 0xff; sp[1] = (uint8_t)(nseq - 0x7f00); sp[2] = (uint8_t)((nseq - 0x7f00) >> 8); }
+        if (nseq == 0) {
+            // no match at all: the block may still be worth a compressed block with entropy-coded literals and zero sequences
+            if (lit_bytes + 1 < bn) {
+                if (lane == 0) body[lit_bytes] = 0;                // Number_of_Sequences = 0: the sequences section ends here
+                payload = lit_bytes + 1;
             }
-            for (uint32_t i = lane; i < sbytes; i += 32) sp[shdr + desc_bytes + i] = buf[i];
-            payload = total;
+        } else {
+            const uint32_t shdr = nseq < 128 ? 1u : (nseq < 0x7f00 ? 2u : 3u);
+            uint8_t* sp = body + lit_bytes;
+            uint32_t desc_bytes = 0;
+            const uint32_t sbytes = ze_encode_sequences(seqs, nseq, (uint32_t*)buf, (ZeCTab*)ht, codes, stv, stn, &fs, sp + shdr, &desc_bytes, lane);
+            const uint32_t total = lit_bytes + shdr + desc_bytes + sbytes;
+            if (total < bn) {
+                if (lane == 0) {
+                    if (shdr == 1) sp[0] = (uint8_t)nseq;
+                    else if (shdr == 2) { sp[0] = (uint8_t)((nseq >> 8) + 0x80); sp[1] = (uint8_t)nseq; }
+                    else { sp[0] = 0xff; sp[1] = (uint8_t)(nseq - 0x7f00); sp[2] = (uint8_t)((nseq - 0x7f00) >> 8); }
+                }
+                _Pragma("unroll 2")
+                for (uint32_t i = lane; i < sbytes; i += 32) sp[shdr + desc_bytes + i] = buf[i];
+                payload = total;
+            }
         }
     }
     if (payload == 0xffffffffu) {                                  // Raw_Block
+        _Pragma("unroll 2")
         for (uint32_t i = lane; i < bn; i += 32) out[3 + i] = src[i];
     }
     if (lane == 0) {

@@ -74,7 +74,7 @@ __device__ TS_NOINLINE uint32_t ze_write_ncount(uint8_t* out, const uint32_t* no
 // ---- choose the mode of one kind and build its encoding tables.  Warp-uniform.
 // cnt[alphabet]: histogram on entry, normalised counts on exit (FSE mode).  scratch: >= 512 + 4*68 bytes of shared memory.
 // Returns the bytes of table description written at desc (global).
-__device__ __forceinline__ uint32_t ze_build_kind(uint32_t* cnt, uint32_t alphabet, uint32_t N, uint32_t max_log, uint32_t default_log,
+__device__ TS_NOINLINE uint32_t ze_build_kind(uint32_t* cnt, uint32_t alphabet, uint32_t N, uint32_t max_log, uint32_t default_log,
                                                   const uint16_t* pre_state, const zf::FseCSym* pre_sym, uint16_t* st, zf::FseCSym* sy,
                                                   uint8_t* scratch, uint8_t* desc, ZeKind* kind, bool allow_predefined, uint32_t lane) {
     const uint32_t c0 = lane < alphabet ? cnt[lane] : 0, c1 = lane + 32 < alphabet ? cnt[lane + 32] : 0;

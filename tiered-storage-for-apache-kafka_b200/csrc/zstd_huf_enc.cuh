@@ -15,7 +15,7 @@
 namespace ts {
 
 // Raw_Literals_Block with the 3-byte header (Size_Format 11: 20-bit Regenerated_Size).
-__device__ __forceinline__ uint32_t ze_raw_literals(const uint8_t* __restrict__ lits, uint32_t n, uint8_t* body, uint32_t lane) {
+__device__ TS_NOINLINE uint32_t ze_raw_literals(const uint8_t* __restrict__ lits, uint32_t n, uint8_t* body, uint32_t lane) {
     if (lane == 0) {
         body[0] = (uint8_t)((3u << 2) | ((n & 0xf) << 4));
         body[1] = (uint8_t)(n >> 4);
@@ -55,6 +55,7 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
 
     for (uint32_t i = lane; i < 256; i += 32) { hist[i] = 0; ctab[i] = 0; }
     __syncwarp();
+    _Pragma("unroll 2")
     for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[lits[i]], 1u);
     __syncwarp();
 
@@ -90,13 +91,16 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
         for (uint32_t e = lane; e < m; e += 32) {                         // rank sort (keys are distinct)
             const uint32_t key = keys[e];
             uint32_t r = 0;
+            _Pragma("unroll 2")
             for (uint32_t j = 0; j < m; j++) r += keys[j] < key ? 1u : 0u;
             sorted[r] = key;
         }
         __syncwarp();
         if (lane == 0) {
+            _Pragma("unroll 1")
             for (uint32_t i = 0; i < m; i++) nodew[i] = sorted[i] >> 8;
             uint32_t li = 0, ii = m, ni = m;
+            _Pragma("unroll 1")
             for (uint32_t k = 0; k + 1 < m; k++) {
                 uint32_t a, b;
                 if (li < m && (ii >= ni || nodew[li] <= nodew[ii])) a = li++; else a = ii++;
@@ -108,6 +112,7 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
             const uint32_t root = 2 * m - 2;
             depth[root] = 0;
             uint32_t mx = 0;
+            _Pragma("unroll 1")
             for (int32_t i = (int32_t)root - 1; i >= 0; i--) {
                 depth[i] = (uint8_t)(depth[parent[i]] + 1);
                 if ((uint32_t)i < m && depth[i] > mx) mx = depth[i];
@@ -129,12 +134,15 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
     if (lane == 0) {
         uint32_t cnt[16];
         for (int w = 0; w < 16; w++) cnt[w] = 0;
+        _Pragma("unroll 1")
         for (uint32_t i = 0; i < m; i++) cnt[max_len + 1 - depth[i]]++;
         uint32_t start[16], pos = 0;
         for (uint32_t w = 1; w <= max_len; w++) { start[w] = pos; pos += cnt[w] << (w - 1); }
         // sorted[] is ordered by count; symbol order inside a weight class comes from walking symbols ascending
+        _Pragma("unroll 1")
         for (uint32_t i = 0; i < m; i++) ctab[sorted[i] & 0xff] = (uint32_t)depth[i] << 16;      // park the length
         uint64_t total_bits = 0;
+        _Pragma("unroll 1")
         for (uint32_t s = 0; s <= last_sym; s++) {
             const uint32_t len = ctab[s] >> 16;
             if (!len) continue;
@@ -217,13 +225,15 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
     for (uint32_t i = lane; i < (ZB + 128) / 4; i += 32) work[i] = 0;
     __syncwarp();
     uint32_t byte_pos = 0;
-    uint32_t ssz[4];
+    uint64_t ssz_all = 0;                                                 // four 16-bit stream sizes
+    _Pragma("unroll 1")
     for (uint32_t st = 0; st < 4; st++) {
         const uint32_t s0 = st * seg, s1 = st < 3 ? min(n, s0 + seg) : n;
         const uint32_t cnt = s1 > s0 ? s1 - s0 : 0;
         const uint32_t per = (cnt + 31) / 32;
         const uint32_t a = min(cnt, lane * per), b = min(cnt, a + per);   // this lane's run [a, b) of the stream
         uint32_t mybits = 0;
+        _Pragma("unroll 2")
         for (uint32_t i = a; i < b; i++) mybits += ctab[lits[s0 + i]] >> 16;
         // symbols are written last-to-first: the offset of a run is the number of bits of all LATER runs
         const uint32_t incb = warp_inclusive_scan_u32(mybits, lane);
@@ -241,8 +251,9 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
             const uint32_t o = byte_pos * 8 + total;
             atomicOr(&work[o >> 5], 1u << (o & 31));
         }
-        ssz[st] = (total + 1 + 7) >> 3;
-        byte_pos += ssz[st];
+        const uint32_t sz = (total + 1 + 7) >> 3;
+        ssz_all |= (uint64_t)sz << (16 * st);
+        byte_pos += sz;
         __syncwarp();
     }
     const uint32_t comp = tree_bytes + 6 + byte_pos;
@@ -267,12 +278,11 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
             }
         }
         uint8_t* j = t + tree_bytes;
-        j[0] = (uint8_t)ssz[0]; j[1] = (uint8_t)(ssz[0] >> 8);
-        j[2] = (uint8_t)ssz[1]; j[3] = (uint8_t)(ssz[1] >> 8);
-        j[4] = (uint8_t)ssz[2]; j[5] = (uint8_t)(ssz[2] >> 8);
+        for (uint32_t k = 0; k < 6; k++) j[k] = (uint8_t)(ssz_all >> (8 * k));            // jump table: sizes of streams 1-3
     }
     uint8_t* sp = body + hsz + tree_bytes + 6;
     const uint8_t* wb = (const uint8_t*)work;
+    _Pragma("unroll 2")
     for (uint32_t i = lane; i < byte_pos; i += 32) sp[i] = wb[i];
     __syncwarp();
     return hsz + comp;
