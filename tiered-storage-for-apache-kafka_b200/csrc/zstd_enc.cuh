@@ -223,6 +223,18 @@ __device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict_
     return (bitpos + 7) >> 3;
 }
 
+// warp copy of n bytes, any alignment on either side: aligned 32-bit stores in the middle, source words by funnel shift
+__device__ TS_NOINLINE void ze_warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t lane) {
+    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+    if (lane < head) dst[lane] = src[lane];
+    const uint32_t words = (n - head) >> 2;
+    uint32_t* d32 = (uint32_t*)(dst + head);
+    const uint8_t* s = src + head;
+    for (uint32_t i = lane; i < words; i += 32) d32[i] = ld_u32_unaligned(s + 4 * i);
+    const uint32_t done = head + 4 * words;
+    if (lane < n - done) dst[done + lane] = src[done + lane];
+}
+
 __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __grid_constant__ ZstdEncArgs A) {
     TS_DYN_SMEM(smem);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -381,8 +393,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
             src_pos += __shfl_sync(TS_FULL, inc_s, 31);
         }
         const uint32_t ll = bn - anchor;                           // trailing literals
-        _Pragma("unroll 2")
-        for (uint32_t k = lane; k < ll; k += 32) lits[nlit + k] = buf[anchor + k];
+        ze_warp_copy(lits + nlit, buf + anchor, ll, lane);
         nlit += ll;
     }
     __syncwarp();
@@ -420,8 +431,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
         }
     }
     if (payload == 0xffffffffu) {                                  // Raw_Block
-        _Pragma("unroll 2")
-        for (uint32_t i = lane; i < bn; i += 32) out[3 + i] = src[i];
+        ze_warp_copy(out + 3, src, bn, lane);
     }
     if (lane == 0) {
         const uint32_t type = payload == 0xffffffffu ? 0u : 2u;
@@ -445,18 +455,6 @@ __device__ __forceinline__ uint32_t ze_frame_header(uint8_t* h, uint32_t n) {   
         h[p++] = (uint8_t)n; h[p++] = (uint8_t)(n >> 8); h[p++] = (uint8_t)(n >> 16); h[p++] = (uint8_t)(n >> 24);
     }
     return p;
-}
-
-// warp copy of n bytes, src 4-byte aligned (block slots are), dst arbitrary: aligned 32-bit stores in the middle
-__device__ __forceinline__ void ze_warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n, uint32_t lane) {
-    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
-    if (lane < head) dst[lane] = src[lane];
-    const uint32_t words = (n - head) >> 2;
-    uint32_t* d32 = (uint32_t*)(dst + head);
-    const uint8_t* s = src + head;
-    for (uint32_t i = lane; i < words; i += 32) d32[i] = ld_u32_unaligned(s + 4 * i);
-    const uint32_t done = head + 4 * words;
-    if (lane < n - done) dst[done + lane] = src[done + lane];
 }
 
 __global__ void __launch_bounds__(256) zstd_enc_assemble_kernel(const __grid_constant__ ZstdEncArgs A) {
