@@ -30,7 +30,7 @@ namespace ts {
 constexpr uint32_t ZB = 8192;                  // bytes of original data per zstd block
 constexpr int ZE_HLOG = 10;                    // per-warp hash table: 2^10 x u16 (position + 1)
 constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
-constexpr int ZE_WPB = 1;                      // warps (= blocks in flight) per CTA
+constexpr int ZE_WPB = 4;                      // warps (= blocks in flight) per CTA
 constexpr uint32_t ZE_MAXSEQ = ZB / 8;         // sequences kept per block; beyond that the rest goes out as literals
 constexpr uint32_t ZE_MIN_MATCH = 5;           // a 4-byte match costs more bits than four Huffman-coded literals (libzstd level 3 also uses 5)
 constexpr uint32_t ZE_LANE_EXT = 12;           // bytes a lane extends its own match beyond the first 4
