@@ -27,7 +27,7 @@ clean:
 .PHONY: all oracle clean libtsgpu.so
 
 # C++ host-mirror tests: `_simt` links the test-only emulator build (CPU box), `_gpu` links the product library.
-tests/cpp/test_host_mirror_simt: tests/cpp/test_host_mirror.cpp $(PKG)/host/chunk_transform.hpp tests/simt/libtsgpu_simt.so oracle
+tests/cpp/test_host_mirror_simt: tests/cpp/test_host_mirror.cpp $(PKG)/host/chunk_transform.hpp $(PKG)/host/segment_upload.hpp tests/simt/libtsgpu_simt.so oracle
 	g++ -O1 -g -std=c++17 -o $@ tests/cpp/test_host_mirror.cpp -Ltests/simt -ltsgpu_simt -Loracle -ltsoracle -Wl,-rpath,'$$ORIGIN/../simt' -Wl,-rpath,'$$ORIGIN/../../oracle'
-tests/cpp/test_host_mirror_gpu: tests/cpp/test_host_mirror.cpp $(PKG)/host/chunk_transform.hpp $(PKG)/libtsgpu.so oracle
+tests/cpp/test_host_mirror_gpu: tests/cpp/test_host_mirror.cpp $(PKG)/host/chunk_transform.hpp $(PKG)/host/segment_upload.hpp $(PKG)/libtsgpu.so oracle
 	g++ -O1 -g -std=c++17 -o $@ tests/cpp/test_host_mirror.cpp -L$(PKG) -ltsgpu -Loracle -ltsoracle -Wl,-rpath,'$$ORIGIN/../../$(PKG)' -Wl,-rpath,'$$ORIGIN/../../oracle' -Wl,-rpath,/usr/local/cuda/lib64

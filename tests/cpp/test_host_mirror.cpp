@@ -4,13 +4,16 @@
 //   VariableSizeChunkIndexBuilderTest.java:45-81, core/T/transform/BaseTransformChunkEnumerationTest.java:65-94,
 //   core/T/transform/TransformFinisherTest.java:97-125, core/T/fetch/FetchChunkEnumerationTest.java:105-145,
 //   core/T/transform/TransformsEndToEndTest.java:44-116 (round trip through the batched GPU chain, checked
-//   against the oracle's libzstd/OpenSSL reader).
+//   against the oracle's libzstd/OpenSSL reader),
+//   core/T/SegmentCompressionCheckerTest.java:43-130, core/T/transform/RateLimitedInputStreamTest.java:36-100 (with an
+//   injected clock instead of wall-clock waits), RemoteStorageManager.requiresCompression (RemoteStorageManager.java:381-398).
 // Links libtsgpu.so on a GPU box, or the test-only SIMT build on the CPU box (same sources, emulated kernels).
 #include <cstdio>
 #include <cstring>
 #include <random>
 #include <sstream>
 #include "../../tiered-storage-for-apache-kafka_b200/host/chunk_transform.hpp"
+#include "../../tiered-storage-for-apache-kafka_b200/host/segment_upload.hpp"
 #include "../../oracle/tsoracle.h"
 
 using namespace tieredstorage;
@@ -161,8 +164,141 @@ static void gpuChainTests(tsgpu_ctx* ctx) {
     }
 }
 
+
+// ---- record batches as kafka-clients 3.6.0 writes them (MemoryRecordsBuilder), built by hand from the published format
+static void put32(Bytes& b, size_t at, uint32_t v) { b[at] = v >> 24; b[at + 1] = v >> 16; b[at + 2] = v >> 8; b[at + 3] = v; }
+static Bytes batchV2(int codec, const std::string& payload, int64_t baseOffset = 0) {
+    Bytes b(61 + payload.size(), 0);
+    for (int i = 0; i < 8; i++) b[i] = (uint8_t)(baseOffset >> (56 - 8 * i));
+    put32(b, 8, (uint32_t)(b.size() - 12));                  // batchLength
+    b[16] = 2;                                               // magic
+    b[21] = 0; b[22] = (uint8_t)codec;                       // attributes
+    put32(b, 57, 1);                                         // recordsCount
+    memcpy(b.data() + 61, payload.data(), payload.size());
+    put32(b, 17, crc32c(b.data() + 21, b.size() - 21));
+    return b;
+}
+static Bytes recordV1(int codec, const std::string& payload) {
+    Bytes b(12 + 22 + payload.size(), 0);                    // offset, size | crc, magic, attributes, timestamp, keyLen(-1), valueLen
+    put32(b, 8, (uint32_t)(b.size() - 12));
+    b[16] = 1; b[17] = (uint8_t)codec;
+    put32(b, 26, 0xffffffffu);                               // null key
+    put32(b, 30, (uint32_t)payload.size());
+    memcpy(b.data() + 34, payload.data(), payload.size());
+    put32(b, 12, crc32(b.data() + 16, b.size() - 16));
+    return b;
+}
+
+static void uploadSideTests() {
+    // checksum known answers (the "check" values of the CRC catalogue): pins both polynomials and the reflection
+    CHECK(crc32c((const uint8_t*)"123456789", 9) == 0xE3069283u);
+    CHECK(crc32((const uint8_t*)"123456789", 9) == 0xCBF43926u);
+    // SegmentCompressionCheckerTest.shouldFailWhenReadingEmptyFile
+    CHECK(throwsWith<InvalidRecordBatchException>([] { SegmentCompressionChecker::check(nullptr, 0); }, "Record batch is null"));
+    // shouldReturnCompressedWhenEnabled: NONE -> false, ZSTD -> true (and the other codecs)
+    for (int codec = 0; codec <= 4; codec++) {
+        Bytes b = batchV2(codec, "key-0value-0");
+        CHECK(SegmentCompressionChecker::check(b.data(), b.size()) == (codec != 0));
+        Bytes l = recordV1(codec & 3, "value-0");
+        CHECK(SegmentCompressionChecker::check(l.data(), l.size()) == ((codec & 3) != 0));
+    }
+    // shouldReturnCompressedWhenCompressionChanges: only the FIRST batch decides
+    for (int first = 0; first < 2; first++) {
+        Bytes a = batchV2(first ? 4 : 0, "key-0value-0"), b2 = batchV2(first ? 0 : 4, "key-1value-1", 1);
+        a.insert(a.end(), b2.begin(), b2.end());
+        CHECK(SegmentCompressionChecker::check(a.data(), a.size()) == (first == 1));
+    }
+    // shouldFailWhenReadingInvalidFile: a damaged record body fails the checksum
+    {
+        Bytes b = batchV2(0, "key-0value-0");
+        for (auto& c : b) if (c == '0') c = '1';
+        CHECK(throwsWith<InvalidRecordBatchException>([&] { SegmentCompressionChecker::check(b.data(), b.size()); }, "Failed to read and validate first batch"));
+        Bytes t = batchV2(4, "key-0value-0"); t.pop_back();  // a partial batch is "no batch" (FileLogInputStream.nextBatch)
+        CHECK(throwsWith<InvalidRecordBatchException>([&] { SegmentCompressionChecker::check(t.data(), t.size()); }, "Record batch is null"));
+        Bytes m = batchV2(0, "x"); m[16] = 9;
+        CHECK(throwsWith<InvalidRecordBatchException>([&] { SegmentCompressionChecker::check(m.data(), m.size()); }, "Failed to read and validate first batch"));
+    }
+    // RemoteStorageManager.requiresCompression
+    {
+        Bytes plain = batchV2(0, "v"), z = batchV2(4, "v"), bad = batchV2(0, "v"); bad[30] ^= 1;
+        CHECK(!requiresCompression(false, false, plain.data(), plain.size()));
+        CHECK(requiresCompression(true, false, z.data(), z.size()));            // heuristic off: always compress
+        CHECK(requiresCompression(true, true, plain.data(), plain.size()));
+        CHECK(!requiresCompression(true, true, z.data(), z.size()));
+        CHECK(!requiresCompression(true, true, bad.data(), bad.size()));        // unreadable first batch: upload uncompressed
+    }
+    // RateLimitedInputStreamTest with an injected clock: sleeping advances it
+    {
+        int64_t now = 0, slept = 0;
+        auto clock = [&] { return now; };
+        auto sleep = [&](int64_t ns) { slept += ns; now += ns; };
+        RateLimitBucket bucket(1, clock, sleep);
+        CHECK(bucket.capacity() == RateLimitBucket::MIN_RATE);                  // rateLimitBucket: max(uploadRate, MIN_RATE)
+        CHECK(bucket.consume(RateLimitBucket::MIN_RATE - 1) == 0);              // testDoesNotBlockRead
+        CHECK(bucket.consume(0) == 0);
+        const int64_t w = bucket.consume(RateLimitBucket::MIN_RATE - 1);        // testBlocksOnSeparateStreams: ~1 s for the refill
+        CHECK(w > 990000000 && w <= 1000000000);
+        RateLimitBucket b2(1, clock, sleep);
+        const int64_t w2 = b2.consume(RateLimitBucket::MIN_RATE + 1);           // testBlocksRead: one token short of the capacity
+        CHECK(w2 > 0 && w2 < 1000000);
+        b2.forceAddTokens(100);                                                 // tokens handed back for bytes not read
+        CHECK(b2.availableTokens() > 98.0 && b2.availableTokens() < 101.0);
+        now += 5000000000ll;                                                    // refill stops at the capacity
+        CHECK(b2.availableTokens() == (double)RateLimitBucket::MIN_RATE);
+        b2.forceAddTokens(7);                                                   // ... but forced tokens may exceed it
+        CHECK(b2.availableTokens() == (double)RateLimitBucket::MIN_RATE + 7);
+    }
+    // S3MultiPartOutputStream part plan
+    {
+        auto parts = multipartPlan(12, 5);
+        CHECK(parts.size() == 3 && parts[0].partNumber == 1 && parts[2].offset == 10 && parts[2].size == 2);
+        CHECK(multipartPlan(0, 5).empty() && multipartPlan(10, 5).size() == 2);
+        CHECK(throwsWith<IllegalArgumentException>([] { multipartPlan(1, 0); }, "partSize must be positive"));
+    }
+}
+
+// RemoteStorageManager.uploadSegmentLog through the GPU chain: heuristic decides the flags, parts arrive in order, the
+// object equals what the reference-side reader expects, the chunk index is the reference's
+static void segmentUploadTests(tsgpu_ctx* ctx) {
+    std::mt19937 rng(5);
+    for (int codec : {0, 4}) for (int enc = 0; enc < 2; enc++) {
+        std::string payload;
+        for (int i = 0; i < 40000; i++) payload += codec ? (char)rng() : "topic-partition-offset "[i % 23];
+        Bytes seg = batchV2(codec, payload);
+        Bytes more = batchV2(codec, payload, 1); seg.insert(seg.end(), more.begin(), more.end());
+        const int cs = 30000;
+        const int n = (int)seg.size(), nch = (n + cs - 1) / cs;
+        DataKeyAndAAD km; km.dataKey.resize(32); km.aad.resize(32);
+        for (auto& b : km.dataKey) b = (uint8_t)rng();
+        for (auto& b : km.aad) b = (uint8_t)rng();
+        Bytes ivs(12 * nch); for (auto& b : ivs) b = (uint8_t)rng();
+        int64_t now = 0, slept = 0;
+        RateLimitBucket bucket(1 << 20, [&] { return now; }, [&](int64_t ns) { slept += ns; now += ns; });
+        SegmentLogUploader up(ctx, cs, /*compressionEnabled=*/true, /*heuristic=*/true, enc != 0, /*partSize=*/16384, &bucket);
+        Bytes object; int lastPart = 0; bool ordered = true;
+        auto res = up.upload(seg.data(), (uint64_t)n, enc ? &km : nullptr, enc ? ivs.data() : nullptr, [&](const UploadPart& p, const uint8_t* d) {
+            ordered = ordered && p.partNumber == lastPart + 1 && p.offset == object.size(); lastPart = p.partNumber;
+            object.insert(object.end(), d, d + p.size);
+        });
+        CHECK(ordered && object.size() == res.objectBytes);
+        CHECK(res.compressed == (codec == 0));                                  // already-compressed batches skip zstd
+        CHECK((dynamic_cast<VariableSizeChunkIndex*>(res.chunkIndex.get()) != nullptr) == res.compressed);
+        const uint32_t flags = (res.compressed ? 1u : 0u) | (enc ? 2u : 0u);
+        std::vector<uint32_t> ts; for (auto& c : res.chunkIndex->chunks()) ts.push_back((uint32_t)c.transformedSize);
+        CHECK((int)ts.size() == nch);
+        Bytes back(n + 64); std::vector<uint32_t> osz(ts.size());
+        if (flags) {
+            int rc = ora_detransform_chunks(flags, object.data(), ts.data(), (uint32_t)ts.size(), km.dataKey.data(), km.aad.data(), 32, back.data(), back.size(), osz.data());
+            CHECK(rc == 0);
+            CHECK(memcmp(back.data(), seg.data(), n) == 0);
+        } else CHECK(object == seg);
+        if (object.size() > (size_t)bucket.capacity()) CHECK(slept > 0);       // the limiter was charged for every part
+    }
+}
+
 int main(int argc, char** argv) {
     builderTests();
+    uploadSideTests();
     manifestTests();
     baseAndFinisherTests();
     if (argc > 1 && !strcmp(argv[1], "--device")) {
@@ -170,6 +306,7 @@ int main(int argc, char** argv) {
         int rc = tsgpu_create(nullptr, 0, 400000, 16, &ctx);
         if (rc) { printf("tsgpu_create failed: %s\n", tsgpu_last_error()); return 2; }
         gpuChainTests(ctx);
+        segmentUploadTests(ctx);
         tsgpu_destroy(ctx);
     }
     printf("%s: %d checks, %d failures\n", failures ? "FAILED" : "OK", checks, failures);
