@@ -21,8 +21,13 @@ tests/simt/libtsgpu_simt.so: $(CSRC)/tsgpu.cu $(HDRS) tests/simt/simt.h tests/si
 	g++ -O2 -g -std=c++17 -fPIC -shared -DTSGPU_SIMT=1 -Itests/simt -I$(CSRC) -x c++ $(CSRC)/tsgpu.cu tests/simt/simt.cpp \
 	    -o $@ -Wall -Wno-unknown-pragmas -Wno-unused-function -Wno-unused-variable
 
+# TEST-ONLY: the emulator build under AddressSanitizer (shared memory and scratch are heap blocks there, so overruns show)
+tests/simt/libtsgpu_simt_asan.so: $(CSRC)/tsgpu.cu $(HDRS) tests/simt/simt.h tests/simt/simt.cpp
+	g++ -O1 -g -std=c++17 -fPIC -shared -fsanitize=address -DTSGPU_SIMT=1 -Itests/simt -I$(CSRC) -x c++ $(CSRC)/tsgpu.cu tests/simt/simt.cpp \
+	    -o $@ -Wno-unknown-pragmas
+
 clean:
-	rm -f $(PKG)/libtsgpu.so tests/simt/libtsgpu_simt.so build_ptxas.log
+	rm -f $(PKG)/libtsgpu.so tests/simt/libtsgpu_simt.so tests/simt/libtsgpu_simt_asan.so build_ptxas.log
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean libtsgpu.so
 

@@ -1,0 +1,91 @@
+"""The committed fixtures under tests/golden/ (made by tests/golden/make_golden.py): golden vectors transcribed from the
+reference's tests + public AES known answers, and libzstd-written frames.  CPU leg: the oracle and the SIMT-emulated
+product code both reproduce them; the `-m gpu` leg repeats the product checks on a B200 through the C-ABI."""
+import base64
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as ora
+import tsgpu
+from tsgpu import corpus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+SIMT_LIB = os.path.join(ROOT, "tests", "simt", "libtsgpu_simt.so")
+VEC = json.load(open(os.path.join(GOLD, "reference_vectors.json")))
+FRAMES = json.load(open(os.path.join(GOLD, "libzstd_frames.json")))["frames"]
+Z, A = tsgpu.FLAG_ZSTD, tsgpu.FLAG_AES
+
+
+def test_fixture_inputs_are_reproducible():
+    # the inputs behind the frames come from corpus.gen_chunk: the fixture pins the generator too
+    for f in FRAMES:
+        src = corpus.gen_chunk(f["kind"], f["seed"], 0, f["n"])
+        assert hashlib.sha256(src.tobytes()).hexdigest() == f["sha256"]
+
+
+def test_oracle_reproduces_reference_vectors():
+    e = VEC["encoded_chunks"]
+    assert ora.codec_encode(e["sizes"]) == bytes.fromhex(e["codec_hex"])
+    assert ora.transformed_chunks_serialize(e["sizes"]) == e["base64"]
+    assert ora.transformed_chunks_deserialize(e["base64"]) == e["sizes"]
+    j = VEC["chunk_index_json"]
+    assert ora.ChunkIndex.fixed(*j["fixed"]["args"]).to_json() == j["fixed"]["json"]
+    assert ora.ChunkIndex.variable(*j["variable"]["args"]).to_json() == j["variable"]["json"]
+    m = VEC["materialized_chunks"]
+    assert [list(c) for c in ora.ChunkIndex.fixed(*j["fixed"]["args"]).chunks()] == m["fixed"]
+    assert [list(c) for c in ora.ChunkIndex.variable(*j["variable"]["args"]).chunks()] == m["variable"]
+    for values, bpv in VEC["codec_bytes_per_value"]["cases"]:
+        enc = ora.codec_encode(values)
+        assert enc[8] == bpv and len(enc) == 13 + (len(values) - 1) * bpv and ora.codec_decode(enc) == values
+    for k in VEC["aes256_gcm_kats"]["cases"]:
+        key, iv, aad, pt = (bytes.fromhex(k[x]) for x in ("key", "iv", "aad", "pt"))
+        assert ora.aesgcm_encrypt_chunk(key, iv, aad, pt) == iv + bytes.fromhex(k["ct"]) + bytes.fromhex(k["tag"])
+    b = VEC["aes256_block"]
+    assert ora.aes256_encrypt_block(bytes.fromhex(b["key"]), bytes.fromhex(b["pt"])) == bytes.fromhex(b["ct"])
+    for f in FRAMES:
+        out = ora.zstd_decompress_chunk(base64.b64decode(f["frame_b64"]))
+        assert hashlib.sha256(out).hexdigest() == f["sha256"]
+
+
+def _product_checks(ctx):
+    e = VEC["encoded_chunks"]
+    assert ctx.transformed_chunks_deserialize(e["base64"]) == e["sizes"]
+    # AES-256-GCM known answers through the transform entry point: IV || CT || TAG, bit-exact
+    for k in VEC["aes256_gcm_kats"]["cases"]:
+        key, iv, aad, pt = (bytes.fromhex(k[x]) for x in ("key", "iv", "aad", "pt"))
+        if not pt:
+            continue                                         # an empty chunk is not a chunk (BaseTransformChunkEnumeration ends the stream)
+        src = np.frombuffer(pt, dtype=np.uint8)
+        out, sizes = ctx.transform(A, src, 0, key, aad, iv)
+        assert bytes(out[:sizes[0]]) == iv + bytes.fromhex(k["ct"]) + bytes.fromhex(k["tag"])
+        back, _ = ctx.detransform(A, out, sizes, src.size, key, aad)
+        assert bytes(back) == pt
+    # every libzstd-written frame (levels 1 / 3 / 19) decodes to its input
+    for f in FRAMES:
+        frame = np.frombuffer(base64.b64decode(f["frame_b64"]), dtype=np.uint8)
+        back, osz = ctx.detransform(Z, frame, [frame.size], f["n"])
+        assert osz == [f["n"]] and hashlib.sha256(back.tobytes()).hexdigest() == f["sha256"], f
+
+
+def test_emulated_product_code_reproduces_fixtures():
+    subprocess.check_call(["make", "-s", "-C", ROOT, "tests/simt/libtsgpu_simt.so"])
+    ctx = tsgpu.Context(max_chunk_bytes=1 << 19, max_batch=2, lib_path=SIMT_LIB)
+    try:
+        _product_checks(ctx)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_fixtures():
+    ctx = tsgpu.Context(max_chunk_bytes=1 << 19, max_batch=2)
+    try:
+        _product_checks(ctx)
+    finally:
+        ctx.close()
