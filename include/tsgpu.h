@@ -49,6 +49,11 @@ const char* tsgpu_version(void);
  * Context: owns, per listed device, streams, device arenas and pinned staging sized for `max_batch` chunks of
  * `max_chunk_bytes` original bytes (= chunk.size, RemoteStorageManagerConfig.java:123-130).
  * Batches are dealt round-robin to the devices (BASELINE.json north_star: segments shard by chunk batch).
+ * A host-buffer call (tsgpu_transform / tsgpu_detransform) cuts its chunks into batches of `max_batch` and keeps up to
+ * 8 of them in flight per device (work slots, allocated on first use; each has a compute stream and a copy-out stream).
+ * With 4 MiB chunks `max_batch = 4` measured best through PCIe; device-resident callers pass whole segments.
+ * Environment (read once by tsgpu_create; tuning only): TSGPU_SLOTS=1..16 slots per device, TSGPU_SPLIT_OUT=0 puts the
+ * copies-out back on the compute stream.
  * --------------------------------------------------------------------------------------------------------- */
 int  tsgpu_create(const int* device_ids, int n_devices, uint32_t max_chunk_bytes, uint32_t max_batch,
                   tsgpu_ctx** out);

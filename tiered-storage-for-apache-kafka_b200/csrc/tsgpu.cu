@@ -258,6 +258,7 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
                            const uint8_t* aad, uint32_t aad_len, const uint8_t* ivs, XfBatch& xb) {
     RT(rt::set_device(w.device));
     rt::stream_t st = w.stream;
+    w.busy = true;                                       // from here on the caller must drain this slot's streams before returning
     const uint64_t byte0 = off[c0];
     const uint64_t byte1 = off[c0 + nb - 1] + len[c0 + nb - 1];
     RT(rt::h2d(w.d_orig, src + byte0, byte1 - byte0, st));
@@ -401,9 +402,10 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
     uint32_t drained = 0;
     for (uint32_t b = 0; b < nbatches && rc == TSGPU_OK; b++) {
         if (b >= nwork) {
-            // The slot is reused.  Its previous batch has been drained (sizes read on the host, copies-out enqueued);
-            // the new batch is enqueued on the same stream, so stream order keeps it behind those copies — the host
-            // does not wait, which keeps all slots' queues full.
+            // The slot is reused.  Its previous batch has been drained (sizes read on the host, copies-out enqueued on
+            // the slot's out_stream); the new batch's copy-in and first kernels start right away and only the kernel
+            // that overwrites the buffer being copied out waits for those copies (wait_copies_out) — the host never
+            // waits here, which keeps all slots' queues full.
             if (drained <= b - nwork) { rc = drain(drained++); if (rc) break; }
         }
         uint32_t c0 = b * c->max_batch, nb = std::min(c->max_batch, n - c0);
@@ -433,6 +435,7 @@ static int detransform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_
                              DxBatch& db) {
     RT(rt::set_device(w.device));
     rt::stream_t st = w.stream;
+    w.busy = true;
     uint64_t ip = 0, op = 0;
     uint32_t max_t = 0;
     for (uint32_t i = 0; i < nb; i++) {
