@@ -1,8 +1,9 @@
 /*
  * tsgpu_jni.c — JNI glue between the reference's Java operator surface and the C-ABI of include/tsgpu.h.
- * NOT compiled in this repository's image (no JDK / jni.h); build on the broker host with
+ * There is no JDK in this repository's build image: the tests compile this file against a test-only stand-in for
+ * <jni.h> and drive it through a fake JNIEnv (tests/cpp/test_jni_shim.c).  Build on the broker host with
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude jni/tsgpu_jni.c -L<pkg> -ltsgpu -o libtsgpu_jni.so
- * Java side: jni/io/aiven/kafka/tieredstorage/transform/gpu/*.java (implements TransformChunkEnumeration /
+ * Java side: jni/io/aiven/kafka/tieredstorage/transform/gpu/{TsGpu,GpuTransformChunkEnumeration}.java (implements TransformChunkEnumeration /
  * DetransformChunkEnumeration of the reference, core/M/transform/TransformChunkEnumeration.java:28-42).
  *
  * Buffers are direct ByteBuffers (ideally over tsgpu_host_alloc'ed pinned memory, see allocPinned), so there is no
