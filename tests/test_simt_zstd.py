@@ -140,3 +140,22 @@ def test_simt_index_files_ride_one_ragged_batch(ctx):
     assert np.array_equal(back, src) and osz == [b.size for b in blobs]
     with pytest.raises(tsgpu.TsgpuError):
         ctx.transform_chunks(A, src, [10, 0, 5], key, aad, ivs)
+
+
+def test_simt_two_launch_compressor_matches_the_fused_kernel(ctx, monkeypatch):
+    # TSGPU_ENC_SPLIT=1 runs parse and entropy stage as two launches over the same code (zstd_enc_*.inc): same frames
+    monkeypatch.setenv("TSGPU_ENC_SPLIT", "1")
+    c2 = tsgpu.Context(max_chunk_bytes=1 << 20, max_batch=4, lib_path=SIMT_LIB)
+    try:
+        c2.profile_enable(True)
+        for kind, n, cs in (("K", 200000, 65536), ("R", 40000, 0), ("Z", 70000, 32768), ("M", 150000, 50000), ("K", 5, 0)):
+            src = _mixed(n, 11) if kind == "M" else corpus.gen_segment(kind, 0, n, cs if cs else n)
+            a, asz = ctx.transform(Z, src, cs)
+            b, bsz = c2.transform(Z, src, cs)
+            assert asz == bsz and np.array_equal(a, b)
+            back, _ = ora.detransform_chunks(Z, b, bsz, n)
+            assert np.array_equal(back, src)
+        names = set(c2.profile_report())
+        assert "zstd_enc_parse" in names and "zstd_enc_entropy" in names and "zstd_enc_blocks" not in names
+    finally:
+        c2.close()

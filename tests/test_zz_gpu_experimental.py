@@ -1,0 +1,31 @@
+"""Variants that are off by default and have not been timed yet (they sort last on purpose): the two-launch compressor
+(TSGPU_ENC_SPLIT=1) must produce frames the oracle reads and this library's fetch side reads."""
+import numpy as np
+import pytest
+
+from oracle import oracle as ora
+import tsgpu
+from tsgpu import corpus
+
+Z, A = tsgpu.FLAG_ZSTD, tsgpu.FLAG_AES
+
+
+@pytest.mark.gpu
+def test_gpu_two_launch_compressor(monkeypatch):
+    monkeypatch.setenv("TSGPU_ENC_SPLIT", "1")
+    ctx = tsgpu.Context(max_chunk_bytes=1 << 20, max_batch=8)
+    try:
+        ctx.profile_enable(True)
+        for kind, n, cs in (("K", 5 * (1 << 20) + 777, 1 << 20), ("R", 300000, 65536), ("Z", 70000, 0)):
+            src = corpus.gen_segment(kind, 3, n, cs if cs else n)
+            nch = (n + cs - 1) // cs if cs else 1
+            key, aad, ivs = corpus.fixed_key_material(nch)
+            out, sizes = ctx.transform(Z | A, src, cs, key, aad, ivs)
+            back, _ = ora.detransform_chunks(Z | A, out, sizes, n, key, aad)
+            assert np.array_equal(back, src)
+            mine, _ = ctx.detransform(Z | A, out, sizes, n, key, aad)
+            assert np.array_equal(mine, src)
+        names = set(ctx.profile_report())
+        assert "zstd_enc_parse" in names and "zstd_enc_entropy" in names and "zstd_enc_blocks" not in names
+    finally:
+        ctx.close()

@@ -865,6 +865,8 @@ constexpr uint32_t ZD_SMEM_BYTES = ZD_WPB * sizeof(ZdWarpCtx);
 inline const char* zstd_kernels_configure() {
     const char* e;
     if ((e = rt::allow_smem(zstd_enc_blocks_kernel, ZE_SMEM_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_enc_parse_kernel, ZE_SMEM_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_enc_entropy_kernel, ZE_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_blocks_kernel, ZD_WPB_FAST * ZD_FAST_WARP_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_frames_kernel, ZD_SMEM_BYTES))) return e;
     return nullptr;

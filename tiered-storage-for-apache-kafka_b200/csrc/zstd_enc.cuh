@@ -53,13 +53,15 @@ struct ZstdEncScratch {
     uint32_t* blk_size = nullptr;    // n_chunks * blocks_per_chunk
     uint2* seqs = nullptr;           // n_chunks * blocks_per_chunk * ZE_MAXSEQ
     uint8_t* lits = nullptr;         // n_chunks * blocks_per_chunk * ZB   (literal staging for Huffman)
+    uint32_t* blk_meta = nullptr;    // n_chunks * blocks_per_chunk * 2    (nseq, nlit: only the two-launch variant uses it)
+    bool split = false;              // TSGPU_ENC_SPLIT=1: parse and entropy stage as two launches
     uint32_t blocks_per_chunk = 0;
     uint32_t max_batch = 0;
 };
 
 struct ZstdEncArgs {
     const uint8_t* in_base; const uint64_t* in_off; const uint32_t* in_len;
-    uint8_t* blk_out; uint32_t* blk_size; uint2* seqs; uint8_t* lits;
+    uint8_t* blk_out; uint32_t* blk_size; uint2* seqs; uint8_t* lits; uint32_t* blk_meta;
     uint32_t blocks_per_chunk;
     uint8_t* out_base; const uint64_t* out_off; uint32_t* out_len;
 };
@@ -236,210 +238,23 @@ __device__ TS_NOINLINE void ze_warp_copy(uint8_t* __restrict__ dst, const uint8_
 }
 
 __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __grid_constant__ ZstdEncArgs A) {
-    TS_DYN_SMEM(smem);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const ZeFseShared& fs = *(const ZeFseShared*)&g_pre_ctables;   // predefined tables stay in constant memory
+#include "zstd_enc_prologue.inc"
+#include "zstd_enc_parse.inc"
+#include "zstd_enc_emit.inc"
+}
 
-    const uint32_t chunk = blockIdx.y;
-    const uint32_t blk = blockIdx.x * ZE_WPB + warp;
-    const uint32_t clen = A.in_len[chunk];
-    if ((uint64_t)blk * ZB >= clen) return;                       // whole warp
-    const uint32_t bn = min(ZB, clen - blk * ZB);
-    const bool last_block = (uint64_t)(blk + 1) * ZB >= clen;
-    const uint8_t* src = A.in_base + A.in_off[chunk] + (size_t)blk * ZB;
-    const size_t gblk = (size_t)chunk * A.blocks_per_chunk + blk;
-    uint8_t* out = A.blk_out + gblk * ZE_SLOT;
-    uint2* seqs = A.seqs + gblk * ZE_MAXSEQ;
-    uint8_t* lits = A.lits + gblk * ZB;
-
-    uint8_t* wbase = smem + warp * ZE_SMEM_WARP_AL;
-    uint8_t* buf = wbase;
-    uint16_t* ht = (uint16_t*)(wbase + ZB + ZE_BUF_PAD);
-    uint8_t* codes = buf + ZE_SEQ_AUX_OFF;
-    uint16_t* stv = (uint16_t*)(codes + 96);
-    uint8_t* stn = (uint8_t*)(stv + 96);
-
-    // ---- stage the block in shared memory (128-bit loads when the source is aligned), zero the pad, reset the table
-    if ((((uintptr_t)src) & 15) == 0) {
-        for (uint32_t i = lane * 16; i < bn; i += 512) {
-            if (i + 16 <= bn) *(uint4*)(buf + i) = ldg128_stream((const uint4*)(src + i));
-            else for (uint32_t k = i; k < bn; k++) buf[k] = src[k];
-        }
-    } else {
-        _Pragma("unroll 2")
-        for (uint32_t i = lane; i < bn; i += 32) buf[i] = src[i];
-    }
-    _Pragma("unroll 1")
-    for (uint32_t i = bn + lane; i < ZB + ZE_BUF_PAD; i += 32) buf[i] = 0;
-    for (uint32_t i = lane; i < ZE_HSIZE / 2; i += 32) ((uint32_t*)ht)[i] = 0;
-    __syncwarp();
-
-    // ---- phase A: greedy LZ parse, 32 positions per step
-    // Selection (which of the 32 candidate matches survive, left to right) is the only serial part and costs a
-    // handful of instructions per taken match; sequences are then written by their own lanes in parallel and
-    // literals are gathered in one pass afterwards.
-    uint32_t anchor = 0, cur = 0, nseq = 0;
-    while (cur + 4 <= bn && nseq + 8 <= ZE_MAXSEQ) {                // a step adds at most 8 sequences (min match 4)
-        const uint32_t p = cur + lane;
-        const bool valid = p + 4 <= bn;
-        // unaligned 4-byte reads as a rolling pair of aligned words per stream: one new LDS per stream and step
-        const uint32_t* wp = (const uint32_t*)(buf + (p & ~3u));
-        const uint32_t shp = (p & 3) * 8;
-        uint32_t a0 = wp[0], a1 = wp[1];
-        const uint32_t v = __funnelshift_r(a0, a1, shp);
-        const uint32_t h = ze_hash(v);
-        const uint32_t slot = valid ? ht[h] : 0u;                  // position + 1, 0 = empty
-        __syncwarp();
-        // Lanes of this step that share a slot all store; the CUDA model lets any one of them win.  Every outcome is a
-        // valid parse (candidates are verified before use), so frames may differ in bytes, never in what they decode to.
-        if (valid) ht[h] = (uint16_t)(p + 1);
-        __syncwarp();
-        const uint32_t cand = slot ? slot - 1 : 0u;
-        const uint32_t* wc = (const uint32_t*)(buf + (cand & ~3u));
-        const uint32_t shc = (cand & 3) * 8;
-        uint32_t c0 = wc[0], c1 = wc[1];
-        const bool ok = slot != 0 && __funnelshift_r(c0, c1, shc) == v;
-        uint32_t len = 0;
-        if (ok) {
-            len = 4;
-            const uint32_t lim = min(bn - p, 4 + ZE_LANE_EXT);
-            for (uint32_t k = 2; len < lim; k++) {
-                a0 = a1; a1 = wp[k]; c0 = c1; c1 = wc[k];
-                const uint32_t c = ze_common_bytes(__funnelshift_r(a0, a1, shp) ^ __funnelshift_r(c0, c1, shc));
-                len += c;
-                if (c < 4) break;
-            }
-            len = min(len, lim);
-        }
-        const uint32_t mask = __ballot_sync(TS_FULL, ok && len >= ZE_MIN_MATCH);
-        // Greedy selection, left to right.  Every lane precomputes where its match would end and which candidate would
-        // come next, so one shuffle per taken match walks the chain (the only serial part of the parse).
-        const uint32_t e = lane + len;
-        const uint32_t mnext = e < 32 ? mask & (0xffffffffu << e) : 0u;
-        const uint32_t nxt = mnext ? (uint32_t)__ffs((int)mnext) - 1 : 32u;
-        const bool capped = ok && len == 4 + ZE_LANE_EXT && p + len < bn;
-        const uint32_t packed = e | (nxt << 8) | (capped ? 1u << 16 : 0u);
-        uint32_t taken = 0, pos = 0;
-        uint32_t f = mask ? (uint32_t)__ffs((int)mask) - 1 : 32u;
-        while (f < 32) {
-            const uint32_t info = __shfl_sync(TS_FULL, packed, f);
-            uint32_t end = info & 0xffu, nf = (info >> 8) & 0xffu;
-            if (info >> 16) {                                      // warp-wide extension of a long match
-                uint32_t L = 4 + ZE_LANE_EXT;
-                const uint32_t off = __shfl_sync(TS_FULL, p - cand, f);
-                const uint32_t mpos = cur + f;
-                while (true) {
-                    const uint32_t q = mpos + L + 4 * lane;
-                    uint32_t c = 0;
-                    if (q < bn) {
-                        c = ze_common_bytes(ld_u32_unaligned(buf + q) ^ ld_u32_unaligned(buf + q - off));
-                        c = min(c, bn - q);
-                    }
-                    const uint32_t stop = __ballot_sync(TS_FULL, c < 4);
-                    if (stop) {
-                        const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
-                        L += 4 * fl + __shfl_sync(TS_FULL, c, fl);
-                        break;
-                    }
-                    L += 128;
-                }
-                if (lane == f) len = L;
-                end = f + L;
-                const uint32_t m2 = end < 32 ? mask & (0xffffffffu << end) : 0u;
-                nf = m2 ? (uint32_t)__ffs((int)m2) - 1 : 32u;
-            }
-            taken |= 1u << f;
-            pos = end;
-            f = nf;
-        }
-        if (taken) {
-            const uint32_t my_end = p + len;                       // meaningful on taken lanes
-            const uint32_t lower = taken & ((1u << lane) - 1);
-            const uint32_t prev_lane = lower ? (uint32_t)(31 - __clz((int)lower)) : 0u;
-            uint32_t prev_end = __shfl_sync(TS_FULL, my_end, prev_lane);
-            if (!lower) prev_end = anchor;
-            if ((taken >> lane) & 1)
-                seqs[nseq + (uint32_t)__popc(lower)] = make_uint2((p - prev_end) | ((len - 3) << 16), p - cand);
-            nseq += (uint32_t)__popc(taken);
-            anchor = cur + pos;
-        }
-        cur = max(cur + 32, anchor);
-    }
-    __syncwarp();
-    __threadfence_block();
-    // ---- literal gather: one lane per sequence copies its literal run; long runs are finished by the whole warp
-    uint32_t nlit = 0;
-    {
-        uint32_t src_pos = 0;
-        uint2 pre = lane < nseq ? seqs[lane] : make_uint2(0, 0);
-        for (uint32_t t0 = 0; t0 < nseq; t0 += 32) {
-            const uint32_t i = t0 + lane;
-            uint32_t ll = 0, ml = 0;
-            const uint2 sq = pre;
-            if (i + 32 < nseq) pre = seqs[i + 32];
-            if (i < nseq) { ll = sq.x & 0xffff; ml = (sq.x >> 16) + 3; }
-            const uint32_t inc_l = warp_inclusive_scan_u32(ll, lane), inc_s = warp_inclusive_scan_u32(ll + ml, lane);
-            const uint32_t lo = nlit + inc_l - ll, so = src_pos + inc_s - ll - ml;
-            const uint32_t quick = min(ll, 16u);
-            for (uint32_t k = 0; k < quick; k++) lits[lo + k] = buf[so + k];
-            uint32_t longs = __ballot_sync(TS_FULL, ll > 16);
-            while (longs) {
-                const uint32_t f = (uint32_t)__ffs((int)longs) - 1;
-                longs &= longs - 1;
-                const uint32_t flo = __shfl_sync(TS_FULL, lo, f), fso = __shfl_sync(TS_FULL, so, f), fll = __shfl_sync(TS_FULL, ll, f);
-                for (uint32_t k = 16 + lane; k < fll; k += 32) lits[flo + k] = buf[fso + k];
-            }
-            nlit += __shfl_sync(TS_FULL, inc_l, 31);
-            src_pos += __shfl_sync(TS_FULL, inc_s, 31);
-        }
-        const uint32_t ll = bn - anchor;                           // trailing literals
-        ze_warp_copy(lits + nlit, buf + anchor, ll, lane);
-        nlit += ll;
-    }
-    __syncwarp();
-    __threadfence_block();
-
-    // ---- phase B: entropy stage into the (now free) shared block buffer, then emit
-    uint32_t payload = 0xffffffffu;                                // "not compressible"
-    {
-        // literals section first (into `out` directly), then the sequences bit stream staged in `buf`
-        uint8_t* body = out + 3;
-        const uint32_t lit_bytes = ze_encode_literals(lits, nlit, body, (uint32_t*)buf, ht, lane);   // header + payload
-        __syncwarp();
-        if (nseq == 0) {
-            // no match at all: the block may still be worth a compressed block with entropy-coded literals and zero sequences
-            if (lit_bytes + 1 < bn) {
-                if (lane == 0) body[lit_bytes] = 0;                // Number_of_Sequences = 0: the sequences section ends here
-                payload = lit_bytes + 1;
-            }
-        } else {
-            const uint32_t shdr = nseq < 128 ? 1u : (nseq < 0x7f00 ? 2u : 3u);
-            uint8_t* sp = body + lit_bytes;
-            uint32_t desc_bytes = 0;
-            const uint32_t sbytes = ze_encode_sequences(seqs, nseq, (uint32_t*)buf, (ZeCTab*)ht, codes, stv, stn, &fs, sp + shdr, &desc_bytes, lane);
-            const uint32_t total = lit_bytes + shdr + desc_bytes + sbytes;
-            if (total < bn) {
-                if (lane == 0) {
-                    if (shdr == 1) sp[0] = (uint8_t)nseq;
-                    else if (shdr == 2) { sp[0] = (uint8_t)((nseq >> 8) + 0x80); sp[1] = (uint8_t)nseq; }
-                    else { sp[0] = 0xff; sp[1] = (uint8_t)(nseq - 0x7f00); sp[2] = (uint8_t)((nseq - 0x7f00) >> 8); }
-                }
-                _Pragma("unroll 2")
-                for (uint32_t i = lane; i < sbytes; i += 32) sp[shdr + desc_bytes + i] = buf[i];
-                payload = total;
-            }
-        }
-    }
-    if (payload == 0xffffffffu) {                                  // Raw_Block
-        ze_warp_copy(out + 3, src, bn, lane);
-    }
-    if (lane == 0) {
-        const uint32_t type = payload == 0xffffffffu ? 0u : 2u;
-        const uint32_t bsize = payload == 0xffffffffu ? bn : payload;
-        const uint32_t hdr = (last_block ? 1u : 0u) | (type << 1) | (bsize << 3);
-        out[0] = (uint8_t)hdr; out[1] = (uint8_t)(hdr >> 8); out[2] = (uint8_t)(hdr >> 16);
-        A.blk_size[gblk] = 3 + bsize;
-    }
+// The same block compressor as two launches (TSGPU_ENC_SPLIT=1; off by default): the parse kernel's hot loop is a few KB
+// of SASS that stays in the instruction caches, instead of competing with the entropy stage's code in one 90 KB kernel.
+// Sequences and literals already travel through global scratch, so the split adds 8 bytes of per-block state.
+__global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_parse_kernel(const __grid_constant__ ZstdEncArgs A) {
+#include "zstd_enc_prologue.inc"
+#include "zstd_enc_parse.inc"
+    if (lane == 0) { A.blk_meta[2 * gblk] = nseq; A.blk_meta[2 * gblk + 1] = nlit; }
+}
+__global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_entropy_kernel(const __grid_constant__ ZstdEncArgs A) {
+#include "zstd_enc_prologue.inc"
+    const uint32_t nseq = A.blk_meta[2 * gblk], nlit = A.blk_meta[2 * gblk + 1];
+#include "zstd_enc_emit.inc"
 }
 
 // ------------------------------------------------------------------------------------------ frame assembly
@@ -522,10 +337,12 @@ inline const char* zstd_enc_scratch_alloc(ZstdEncScratch& s, uint32_t chunk_cap,
     if ((e = rt::malloc_device((void**)&s.blk_size, nblk * 4 + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.seqs, nblk * ZE_MAXSEQ * sizeof(uint2) + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.lits, nblk * ZB + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.blk_meta, nblk * 8 + 256))) return e;
+    { const char* v = getenv("TSGPU_ENC_SPLIT"); s.split = v && atoi(v) != 0; }
     return nullptr;
 }
 inline void zstd_enc_scratch_free(ZstdEncScratch& s) {
-    rt::free_device(s.blk_out); rt::free_device(s.blk_size); rt::free_device(s.seqs); rt::free_device(s.lits);
+    rt::free_device(s.blk_out); rt::free_device(s.blk_size); rt::free_device(s.seqs); rt::free_device(s.lits); rt::free_device(s.blk_meta);
     s = ZstdEncScratch{};
 }
 
@@ -539,12 +356,17 @@ inline int zstd_compress_batch(ZstdEncScratch& s, rt::stream_t st, const uint8_t
     if (bpc > s.blocks_per_chunk) { g_zstd_err = "chunk larger than the context"; return -1; }
     ZstdEncArgs A;
     A.in_base = in_base; A.in_off = d_in_off; A.in_len = d_in_len;
-    A.blk_out = s.blk_out; A.blk_size = s.blk_size; A.seqs = s.seqs; A.lits = s.lits;
+    A.blk_out = s.blk_out; A.blk_size = s.blk_size; A.seqs = s.seqs; A.lits = s.lits; A.blk_meta = s.blk_meta;
     A.blocks_per_chunk = s.blocks_per_chunk;
     A.out_base = out_base; A.out_off = d_out_off; A.out_len = d_out_len;
     if (bpc) {
-        TS_LAUNCH_P(prof, "zstd_enc_blocks", zstd_enc_blocks_kernel, dim3((bpc + ZE_WPB - 1) / ZE_WPB, n_chunks), dim3(ZE_WPB * 32),
-                    ZE_SMEM_BYTES, st, A);
+        const dim3 grid((bpc + ZE_WPB - 1) / ZE_WPB, n_chunks), block(ZE_WPB * 32);
+        if (!s.split) {
+            TS_LAUNCH_P(prof, "zstd_enc_blocks", zstd_enc_blocks_kernel, grid, block, ZE_SMEM_BYTES, st, A);
+        } else {
+            TS_LAUNCH_P(prof, "zstd_enc_parse", zstd_enc_parse_kernel, grid, block, ZE_SMEM_BYTES, st, A);
+            TS_LAUNCH_P(prof, "zstd_enc_entropy", zstd_enc_entropy_kernel, grid, block, ZE_SMEM_BYTES, st, A);
+        }
         const char* e = rt::last_error();
         if (e) { g_zstd_err = e; return -7; }
     }
