@@ -9,3 +9,7 @@ python bench.py --corpus R --steps 3 --warmup 2 --no-e2e --no-cpu-baseline 2>/de
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('R value %.1f GiB/s  ratio %.3f' % (d['value'], d['compression_ratio']), {k: round(v['ms'], 2) for k, v in d['kernels_ms_per_step'].items()})"
+TSGPU_ENC_SPLIT=1 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('K (two-launch compressor) value %.1f GiB/s  ratio %.3f' % (d['value'], d['compression_ratio']), {k: round(v['ms'], 2) for k, v in d['kernels_ms_per_step'].items()})"
