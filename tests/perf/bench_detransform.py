@@ -1,8 +1,8 @@
 """Detransform (fetch side) throughput probe: device-resident decrypt+decompress of (a) this library's frames
 (per-block fast path), (b) libzstd level-3 frames (general path), and (c) the config-5 ranged fetch
 (16 MiB window = 4 chunks) through the host C-ABI."""
-import json, sys, time
-sys.path.insert(0, '.')
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import tsgpu
 from tsgpu import corpus
