@@ -51,3 +51,23 @@ def test_simt_aad_lengths(simt_ctx):
         want, _ = ora.transform_segment(ora.FLAG_AES, src, 0, key, aad, ivs)
         got, _ = simt_ctx.transform(tsgpu.FLAG_AES, src, 0, key, aad, ivs)
         assert np.array_equal(got, want)
+
+
+def test_simt_key_tables_follow_the_key_across_calls(simt_ctx):
+    # a slot keeps its GHASH tables while calls use the same key (one data key per segment) and rebuilds them when it changes
+    rng = np.random.default_rng(99)
+    src = rng.integers(0, 256, 50000, dtype=np.uint8)
+    k1, k2, aad = rng.bytes(32), rng.bytes(32), rng.bytes(32)
+    ivs = rng.bytes(12 * 4)
+    for key in (k1, k1, k2, k1, k2, k2):
+        want, wsizes = ora.transform_segment(ora.FLAG_AES, src, 16384, key, aad, ivs)
+        got, gsizes = simt_ctx.transform(tsgpu.FLAG_AES, src, 16384, key, aad, ivs)
+        assert gsizes == wsizes and np.array_equal(got, want)
+        back, _ = simt_ctx.detransform(tsgpu.FLAG_AES, want, wsizes, src.size, key, aad)
+        assert np.array_equal(back, src)
+    simt_ctx.profile_enable(True)
+    simt_ctx.transform(tsgpu.FLAG_AES, src, 16384, k2, aad, ivs)      # same key as the previous call: no set-up launch
+    assert "gcm_key_setup" not in simt_ctx.profile_report()
+    simt_ctx.transform(tsgpu.FLAG_AES, src, 16384, k1, aad, ivs)
+    assert "gcm_key_setup" in simt_ctx.profile_report()
+    simt_ctx.profile_enable(False)

@@ -29,3 +29,22 @@ def test_gpu_two_launch_compressor(monkeypatch):
         assert "zstd_enc_parse" in names and "zstd_enc_entropy" in names and "zstd_enc_blocks" not in names
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_key_tables_follow_the_key_across_calls():
+    # the slot's GHASH tables are kept while the key stays the same and rebuilt when it changes (bit-exact either way)
+    rng = np.random.default_rng(99)
+    src = rng.integers(0, 256, 3 * (1 << 20) + 5, dtype=np.uint8)
+    k1, k2, aad = rng.bytes(32), rng.bytes(32), rng.bytes(32)
+    ivs = rng.bytes(12 * 4)
+    ctx = tsgpu.Context(max_chunk_bytes=1 << 20, max_batch=2)
+    try:
+        for key in (k1, k1, k2, k1, k2, k2):
+            want, wsizes = ora.transform_segment(ora.FLAG_AES, src, 1 << 20, key, aad, ivs)
+            got, gsizes = ctx.transform(A, src, 1 << 20, key, aad, ivs)
+            assert gsizes == wsizes and np.array_equal(got, want)
+            back, _ = ctx.detransform(A, want, wsizes, src.size, key, aad)
+            assert np.array_equal(back, src)
+    finally:
+        ctx.close()

@@ -58,7 +58,8 @@ struct Work {
     rt::event_t ev_sizes{}, ev_done{};
     bool out_pending = false;              // a copy-out on out_stream still reads this slot's final buffer
     bool busy = false, ready = false;
-    uint64_t key_epoch = 0;        // host call whose key this slot's GcmKeyCtx currently holds
+    Aes256RoundKeys key_rk{};      // the key this slot's GcmKeyCtx (H powers, Shoup table) was built for
+    bool key_valid = false;        //   ... consecutive calls with one segment's data key skip the set-up kernel
     uint8_t* d_orig = nullptr;     // max_batch * chunk_cap
     uint8_t* d_frames = nullptr;   // max_batch * frame_stride        (zstd frames, 16-byte aligned slots)
     uint8_t* d_xf = nullptr;       // max_batch * slot_stride         (transformed slots)
@@ -85,7 +86,6 @@ struct tsgpu_ctx {
     LaunchProf prof;
     uint32_t nslot = 8;            // work slots per device in flight (TSGPU_SLOTS overrides; measured best with batches of 4 x 4 MiB)
     bool split_out = true;         // copies-out ride their own stream (the slot's next batch starts behind an event, not behind them)
-    uint64_t call_epoch = 0;       // one key per host call: a slot builds its H tables once per call, not once per batch
 };
 
 static void carve_desc(uint8_t* base, uint32_t nb, Desc& d, size_t* total) {
@@ -134,6 +134,7 @@ static void work_free(Work& w) {
     rt::free_device(w.d_desc); rt::free_host(w.h_desc);
     rt::free_device(w.d_partials); rt::free_device(w.d_keyctx); rt::free_host(w.h_sizes);
     zstd_enc_scratch_free(w.zenc); zstd_dec_scratch_free(w.zdec);
+    memset(&w.key_rk, 0, sizeof w.key_rk); w.key_valid = false;
     rt::event_destroy(w.ev_sizes); rt::event_destroy(w.ev_done);
     rt::stream_destroy(w.stream); rt::stream_destroy(w.out_stream);
 }
@@ -286,8 +287,8 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
         xb.final_base = w.d_frames; xb.final_stride = c->frame_stride; xb.final_head = 0;
     }
     if (flags & TSGPU_FLAG_AES) {
-        const bool key_ready = w.key_epoch == c->call_epoch;
-        w.key_epoch = c->call_epoch;
+        const bool key_ready = w.key_valid && memcmp(&w.key_rk, &rk, sizeof rk) == 0;
+        w.key_rk = rk; w.key_valid = true;
         { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }                                  // d_xf is the final buffer
         int rc = gcm_stage<true>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, w.d_xf, w.dd.c_off, w.dd.c_len,
                                  w.dd.ivs, w.dd.aad, aad_len, w.dd.status, nb, cur_max, w.d_partials, w.max_ranges);
@@ -374,7 +375,6 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
     }
     Aes256RoundKeys rk{};
     if (flags & TSGPU_FLAG_AES) rk = aes256_expand_key(key);
-    c->call_epoch++;
 
     const uint32_t nbatches = (n + c->max_batch - 1) / c->max_batch;
     const uint32_t nwork = (uint32_t)c->lanes.size() * c->nslot;
@@ -460,8 +460,8 @@ static int detransform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_
         uint8_t* ob = z ? w.d_frames : w.d_orig;
         const uint64_t* oo = z ? w.dd.b_off : w.dd.a_off;
         uint32_t* ol = z ? w.dd.b_len : w.dd.a_len;
-        const bool key_ready = w.key_epoch == c->call_epoch;
-        w.key_epoch = c->call_epoch;
+        const bool key_ready = w.key_valid && memcmp(&w.key_rk, &rk, sizeof rk) == 0;
+        w.key_rk = rk; w.key_valid = true;
         if (!z) { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }                          // d_orig is the final buffer
         int rc = gcm_stage<false>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
                                   w.dd.status, nb, max_t, w.d_partials, w.max_ranges);
@@ -507,7 +507,6 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     }
     Aes256RoundKeys rk{};
     if (flags & TSGPU_FLAG_AES) rk = aes256_expand_key(key);
-    c->call_epoch++;
 
     const uint32_t nbatches = (n_chunks + c->max_batch - 1) / c->max_batch;
     const uint32_t nwork = (uint32_t)c->lanes.size() * c->nslot;
@@ -619,6 +618,7 @@ extern "C" int tsgpu_transform_device(tsgpu_ctx* c, int device_index, uint32_t f
         cur_base = fb; cur_off = fo; cur_len = fl; cur_max = (uint32_t)frame_bound(cs);
     }
     if (flags & TSGPU_FLAG_AES) {
+        w.key_valid = false;                                 // built on the caller's stream: do not reuse across calls
         rc = gcm_stage<true>(c, w, st, rk, false, cur_base, cur_off, cur_len, d_slots, w.dd.c_off, d_transformed_sizes,
                              w.dd.ivs, w.dd.aad, aad_len, w.dd.status, nb, cur_max, w.d_partials, w.max_ranges);
         if (rc) return rc;
@@ -656,6 +656,7 @@ extern "C" int tsgpu_detransform_device(tsgpu_ctx* c, int device_index, uint32_t
         const uint64_t* oo = z ? w.dd.b_off : w.dd.a_off;
         uint32_t* ol = z ? w.dd.b_len : d_original_sizes;
         uint32_t max_t = (uint32_t)(slot_stride - TSGPU_SLOT_HEAD);
+        w.key_valid = false;
         rc = gcm_stage<false>(c, w, st, rk, false, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
                               d_status, n_chunks, max_t, w.d_partials, w.max_ranges);
         if (rc) return rc;
