@@ -98,8 +98,18 @@ static void carve_desc(uint8_t* base, uint32_t nb, Desc& d, size_t* total) {
     if (total) *total = p;
 }
 
+static void work_free(Work& w);
+static int work_init_impl(tsgpu_ctx* c, Work& w, int device);
+// A slot that could not be fully allocated (out of memory on a busy GPU) is released again and stays "not ready", so a
+// later call retries instead of running on half-initialised buffers.
 static int work_init(tsgpu_ctx* c, Work& w, int device) {
-    w.device = device; w.ready = true;
+    const int rc = work_init_impl(c, w, device);
+    if (rc) { work_free(w); w = Work{}; w.device = device; }
+    else w.ready = true;
+    return rc;
+}
+static int work_init_impl(tsgpu_ctx* c, Work& w, int device) {
+    w.device = device;
     RT(rt::set_device(device));
     RT(rt::stream_create(&w.stream));
     RT(rt::stream_create(&w.out_stream));
