@@ -28,12 +28,17 @@
 namespace ts {
 
 constexpr uint32_t ZB = 8192;                  // bytes of original data per zstd block
-constexpr int ZE_HLOG = 10;                    // per-warp hash table: 2^10 x u16 (position + 1)
+#ifndef ZE_TUNE_HLOG                           // the ZE_TUNE_* macros exist for parameter studies (-DZE_TUNE_...=v); the defaults are the product
+#define ZE_TUNE_HLOG 10
+#define ZE_TUNE_MIN_MATCH 5
+#define ZE_TUNE_LANE_EXT 12
+#endif
+constexpr int ZE_HLOG = ZE_TUNE_HLOG;          // per-warp hash table: 2^10 x u16 (position + 1)
 constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
 constexpr int ZE_WPB = 4;                      // warps (= blocks in flight) per CTA
 constexpr uint32_t ZE_MAXSEQ = ZB / 8;         // sequences kept per block; beyond that the rest goes out as literals
-constexpr uint32_t ZE_MIN_MATCH = 5;           // a 4-byte match costs more bits than four Huffman-coded literals (libzstd level 3 also uses 5)
-constexpr uint32_t ZE_LANE_EXT = 12;           // bytes a lane extends its own match beyond the first 4
+constexpr uint32_t ZE_MIN_MATCH = ZE_TUNE_MIN_MATCH;   // 5: a 4-byte match costs more bits than four Huffman-coded literals (libzstd level 3 also uses 5)
+constexpr uint32_t ZE_LANE_EXT = ZE_TUNE_LANE_EXT;     // 12: bytes a lane extends its own match beyond the first 4
 constexpr uint32_t ZE_BUF_PAD = 160;
 constexpr uint32_t ZE_SLOT = ZB + 512;         // per-block output slot: 3-byte header + payload (< ZB once accepted; table descriptions are written before that is known)
 constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 2;   // buf, ht
@@ -104,6 +109,8 @@ static inline unsigned __match_any_sync(unsigned, unsigned v) {
 
 #include "zstd_fse_enc.cuh"
 #include "zstd_huf_enc.cuh"
+static_assert(sizeof(ts::ZeCTab) <= ts::ZE_HSIZE * 2 && 2048 <= ts::ZE_HSIZE * 2,
+              "phase B aliases the FSE encoding tables and the 2 KiB Huffman histogram/code table into the hash-table area");
 
 namespace ts {
 
