@@ -588,7 +588,7 @@ extern "C" int tsgpu_transform_device(tsgpu_ctx* c, int device_index, uint32_t f
                                       uint32_t chunk_size, const uint8_t key[32], const uint8_t* aad, uint32_t aad_len,
                                       const uint8_t* ivs, uint8_t* d_slots, uint64_t slot_stride,
                                       uint32_t* d_transformed_sizes, void* stream) {
-    Work* wp; int rc = pick_work(c, device_index, &wp); if (rc) return rc;
+    Work* wp = nullptr; int rc = pick_work(c, device_index, &wp); if (rc) return rc;
     Work& w = *wp;
     if (flags == 0 || (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES))) return fail(TSGPU_E_ARG, "flags must name zstd and/or aes");
     if (chunk_size == 0 || chunk_size > c->chunk_cap) return fail(TSGPU_E_ARG, "chunk_size out of range for this context");
@@ -640,7 +640,7 @@ extern "C" int tsgpu_detransform_device(tsgpu_ctx* c, int device_index, uint32_t
                                         uint64_t slot_stride, const uint32_t* d_transformed_sizes, uint32_t n_chunks,
                                         uint32_t chunk_size, const uint8_t key[32], const uint8_t* aad, uint32_t aad_len,
                                         uint8_t* d_dst, uint32_t* d_original_sizes, uint32_t* d_status, void* stream) {
-    Work* wp; int rc = pick_work(c, device_index, &wp); if (rc) return rc;
+    Work* wp = nullptr; int rc = pick_work(c, device_index, &wp); if (rc) return rc;
     Work& w = *wp;
     if (flags == 0 || (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES))) return fail(TSGPU_E_ARG, "flags must name zstd and/or aes");
     if (chunk_size == 0 || chunk_size > c->chunk_cap) return fail(TSGPU_E_ARG, "chunk_size out of range for this context");
