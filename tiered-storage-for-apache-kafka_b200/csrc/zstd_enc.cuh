@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __gr
 __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_parse_kernel(const __grid_constant__ ZstdEncArgs A) {
 #include "zstd_enc_prologue.inc"
 #include "zstd_enc_parse.inc"
+    (void)fs; (void)last_block; (void)out; (void)stn;              // the prologue is shared with the entropy stage
     if (lane == 0) { A.blk_meta[2 * gblk] = nseq; A.blk_meta[2 * gblk + 1] = nlit; }
 }
 __global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_entropy_kernel(const __grid_constant__ ZstdEncArgs A) {
