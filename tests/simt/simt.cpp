@@ -1,5 +1,6 @@
 // simt.cpp — fiber scheduler of the TEST-ONLY SIMT emulator (see simt.h).
 #define TSGPU_SIMT 1
+#include <cstdlib>
 #include "simt.h"
 
 namespace simt {
@@ -72,9 +73,14 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, std::function<void()> 
         g_stacks.push_back((uint8_t*)p);
     }
     std::vector<uint8_t> smem(dyn_smem_bytes + 64);
+    // TSGPU_SIMT_POISON=1: shared memory starts as garbage for every block, as on the device (a kernel that relies on
+    // zeroed shared memory passes the plain emulator and fails on a GPU)
+    static const bool poison = getenv("TSGPU_SIMT_POISON") && atoi(getenv("TSGPU_SIMT_POISON")) != 0;
+    uint32_t poison_seed = 0x9E3779B9u;
     for (unsigned bz = 0; bz < grid.z; bz++)
     for (unsigned by = 0; by < grid.y; by++)
     for (unsigned bx = 0; bx < grid.x; bx++) {
+        if (poison) { for (auto& v : smem) { poison_seed = poison_seed * 1664525u + 1013904223u; v = (uint8_t)(poison_seed >> 24); } }
         Block b;
         b.bid = uint3{bx, by, bz};
         b.bdim = block; b.gdim = grid;

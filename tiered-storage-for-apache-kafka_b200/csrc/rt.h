@@ -15,7 +15,12 @@ typedef void* stream_t;
 typedef int event_t;
 inline int device_count() { return 1; }
 inline const char* set_device(int) { return nullptr; }
-inline const char* malloc_device(void** p, size_t n) { *p = calloc(1, n + 64); return *p ? nullptr : "calloc failed"; }
+inline bool poison() { static const bool on = getenv("TSGPU_SIMT_POISON") && atoi(getenv("TSGPU_SIMT_POISON")) != 0; return on; }
+inline const char* malloc_device(void** p, size_t n) {      // cudaMalloc does not zero memory: TSGPU_SIMT_POISON=1 fills it with 0xCD
+    *p = calloc(1, n + 64);
+    if (*p && poison()) memset(*p, 0xCD, n + 64);
+    return *p ? nullptr : "calloc failed";
+}
 inline void free_device(void* p) { free(p); }
 inline const char* malloc_host(void** p, size_t n) { *p = calloc(1, n + 64); return *p ? nullptr : "calloc failed"; }
 inline void free_host(void* p) { free(p); }
