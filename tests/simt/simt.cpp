@@ -1,6 +1,7 @@
 // simt.cpp — fiber scheduler of the TEST-ONLY SIMT emulator (see simt.h).
 #define TSGPU_SIMT 1
 #include <cstdlib>
+#include <cstring>
 #include "simt.h"
 
 namespace simt {
@@ -8,6 +9,13 @@ Block* g_blk = nullptr;
 Fiber* g_cur = nullptr;
 size_t g_collectives = 0;
 static const size_t STACK = 256 * 1024;
+// TSGPU_SIMT_ORDER=reverse: lanes run from the highest index down between synchronisation points.  In ascending order
+// lane 0 always runs first, which hides a missing __syncwarp() after a "lane 0 writes, everyone reads" section.
+static const bool g_reverse = getenv("TSGPU_SIMT_ORDER") && !strncmp(getenv("TSGPU_SIMT_ORDER"), "rev", 3);
+// TSGPU_SIMT_ORDER=random[:seed]: the next lane to run is drawn at random at every synchronisation point
+static const bool g_random = getenv("TSGPU_SIMT_ORDER") && !strncmp(getenv("TSGPU_SIMT_ORDER"), "random", 6);
+static uint32_t g_rng = g_random && strchr(getenv("TSGPU_SIMT_ORDER"), ':') ? (uint32_t)atoi(strchr(getenv("TSGPU_SIMT_ORDER"), ':') + 1) * 2654435761u + 1u : 12345u;
+static inline uint32_t next_rand() { g_rng ^= g_rng << 13; g_rng ^= g_rng >> 17; g_rng ^= g_rng << 5; return g_rng; }
 
 asm(R"(
 .text
@@ -52,8 +60,11 @@ void yield() {
     Block& b = *g_blk;
     int n = (int)b.fibers.size();
     int me = b.cur;
-    for (int k = 1; k < n; k++) {
-        int t = me + k; if (t >= n) t -= n;
+    const int start = g_random ? (int)(next_rand() % (uint32_t)n) : 0;
+    for (int k = 1; k <= n; k++) {
+        int t = g_random ? start + k : g_reverse ? me - k : me + k;
+        t %= n; if (t < 0) t += n;
+        if (t == me) continue;
         if (!b.fibers[t].done) {
             Fiber* from = &b.fibers[me];
             b.cur = t; g_cur = &b.fibers[t];
@@ -106,7 +117,8 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, std::function<void()> 
         // run until every fiber is done; each return to the scheduler means one fiber finished
         while (b.alive > 0) {
             int t = -1;
-            for (int k = 0; k < nthreads; k++) if (!b.fibers[k].done) { t = k; break; }
+            if (g_reverse) { for (int k = nthreads - 1; k >= 0; k--) if (!b.fibers[k].done) { t = k; break; } }
+            else for (int k = 0; k < nthreads; k++) if (!b.fibers[k].done) { t = k; break; }
             if (t < 0) break;
             b.cur = t; g_cur = &b.fibers[t];
             simt_switch(&b.sched_sp, b.fibers[t].sp);

@@ -152,7 +152,8 @@ def test_simt_two_launch_compressor_matches_the_fused_kernel(ctx, monkeypatch):
             src = _mixed(n, 11) if kind == "M" else corpus.gen_segment(kind, 0, n, cs if cs else n)
             a, asz = ctx.transform(Z, src, cs)
             b, bsz = c2.transform(Z, src, cs)
-            assert asz == bsz and np.array_equal(a, b)
+            if not os.environ.get("TSGPU_SIMT_ORDER", "").startswith("random"):     # which same-slot store wins depends on lane order
+                assert asz == bsz and np.array_equal(a, b)
             back, _ = ora.detransform_chunks(Z, b, bsz, n)
             assert np.array_equal(back, src)
         names = set(c2.profile_report())
