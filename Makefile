@@ -25,9 +25,14 @@ tests/simt/libtsgpu_simt.so: $(CSRC)/tsgpu.cu $(HDRS) tests/simt/simt.h tests/si
 tests/simt/libtsgpu_simt_asan.so: $(CSRC)/tsgpu.cu $(HDRS) tests/simt/simt.h tests/simt/simt.cpp
 	g++ -O1 -g -std=c++17 -fPIC -shared -fsanitize=address -DTSGPU_SIMT=1 -Itests/simt -I$(CSRC) -x c++ $(CSRC)/tsgpu.cu tests/simt/simt.cpp \
 	    -o $@ -Wno-unknown-pragmas
+# TEST-ONLY: the emulator build under UndefinedBehaviorSanitizer: shift counts >= width (x86 masks them, a GPU clamps) and
+# misaligned vector accesses (x86 tolerates them, a GPU faults) are the two that matter
+tests/simt/libtsgpu_simt_ubsan.so: $(CSRC)/tsgpu.cu $(HDRS) tests/simt/simt.h tests/simt/simt.cpp
+	g++ -O1 -g -std=c++17 -fPIC -shared -fsanitize=undefined -fno-sanitize=vptr -fno-sanitize-recover=undefined -DTSGPU_SIMT=1 -Itests/simt -I$(CSRC) -x c++ $(CSRC)/tsgpu.cu tests/simt/simt.cpp \
+	    -o $@ -Wno-unknown-pragmas
 
 clean:
-	rm -f $(PKG)/libtsgpu.so tests/simt/libtsgpu_simt.so tests/simt/libtsgpu_simt_asan.so build_ptxas.log
+	rm -f $(PKG)/libtsgpu.so tests/simt/libtsgpu_simt.so tests/simt/libtsgpu_simt_asan.so tests/simt/libtsgpu_simt_ubsan.so build_ptxas.log
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean libtsgpu.so
 

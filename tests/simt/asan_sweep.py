@@ -1,4 +1,4 @@
-"""Run by tests/test_simt_asan.py in a subprocess with libasan preloaded: both directions of the emulated kernels over a
+"""Run by tests/test_simt_asan.py in a subprocess with libasan / libubsan preloaded (argv[1] = the library to load): both directions of the emulated kernels over a
 sweep of shapes (block/chunk boundaries, incompressible and constant data, binary alphabets, ragged batches, AES)."""
 import os
 import sys
@@ -10,7 +10,7 @@ import tsgpu  # noqa: E402
 from tsgpu import corpus  # noqa: E402
 from oracle import oracle as ora  # noqa: E402
 
-lib = os.path.join(ROOT, "tests", "simt", "libtsgpu_simt_asan.so")
+lib = os.path.join(ROOT, "tests", "simt", sys.argv[1] if len(sys.argv) > 1 else "libtsgpu_simt_asan.so")
 c = tsgpu.Context(max_chunk_bytes=1 << 18, max_batch=4, lib_path=lib)
 rng = np.random.default_rng(3)
 cases = []
@@ -47,4 +47,4 @@ try:
 except tsgpu.TsgpuError:
     pass
 c.close()
-print("asan sweep ok", len(cases))
+print("sanitizer sweep ok", len(cases))
