@@ -353,327 +353,16 @@ __device__ TS_NOINLINE int32_t zd_seq_table(uint32_t mode, int kind, const uint8
 __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint32_t bsize, uint8_t* dst, uint64_t hist,
                                                         uint32_t limit, ZdWarpCtx* cx, uint8_t* litbuf, uint32_t litcap,
                                                         bool fast_nonfirst, uint32_t lane) {
-    // ---- literals section header (lane 0), shared through cx->tmp
-    if (lane == 0) {
-        uint32_t* t = cx->tmp;
-        t[0] = 0;                                       // ok flag
-        do {
-            if (bsize < 2) break;                       // Compressed_Block needs at least literals header + seq header
-            const uint32_t b0 = blk[0], type = b0 & 3, sf = (b0 >> 2) & 3;
-            uint32_t hs, regen, comp = 0, streams = 1;
-            if (type < 2) {
-                if ((sf & 1) == 0) { hs = 1; regen = b0 >> 3; }
-                else if (sf == 1) { hs = 2; regen = (b0 >> 4) | ((uint32_t)blk[1] << 4); }
-                else { if (bsize < 3) break; hs = 3; regen = (b0 >> 4) | ((uint32_t)blk[1] << 4) | ((uint32_t)blk[2] << 12); }
-                comp = type == 0 ? regen : 1;
-            } else {
-                if (bsize < 5) break;
-                const uint32_t h = blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
-                if (sf <= 1) { hs = 3; regen = (h >> 4) & 0x3ff; comp = (h >> 14) & 0x3ff; streams = sf == 0 ? 1 : 4; }
-                else if (sf == 2) { hs = 4; regen = (h >> 4) & 0x3fff; comp = h >> 18; streams = 4; }
-                else { hs = 5; regen = (h >> 4) & 0x3ffff; comp = (h >> 22) | ((uint32_t)blk[4] << 10); streams = 4; }
-            }
-            if (hs + comp > bsize || regen > limit || regen > zf::BLOCK_MAX) break;
-            if (type >= 2 && regen > litcap) break;
-            uint32_t tree = 0;
-            if (type == 2) {
-                tree = zd_read_huf_table(blk + hs, comp, cx);
-                if (!tree) break;
-            } else if (type == 3) {
-                if (fast_nonfirst) { cx->err = 1; }
-                else if (!cx->huf_valid) break;
-            }
-            t[1] = type; t[2] = hs; t[3] = regen; t[4] = comp; t[5] = streams; t[6] = tree;
-            t[0] = 1;
-        } while (false);
-    }
-    __syncwarp();
-    if (!cx->tmp[0]) { if (lane == 0 && cx->err == 0) cx->err = -1; __syncwarp(); return 0; }
-    if (cx->err) return 0;
-    const uint32_t ltype = cx->tmp[1], lhs = cx->tmp[2], regen = cx->tmp[3], lcomp = cx->tmp[4], streams = cx->tmp[5], tree = cx->tmp[6];
-    const uint8_t* lit = nullptr;                       // literal source: bytes (raw / decoded) or a single RLE byte
-    uint32_t rle_lit = 0x100;
-    if (ltype == 0) lit = blk + lhs;
-    else if (ltype == 1) rle_lit = blk[lhs];
-    else {
-        if (ltype == 2) zd_fill_huf_warp(cx, lane);
-        const uint8_t* hsrc = blk + lhs + tree;
-        const uint32_t hsize = lcomp - tree;
-        bool ok = true;
-        if (streams == 1) {
-            if (lane == 0) ok = zd_huf_stream(cx->huf, cx->huf_log, hsrc, hsize, litbuf, regen);
-        } else {
-            if (hsize < 10) ok = false;
-            else if (lane < 4) {
-                const uint32_t s1 = hsrc[0] | (hsrc[1] << 8), s2 = hsrc[2] | (hsrc[3] << 8), s3 = hsrc[4] | (hsrc[5] << 8);
-                if (6 + s1 + s2 + s3 > hsize) ok = false;
-                else {
-                    const uint32_t s4 = hsize - 6 - s1 - s2 - s3;
-                    const uint32_t per = (regen + 3) / 4;
-                    const uint32_t o = lane == 0 ? 0 : lane == 1 ? s1 : lane == 2 ? s1 + s2 : s1 + s2 + s3;
-                    const uint32_t sz = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : s4;
-                    const uint32_t first = lane * per;
-                    if (first > regen) ok = false;
-                    else {
-                        const uint32_t cnt = lane < 3 ? min(per, regen - first) : regen - first;
-                        if (lane == 3 && 3 * per > regen) ok = false;
-                        else ok = zd_huf_stream(cx->huf, cx->huf_log, hsrc + 6 + o, sz, litbuf + first, cnt);
-                    }
-                }
-            }
-        }
-        if (!__all_sync(TS_FULL, ok)) { if (lane == 0) cx->err = -1; __syncwarp(); return 0; }
-        lit = litbuf;
-        __threadfence_block();
-    }
-    __syncwarp();
-
-    // ---- sequences section header + tables (lane 0)
-    const uint8_t* sp = blk + lhs + lcomp;
-    const uint32_t ssize = bsize - lhs - lcomp;
-    if (lane == 0) {
-        uint32_t* t = cx->tmp;
-        t[0] = 0;
-        do {
-            if (ssize < 1) break;
-            uint32_t nseq = sp[0], hs = 1;
-            if (nseq >= 128) {
-                if (nseq == 255) { if (ssize < 3) break; nseq = sp[1] + ((uint32_t)sp[2] << 8) + 0x7f00; hs = 3; }
-                else { if (ssize < 2) break; nseq = ((nseq - 128) << 8) + sp[1]; hs = 2; }
-            }
-            uint32_t pos = hs, pend = 0;
-            if (nseq) {
-                if (ssize < hs + 1) break;
-                const uint32_t modes = sp[hs];
-                if (modes & 3) break;                   // reserved bits
-                pos = hs + 1;
-                bool bad = false;
-                const uint32_t m3[3] = { modes >> 6, (modes >> 4) & 3, (modes >> 2) & 3 };   // LL, OF, ML
-                for (int k = 0; k < 3 && !bad; k++) {
-                    const int32_t used = zd_seq_table(m3[k], k, sp + pos, ssize - pos, cx, fast_nonfirst, &pend);
-                    if (used < 0) bad = true; else pos += (uint32_t)used;
-                }
-                if (bad || pos > ssize) break;
-            }
-            t[1] = nseq; t[2] = pos; t[3] = pend;
-            t[0] = 1;
-        } while (false);
-    }
-    __syncwarp();
-    if (!cx->tmp[0]) { if (lane == 0 && cx->err == 0) cx->err = -1; __syncwarp(); return 0; }
-    if (cx->err) return 0;
-    const uint32_t nseq = cx->tmp[1];
-    {
-        const uint32_t pend = cx->tmp[3];
-        for (int k = 0; k < 3; k++) if (pend & (1u << k)) zd_build_dtable_warp(k, cx, lane);
-        __syncwarp();
-    }
-    const uint8_t* bs = sp + cx->tmp[2];
-    const uint32_t bs_size = ssize - cx->tmp[2];
-
-    // ---- sequences: lane 0 decodes 32 at a time, the warp executes them
-    uint32_t op = 0, lp = 0;                            // output / literal cursors (uniform)
-    ZdBack br; br.p = bs; br.bits = 0; br.C = 0; br.cbase = 0x3fffffff;
-    uint32_t st_ll = 0, st_of = 0, st_ml = 0;
-    if (nseq) {
-        if (lane == 0) {
-            bool ok = zd_back_init(br, bs, bs_size);
-            if (ok) {
-                st_ll = zd_back_read(br, cx->ll_log); st_of = zd_back_read(br, cx->of_log); st_ml = zd_back_read(br, cx->ml_log);
-                if (br.bits < 0) ok = false;
-            }
-            if (!ok) cx->err = -1;
-        }
-        __syncwarp();
-        if (cx->err) return 0;
-    }
+#include "zd_blk_lit_header.inc"
+#include "zd_blk_lit_decode.inc"
+#include "zd_blk_seq_header.inc"
+#include "zd_blk_seq_init.inc"
     for (uint32_t s0 = 0; s0 < nseq; s0 += 32) {
         const uint32_t cnt = min(32u, nseq - s0);
-        // (1) lane 0 walks ONLY the state chain: per sequence three table entries, the bit count, three state updates.
-        //     It records where each sequence's bits end and which states it was decoded from.
-        if (lane == 0) {
-            const uint32_t* tof = (const uint32_t*)cx->of; const uint32_t* tml = (const uint32_t*)cx->ml; const uint32_t* tll = (const uint32_t*)cx->ll;
-            const uint32_t n_upd = min(cnt, nseq - 1 - s0);          // sequences of this batch that are followed by another one
-            int32_t bits = br.bits;
-            bool bad = false;
-            uint32_t i = 0;
-            for (; i < n_upd; i++) {
-                // Bits of one sequence, first read first: offset extra, match-length extra, literal-length extra, then the
-                // LL, ML, OF state updates (<= 27 bits: one cached window).
-                const uint32_t eo = tof[st_of], em = tml[st_ml], el = tll[st_ll];
-                cx->s_ll[i] = st_of | (st_ml << 10) | (st_ll << 20);
-                cx->s_ml[i] = (uint32_t)bits;
-                const uint32_t t = eo + em + el;                     // bits 0..5: state-update bits, bits 6..11: extra bits
-                bits -= (int32_t)((t >> 6) & 63);
-                const int32_t lo = bits - (int32_t)(t & 63);
-                if (lo < 0) { bad = true; break; }
-                if (lo < br.cbase || bits > br.cbase + 64) {
-                    br.cbase = max(0, ((bits + 7) & ~7) - 64);
-                    br.C = zd_ld64(br.p + (br.cbase >> 3));
-                }
-                uint32_t W = (uint32_t)(br.C >> (lo - br.cbase));
-                const uint32_t u_of = eo & 63, u_ml = em & 63, u_ll = el & 63;
-                st_of = (eo >> 18) + (W & ((1u << u_of) - 1)); W >>= u_of;
-                st_ml = (em >> 18) + (W & ((1u << u_ml) - 1)); W >>= u_ml;
-                st_ll = (el >> 18) + (W & ((1u << u_ll) - 1));
-                bits = lo;
-            }
-            if (!bad && i < cnt) {                                   // the block's last sequence: values only
-                const uint32_t t = tof[st_of] + tml[st_ml] + tll[st_ll];
-                cx->s_ll[i] = st_of | (st_ml << 10) | (st_ll << 20);
-                cx->s_ml[i] = (uint32_t)bits;
-                bits -= (int32_t)((t >> 6) & 63);
-                if (bits < 0) bad = true;
-            }
-            br.bits = bits;
-            if (bad) cx->err = -1;
-        }
-        __syncwarp();
-        if (cx->err) return 0;
-        // (2) every lane cuts the three values of its own sequence out of the stream
-        const bool mine = lane < cnt;
-        uint32_t ll = 0, ml = 0, off = 1, ofv = 4;
-        if (mine) {
-            const uint32_t st = cx->s_ll[lane];
-            const int32_t end = (int32_t)cx->s_ml[lane];
-            const zf::FseDEntry eo = cx->of[st & 1023], em = cx->ml[(st >> 10) & 1023], el = cx->ll[st >> 20];
-            ofv = (1u << eo.sym) + zd_bits_at(bs, end, eo.nb_extra);
-            const uint32_t v = zd_bits_at(bs, end - (int32_t)eo.nb_extra, (uint32_t)em.nb_extra + el.nb_extra);
-            ml = g_seq_tables.ml_base[em.sym] + (v >> el.nb_extra);
-            ll = g_seq_tables.ll_base[el.sym] + (v & ((1u << el.nb_extra) - 1));
-            off = ofv - 3;
-        }
-        // (3) repeat offsets: batches without any (all of this compressor's) need no serial pass
-        const uint32_t rep_mask = __ballot_sync(TS_FULL, mine && ofv <= 3);
-        if (rep_mask == 0) {
-            const uint32_t o1 = __shfl_sync(TS_FULL, off, cnt - 1), o2 = __shfl_sync(TS_FULL, off, cnt >= 2 ? cnt - 2 : 0),
-                           o3 = __shfl_sync(TS_FULL, off, cnt >= 3 ? cnt - 3 : 0);
-            if (lane == 0) {
-                const uint32_t r0 = cx->rep[0], r1 = cx->rep[1];
-                cx->rep[2] = cnt >= 3 ? o3 : cnt == 2 ? r0 : r1;
-                cx->rep[1] = cnt >= 2 ? o2 : r0;
-                cx->rep[0] = o1;
-            }
-        } else {
-            if (fast_nonfirst) { if (lane == 0) cx->err = 1; __syncwarp(); return 0; }    // repeat offsets carried into the block
-            __syncwarp();
-            cx->s_off[lane] = ofv; cx->s_ml[lane] = ll;
-            __syncwarp();
-            if (lane == 0) {
-                uint32_t r0 = cx->rep[0], r1 = cx->rep[1], r2 = cx->rep[2];
-                for (uint32_t i = 0; i < cnt; i++) {
-                    const uint32_t v = cx->s_off[i];
-                    uint32_t o;
-                    if (v > 3) { o = v - 3; r2 = r1; r1 = r0; r0 = o; }
-                    else {
-                        const uint32_t idx = v - 1 + (cx->s_ml[i] == 0 ? 1 : 0);     // 0: rep1, 1: rep2, 2: rep3, 3: rep1 - 1
-                        if (idx == 0) o = r0;
-                        else {
-                            const uint32_t t = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
-                            if (t == 0) { cx->err = -1; break; }
-                            if (idx != 1) r2 = r1;
-                            r1 = r0; r0 = t; o = t;
-                        }
-                    }
-                    cx->s_off[i] = o;
-                }
-                cx->rep[0] = r0; cx->rep[1] = r1; cx->rep[2] = r2;
-            }
-            __syncwarp();
-            if (cx->err) return 0;
-            off = mine ? cx->s_off[lane] : 1;
-        }
-        __syncwarp();
-        // ---- execute the batch: lane i owns sequence i.  Output/literal positions come from shuffle prefix sums;
-        // literal runs are independent; a match may start once its source range lies inside the completed prefix
-        // (multi-round resolution: far matches of a batch all copy at once, so their memory latency overlaps).
-        {
-            const uint32_t inc_o = warp_inclusive_scan_u32(ll + ml, lane), inc_l = warp_inclusive_scan_u32(ll, lane);
-            const uint32_t tot_o = __shfl_sync(TS_FULL, inc_o, 31), tot_l = __shfl_sync(TS_FULL, inc_l, 31);
-            const uint32_t o_start = op + inc_o - ll - ml, l_start = lp + inc_l - ll, m_start = o_start + ll;
-            const bool bad_off = mine && (uint64_t)off > hist + m_start;
-            const uint32_t any_bad = __ballot_sync(TS_FULL, bad_off);
-            if (lp + tot_l > regen || (uint64_t)op + tot_o > limit || any_bad) {
-                if (lane == 0) cx->err = (any_bad && fast_nonfirst && lp + tot_l <= regen && (uint64_t)op + tot_o <= limit) ? 1 : -1;
-                __syncwarp();
-                return 0;
-            }
-            // literals: short runs by their own lane, long runs by the whole warp
-            {
-                const uint32_t quick = min(ll, 32u);
-                if (rle_lit < 0x100) { for (uint32_t k = 0; k < quick; k++) dst[o_start + k] = (uint8_t)rle_lit; }
-                else {                                       // four loads in flight per step (lit and dst never alias)
-                    const uint8_t* ls = lit + l_start; uint8_t* ld = dst + o_start;
-                    uint32_t k = 0;
-                    for (; k + 4 <= quick; k += 4) {
-                        const uint8_t b0 = ls[k], b1 = ls[k + 1], b2 = ls[k + 2], b3 = ls[k + 3];
-                        ld[k] = b0; ld[k + 1] = b1; ld[k + 2] = b2; ld[k + 3] = b3;
-                    }
-                    for (; k < quick; k++) ld[k] = ls[k];
-                }
-                uint32_t longs = __ballot_sync(TS_FULL, ll > 32);
-                while (longs) {
-                    const uint32_t f = (uint32_t)__ffs((int)longs) - 1;
-                    longs &= longs - 1;
-                    const uint32_t fo = __shfl_sync(TS_FULL, o_start, f), fl = __shfl_sync(TS_FULL, l_start, f), fn = __shfl_sync(TS_FULL, ll, f);
-                    if (rle_lit < 0x100) { for (uint32_t k = 32 + lane; k < fn; k += 32) dst[fo + k] = (uint8_t)rle_lit; }
-                    else { for (uint32_t k = 32 + lane; k < fn; k += 32) dst[fo + k] = lit[fl + k]; }
-                }
-            }
-            __syncwarp();
-            // matches
-            bool done = !mine || ml == 0;
-            const int64_t src_end = (int64_t)m_start - (int64_t)off + (int64_t)ml;      // relative to dst
-            while (true) {
-                const uint32_t pending = __ballot_sync(TS_FULL, !done);
-                if (!pending) break;
-                const uint32_t first = (uint32_t)__ffs((int)pending) - 1;
-                const uint32_t frontier = __shfl_sync(TS_FULL, m_start, first);
-                const bool ready = !done && (lane == first || src_end <= (int64_t)frontier);
-                uint8_t* d = dst + m_start;
-                const uint8_t* m = d - off;
-                if (ready && ml <= 64) {
-                    uint32_t k = 0;
-                    if (off >= 4) {                              // the four source bytes of a step all precede its first store
-                        for (; k + 4 <= ml; k += 4) {
-                            const uint8_t b0 = m[k], b1 = m[k + 1], b2 = m[k + 2], b3 = m[k + 3];
-                            d[k] = b0; d[k + 1] = b1; d[k + 2] = b2; d[k + 3] = b3;
-                        }
-                    }
-                    for (; k < ml; k++) d[k] = m[k];             // byte-serial: overlap (off < ml) is fine
-                    done = true;
-                }
-                uint32_t big = __ballot_sync(TS_FULL, ready && ml > 64);
-                while (big) {                                                            // long matches: 32 lanes per match
-                    const uint32_t f = (uint32_t)__ffs((int)big) - 1;
-                    big &= big - 1;
-                    const uint32_t fm = __shfl_sync(TS_FULL, m_start, f), fl = __shfl_sync(TS_FULL, ml, f), fo = __shfl_sync(TS_FULL, off, f);
-                    uint8_t* dd = dst + fm;
-                    const uint8_t* mm = dd - fo;
-                    if (fo >= 32) {
-                        for (uint32_t k0 = 0; k0 < fl; k0 += 32) {
-                            const uint32_t k = k0 + lane;
-                            if (k < fl) dd[k] = mm[k];
-                            if (fo < fl) __syncwarp();                                   // later strides may read what this one wrote
-                        }
-                    } else {
-                        for (uint32_t k = lane; k < fl; k += 32) dd[k] = mm[k % fo];     // periodic source entirely before dd
-                    }
-                    if (lane == f) done = true;
-                }
-                __syncwarp();
-            }
-            op += tot_o; lp += tot_l;
-        }
+#include "zd_blk_decode_batch.inc"
+#include "zd_blk_exec_batch.inc"
     }
-    // ---- trailing literals
-    {
-        const uint32_t ll = regen - lp;
-        if ((uint64_t)op + ll > limit) { if (lane == 0) cx->err = -1; __syncwarp(); return 0; }
-        if (rle_lit < 0x100) { for (uint32_t k = lane; k < ll; k += 32) dst[op + k] = (uint8_t)rle_lit; }
-        else { for (uint32_t k = lane; k < ll; k += 32) dst[op + k] = lit[lp + k]; }
-        op += ll;
-    }
+#include "zd_blk_trailing.inc"
     __syncwarp();
     return op;
 }
