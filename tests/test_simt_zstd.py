@@ -160,3 +160,40 @@ def test_simt_two_launch_compressor_matches_the_fused_kernel(ctx, monkeypatch):
         assert "zstd_enc_parse" in names and "zstd_enc_entropy" in names and "zstd_enc_blocks" not in names
     finally:
         c2.close()
+
+
+def test_simt_parallel_general_path_reads_libzstd_frames(monkeypatch):
+    # TSGPU_DEC_PARALLEL=1: entropy stage per block in parallel, execution per frame; same answers
+    monkeypatch.setenv("TSGPU_DEC_PARALLEL", "1")
+    c2 = tsgpu.Context(max_chunk_bytes=1 << 20, max_batch=4, lib_path=SIMT_LIB)
+    try:
+        c2.profile_enable(True)
+        for kind, n, level in (("K", 1 << 20, 3), ("K", 700000, 1), ("K", 700000, 19), ("M", 300000, 3), ("R", 200000, 3),
+                               ("Z", 500000, 3), ("K", 131072, 3), ("K", 131073, 3), ("K", 5, 3)):
+            src = _mixed(n, 5) if kind == "M" else corpus.gen_chunk(kind, 3, 0, n)
+            frame = np.frombuffer(ora.zstd_compress_level(src, level), dtype=np.uint8)
+            back, osz = c2.detransform(Z, frame, [frame.size], n)
+            assert osz == [n] and np.array_equal(back, src), (kind, n, level)
+        # several frames in one batch, mixed with this library's own frames (fast path) and a corrupt one
+        srcs = [corpus.gen_chunk("K", 9 + i, 0, 300000) for i in range(3)]
+        frames = [np.frombuffer(ora.zstd_compress_chunk(s), dtype=np.uint8) for s in srcs]
+        mine, msz = c2.transform(Z, srcs[0], 0)
+        frames.append(mine[:msz[0]])
+        blob = np.concatenate(frames)
+        back, osz = c2.detransform(Z, blob, [f.size for f in frames], 4 * 300000)
+        assert np.array_equal(back, np.concatenate(srcs + [srcs[0]]))
+        names = set(c2.profile_report())
+        assert "zstd_dec_par_entropy" in names and "zstd_dec_par_execute" in names
+        rng = np.random.default_rng(4)
+        base = frames[1]
+        for trial in range(60):
+            bad = base.copy()
+            bad[int(rng.integers(0, bad.size))] ^= 1 << int(rng.integers(0, 8))
+            try:
+                out, _ = c2.detransform(Z, bad, [bad.size], 300000)
+            except tsgpu.TsgpuError as e:
+                assert e.code == binding.E_CORRUPT
+            else:
+                assert len(out) == 300000
+    finally:
+        c2.close()

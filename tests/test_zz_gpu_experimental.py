@@ -48,3 +48,35 @@ def test_gpu_key_tables_follow_the_key_across_calls():
             assert np.array_equal(back, src)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_parallel_general_path(monkeypatch):
+    # TSGPU_DEC_PARALLEL=1: libzstd-written frames, entropy stage per block in parallel + execution per frame
+    monkeypatch.setenv("TSGPU_DEC_PARALLEL", "1")
+    ctx = tsgpu.Context(max_chunk_bytes=4 << 20, max_batch=4)
+    try:
+        ctx.profile_enable(True)
+        for kind, n, level in (("K", 4 << 20, 3), ("K", 3000000, 19), ("K", 1500000, 1), ("R", 600000, 3), ("Z", 2000000, 3)):
+            src = corpus.gen_chunk(kind, 3, 0, n)
+            frame = np.frombuffer(ora.zstd_compress_level(src, level), dtype=np.uint8)
+            back, osz = ctx.detransform(Z, frame, [frame.size], n)
+            assert osz == [n] and np.array_equal(back, src), (kind, n, level)
+        srcs = [corpus.gen_chunk("K", 9 + i, 0, 1 << 20) for i in range(3)]
+        frames = [np.frombuffer(ora.zstd_compress_chunk(s), dtype=np.uint8) for s in srcs]
+        mine, msz = ctx.transform(Z, srcs[0], 0)
+        frames.append(mine[:msz[0]])
+        back, _ = ctx.detransform(Z, np.concatenate(frames), [f.size for f in frames], 4 << 20)
+        assert np.array_equal(back, np.concatenate(srcs + [srcs[0]]))
+        names = set(ctx.profile_report())
+        assert "zstd_dec_par_entropy" in names and "zstd_dec_par_execute" in names
+        rng = np.random.default_rng(4)
+        for trial in range(40):
+            bad = frames[1].copy()
+            bad[int(rng.integers(0, bad.size))] ^= 1 << int(rng.integers(0, 8))
+            try:
+                ctx.detransform(Z, bad, [bad.size], 1 << 20)
+            except tsgpu.TsgpuError as e:
+                assert e.code == tsgpu.binding.E_CORRUPT
+    finally:
+        ctx.close()

@@ -61,6 +61,12 @@ struct ZstdDecScratch {
     uint8_t* lits_general = nullptr; // n_chunks * ZD_LIT_GENERAL
     uint64_t* pos_tmp = nullptr;     // n_chunks + 1
     uint32_t blocks_per_chunk = 0, max_batch = 0, chunk_cap = 0;
+    // parallel general path (TSGPU_DEC_PARALLEL=1): per-block results of the entropy stage + per-frame arenas
+    bool par = false;
+    uint8_t* par_meta = nullptr;     // n_chunks * blocks_per_chunk * sizeof(ZdBlkMeta)
+    uint8_t* par_lits = nullptr;     // n_chunks * par_lit_cap
+    uint64_t* par_seqs = nullptr;    // n_chunks * par_seq_cap
+    uint32_t par_lit_cap = 0, par_seq_cap = 0;
 };
 
 struct ZstdDecArgs {
@@ -68,8 +74,9 @@ struct ZstdDecArgs {
     uint8_t* out_base; const uint64_t* out_off; uint32_t* out_len; uint32_t* status;
     uint32_t* blk_off; uint32_t* info; uint8_t* lits_fast; uint8_t* lits_general;
     uint32_t blocks_per_chunk, chunk_cap, n_chunks;
+    uint32_t par; uint8_t* par_meta; uint8_t* par_lits; uint64_t* par_seqs; uint32_t par_lit_cap, par_seq_cap;
 };
-constexpr int ZD_INFO = 8;
+constexpr int ZD_INFO = 8;     // fcs, nblk, fast-path eligible, need_general / failed, header size, parallel-general, literal bump, sequence bump
 
 // ------------------------------------------------------------------------------------------ bit readers
 __device__ __forceinline__ uint64_t zd_ld64(const uint8_t* p) {          // unaligned little-endian 64-bit window
@@ -367,6 +374,143 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
     return op;
 }
 
+// ------------------------------------------------------------------------------------------ parallel general path
+// (TSGPU_DEC_PARALLEL=1; off by default, not yet timed.)  Frames written by libzstd have few, large blocks that inherit
+// tables and repeat offsets from each other, so the fast path does not apply and one warp per frame is slow for a lone
+// frame.  Here every block's ENTROPY decoding (Huffman literals, FSE sequences) runs on its own warp into global scratch:
+// tables a block inherits (treeless literals, Repeat_Mode) are rebuilt by replaying the table definitions of the blocks
+// before it; offsets stay unresolved offset VALUES.  One warp per frame then resolves repeat offsets and executes the
+// sequences in order.  The stages are the same textual includes the serial decoder is made of.
+struct ZdBlkMeta { uint32_t status, lit_kind, lit_off, regen, nseq, seq_off; };     // status 1 = decoded, 2 = failed; lit_kind 0 arena, 1 in the block, 2 RLE
+struct ZdParIO { uint8_t* lit_arena; uint32_t lit_cap; uint32_t* lit_bump; uint64_t* seq_arena; uint32_t seq_cap; uint32_t* seq_bump; };
+constexpr uint32_t ZD_PAR_MAX_BLOCKS = 128;
+
+// Table definitions of one Compressed_Block only (Huffman tree, the three FSE tables): what a later block may inherit.
+__device__ __forceinline__ uint32_t zd_block_tables(const uint8_t* blk, uint32_t bsize, ZdWarpCtx* cx, uint32_t lane) {
+    const uint32_t limit = zf::BLOCK_MAX, litcap = zf::BLOCK_MAX;
+    const bool fast_nonfirst = false;
+#include "zd_blk_lit_header.inc"
+    if (ltype == 2) zd_fill_huf_warp(cx, lane);
+    __syncwarp();
+    (void)regen; (void)streams; (void)tree;
+#include "zd_blk_seq_header.inc"
+    (void)nseq; (void)bs; (void)bs_size;
+    return 0;
+}
+
+// Does the block use a table it does not define itself (treeless literals / Repeat_Mode)?  Malformed headers answer yes:
+// the replay or the block's own decode will then report the error.  Lane 0 parses, the warp gets the answer.
+__device__ __forceinline__ bool zd_block_inherits(const uint8_t* blk, uint32_t bsize, uint32_t lane) {
+    uint32_t r = 1;
+    if (lane == 0) {
+        do {
+            if (bsize < 2) break;
+            const uint32_t b0 = blk[0], type = b0 & 3, sf = (b0 >> 2) & 3;
+            uint32_t hs, regen, comp;
+            if (type < 2) {
+                if ((sf & 1) == 0) { hs = 1; regen = b0 >> 3; }
+                else if (sf == 1) { hs = 2; regen = (b0 >> 4) | ((uint32_t)blk[1] << 4); }
+                else { if (bsize < 3) break; hs = 3; regen = (b0 >> 4) | ((uint32_t)blk[1] << 4) | ((uint32_t)blk[2] << 12); }
+                comp = type == 0 ? regen : 1;
+            } else {
+                if (type == 3 || bsize < 5) break;                           // treeless: inherits the Huffman table
+                const uint32_t h = blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
+                if (sf <= 1) { hs = 3; comp = (h >> 14) & 0x3ff; }
+                else if (sf == 2) { hs = 4; comp = h >> 18; }
+                else { hs = 5; comp = (h >> 22) | ((uint32_t)blk[4] << 10); }
+            }
+            if ((uint64_t)hs + comp + 1 > bsize) break;
+            const uint8_t* sp = blk + hs + comp;
+            const uint32_t ssize = bsize - hs - comp;
+            uint32_t nseq = sp[0], sh = 1;
+            if (nseq >= 128) { sh = nseq == 255 ? 3 : 2; if (ssize < sh) break; nseq = 1; }
+            if (nseq == 0) { r = 0; break; }
+            if (ssize < sh + 1) break;
+            const uint32_t modes = sp[sh];
+            r = ((modes >> 6) == 3 || ((modes >> 4) & 3) == 3 || ((modes >> 2) & 3) == 3) ? 1u : 0u;
+        } while (false);
+    }
+    return __shfl_sync(TS_FULL, r, 0) != 0;
+}
+
+// Entropy stage of one Compressed_Block: literals into the frame's literal arena (unless Raw / RLE), sequences as
+// packed (offset value : 30, literal length : 17, match length - 3 : 17) into the frame's sequence arena.
+__device__ __forceinline__ uint32_t zd_block_entropy(const uint8_t* blk, uint32_t bsize, ZdWarpCtx* cx, const ZdParIO& io,
+                                                     ZdBlkMeta* meta, uint32_t lane) {
+    const uint32_t limit = zf::BLOCK_MAX, litcap = zf::BLOCK_MAX;
+    const bool fast_nonfirst = false;
+#include "zd_blk_lit_header.inc"
+    uint8_t* litbuf = nullptr;
+    uint32_t lit_at = 0;
+    if (ltype >= 2) {
+        if (lane == 0) {
+            const uint32_t o = atomicAdd(io.lit_bump, (regen + 15) & ~15u);
+            cx->tmp[7] = o;
+            if ((uint64_t)o + regen + 16 > io.lit_cap) cx->err = -1;
+        }
+        __syncwarp();
+        if (cx->err) return 0;
+        lit_at = cx->tmp[7];
+        litbuf = io.lit_arena + lit_at;
+    }
+#include "zd_blk_lit_decode.inc"
+#include "zd_blk_seq_header.inc"
+    if (lane == 0) {
+        const uint32_t o = atomicAdd(io.seq_bump, nseq);
+        cx->tmp[7] = o;
+        if ((uint64_t)o + nseq > io.seq_cap) cx->err = -1;
+    }
+    __syncwarp();
+    if (cx->err) return 0;
+    const uint32_t seq_at = cx->tmp[7];
+    uint64_t* sq = io.seq_arena + seq_at;
+#include "zd_blk_seq_init.inc"
+    for (uint32_t s0 = 0; s0 < nseq; s0 += 32) {
+        const uint32_t cnt = min(32u, nseq - s0);
+#include "zd_blk_decode_batch.inc"
+        const bool wide = mine && (ofv >= (1u << 30) || ll >= (1u << 17) || ml - 3 >= (1u << 17));
+        if (__ballot_sync(TS_FULL, wide)) { if (lane == 0) cx->err = -1; __syncwarp(); return 0; }
+        if (mine) sq[s0 + lane] = (uint64_t)ofv | ((uint64_t)ll << 30) | ((uint64_t)(ml - 3) << 47);
+        (void)off;
+    }
+    (void)op; (void)lp; (void)lit;
+    if (lane == 0) {
+        meta->lit_kind = ltype == 0 ? 1u : ltype == 1 ? 2u : 0u;
+        meta->lit_off = ltype == 0 ? lhs : ltype == 1 ? rle_lit : lit_at;
+        meta->regen = regen; meta->nseq = nseq; meta->seq_off = seq_at;
+    }
+    return 0;
+}
+
+// Execution stage of one Compressed_Block from what zd_block_entropy left: repeat offsets, literal runs, matches.
+__device__ __forceinline__ uint32_t zd_block_execute(const uint8_t* blk, uint8_t* dst, uint64_t hist, uint32_t limit, ZdWarpCtx* cx,
+                                                     const ZdBlkMeta m, const uint8_t* lit_arena, const uint64_t* seq_arena,
+                                                     uint32_t lane) {
+    const bool fast_nonfirst = false;
+    const uint32_t regen = m.regen, nseq = m.nseq;
+    const uint8_t* lit = nullptr;
+    uint32_t rle_lit = 0x100;
+    if (m.lit_kind == 1) lit = blk + m.lit_off;
+    else if (m.lit_kind == 2) rle_lit = m.lit_off & 0xff;
+    else lit = lit_arena + m.lit_off;
+    const uint64_t* sq = seq_arena + m.seq_off;
+    uint32_t op = 0, lp = 0;
+    for (uint32_t s0 = 0; s0 < nseq; s0 += 32) {
+        const uint32_t cnt = min(32u, nseq - s0);
+        const bool mine = lane < cnt;
+        uint32_t ll = 0, ml = 0, off = 1, ofv = 4;
+        if (mine) {
+            const uint64_t v = sq[s0 + lane];
+            ofv = (uint32_t)v & 0x3fffffffu; ll = (uint32_t)(v >> 30) & 0x1ffffu; ml = (uint32_t)(v >> 47) + 3;
+            off = ofv - 3;
+        }
+#include "zd_blk_exec_batch.inc"
+    }
+#include "zd_blk_trailing.inc"
+    __syncwarp();
+    return op;
+}
+
 // ------------------------------------------------------------------------------------------ frame header
 // Returns header size (0 on error); fcs = 0xffffffffffffffff when absent.
 __device__ __forceinline__ uint32_t zd_frame_header(const uint8_t* p, uint32_t n, uint64_t* fcs) {
@@ -400,7 +544,7 @@ __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_consta
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t n = A.in_len[chunk];
     uint64_t fcs = 0;
-    info[0] = 0; info[1] = 0; info[2] = 0; info[3] = 0; info[4] = 0;
+    info[0] = 0; info[1] = 0; info[2] = 0; info[3] = 0; info[4] = 0; info[5] = 0; info[6] = 0; info[7] = 0;
     if (A.status[chunk] != 0) { A.out_len[chunk] = 0; info[3] = 2; return; }      // e.g. tag mismatch upstream: nothing to decode
     const uint32_t hs = zd_frame_header(p, n, &fcs);
     // "Invalid decompressed size" (DecompressionChunkEnumeration.java:41-44): no FCS, or larger than a chunk can be
@@ -426,6 +570,8 @@ __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_consta
     if (!ok) { A.status[chunk] = ZD_ST_CORRUPT; info[3] = 2; return; }
     info[1] = nblk;
     info[2] = (last && nblk == want && nblk <= A.blocks_per_chunk) ? 1 : 0;      // eligible for the per-block path
+    // libzstd-shaped frames (few large blocks): entropy-decode the blocks in parallel when that variant is switched on
+    info[5] = (A.par && !info[2] && last && nblk <= A.blocks_per_chunk && nblk <= ZD_PAR_MAX_BLOCKS) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------ kernel 2: per-block fast path
@@ -487,6 +633,7 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_frames_kernel(const __gr
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
     if (info[3] == 2) return;                            // already failed in the index pass
     if (info[2] && info[3] == 0) return;                 // the per-block path finished this frame
+    if (info[5]) return;                                 // the parallel general path owns this frame
     ZdWarpCtx* cx = (ZdWarpCtx*)(smem + (size_t)warp * sizeof(ZdWarpCtx));
     const uint32_t fcs = info[0];
     const uint8_t* p = A.in_base + A.in_off[chunk];
@@ -530,6 +677,97 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_frames_kernel(const __gr
     }
 }
 
+// ------------------------------------------------------------------------------------------ kernels 3a / 3b: parallel general path
+__global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_entropy_kernel(const __grid_constant__ ZstdDecArgs A) {
+    TS_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.y, b = blockIdx.x * ZD_WPB + warp;
+    uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
+    if (!info[5] || b >= info[1]) return;
+    ZdWarpCtx* cx = (ZdWarpCtx*)(smem + (size_t)warp * sizeof(ZdWarpCtx));
+    ZdBlkMeta* meta = (ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk + b;
+    const uint8_t* p = A.in_base + A.in_off[chunk];
+    const uint32_t n = A.in_len[chunk];
+    const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
+    const uint32_t pos = bo[b];
+    const uint32_t h = p[pos] | (p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
+    const uint32_t type = (h >> 1) & 3, bsz = h >> 3;
+    if (type != 2) { if (lane == 0) meta->status = 1; return; }           // Raw / RLE blocks need no entropy stage
+    if (pos + 3 + bsz > n || bsz > zf::BLOCK_MAX) { if (lane == 0) meta->status = 2; return; }
+    if (lane == 0) { cx->err = 0; cx->huf_valid = 0; cx->ll_valid = 0; cx->ml_valid = 0; cx->of_valid = 0; }
+    __syncwarp();
+    if (zd_block_inherits(p + pos + 3, bsz, lane)) {
+        // replay the table definitions of every earlier Compressed_Block, in order (the index pass checked their bounds)
+        for (uint32_t j = 0; j < b; j++) {
+            const uint32_t pj = bo[j];
+            const uint32_t hj = p[pj] | (p[pj + 1] << 8) | ((uint32_t)p[pj + 2] << 16);
+            if (((hj >> 1) & 3) != 2) continue;
+            const uint32_t bj = hj >> 3;
+            if (bj > zf::BLOCK_MAX) { if (lane == 0) cx->err = -1; __syncwarp(); break; }
+            zd_block_tables(p + pj + 3, bj, cx, lane);
+            __syncwarp();
+            if (cx->err) break;
+        }
+    }
+    if (!cx->err) {
+        ZdParIO io;
+        io.lit_arena = A.par_lits + (size_t)chunk * A.par_lit_cap; io.lit_cap = A.par_lit_cap; io.lit_bump = info + 6;
+        io.seq_arena = A.par_seqs + (size_t)chunk * A.par_seq_cap; io.seq_cap = A.par_seq_cap; io.seq_bump = info + 7;
+        zd_block_entropy(p + pos + 3, bsz, cx, io, meta, lane);
+    }
+    __syncwarp();
+    if (lane == 0) meta->status = cx->err ? 2u : 1u;
+}
+
+__global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
+    TS_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * ZD_WPB + warp;
+    if (chunk >= A.n_chunks) return;
+    uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
+    if (!info[5] || info[3] == 2) return;
+    ZdWarpCtx* cx = (ZdWarpCtx*)(smem + (size_t)warp * sizeof(ZdWarpCtx));
+    const uint32_t fcs = info[0], nblk = info[1];
+    const uint8_t* p = A.in_base + A.in_off[chunk];
+    const uint32_t n = A.in_len[chunk];
+    uint8_t* dst = A.out_base + A.out_off[chunk];
+    const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
+    const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
+    const uint8_t* lit_arena = A.par_lits + (size_t)chunk * A.par_lit_cap;
+    const uint64_t* seq_arena = A.par_seqs + (size_t)chunk * A.par_seq_cap;
+    if (lane == 0) { cx->err = 0; cx->rep[0] = 1; cx->rep[1] = 4; cx->rep[2] = 8; }
+    __syncwarp();
+    uint64_t op = 0;
+    bool bad = false;
+    for (uint32_t b = 0; b < nblk && !bad; b++) {
+        const uint32_t pos = bo[b];
+        const uint32_t h = p[pos] | (p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
+        const uint32_t type = (h >> 1) & 3, bsz = h >> 3;
+        const uint32_t room = (uint32_t)min((uint64_t)zf::BLOCK_MAX, (uint64_t)fcs - op);
+        if (type == 0) {
+            if (bsz > room || pos + 3 + bsz > n) { bad = true; break; }
+            for (uint32_t k = lane; k < bsz; k += 32) dst[op + k] = p[pos + 3 + k];
+            op += bsz;
+        } else if (type == 1) {
+            if (bsz > room || pos + 4 > n) { bad = true; break; }
+            const uint8_t v = p[pos + 3];
+            for (uint32_t k = lane; k < bsz; k += 32) dst[op + k] = v;
+            op += bsz;
+        } else {
+            const ZdBlkMeta m = meta[b];
+            if (m.status != 1) { bad = true; break; }
+            const uint32_t made = zd_block_execute(p + pos + 3, dst + op, op, room, cx, m, lit_arena, seq_arena, lane);
+            if (cx->err) { bad = true; break; }
+            op += made;
+        }
+        __syncwarp();
+        __threadfence_block();
+    }
+    if (lane == 0) {
+        if (bad || op != fcs) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 inline const char* zstd_dec_scratch_alloc(ZstdDecScratch& s, uint32_t chunk_cap, uint32_t max_batch) {
     s.blocks_per_chunk = (chunk_cap + ZB - 1) / ZB;
@@ -541,11 +779,19 @@ inline const char* zstd_dec_scratch_alloc(ZstdDecScratch& s, uint32_t chunk_cap,
     if ((e = rt::malloc_device((void**)&s.lits_fast, (size_t)max_batch * s.blocks_per_chunk * (ZB + 64) + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.lits_general, (size_t)max_batch * ZD_LIT_GENERAL + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.pos_tmp, (size_t)(max_batch + 1) * 8 + 256))) return e;
+    { const char* v = getenv("TSGPU_DEC_PARALLEL"); s.par = v && atoi(v) != 0; }
+    if (s.par) {
+        s.par_lit_cap = (uint32_t)(((uint64_t)chunk_cap + 16ull * (ZD_PAR_MAX_BLOCKS + 1) + 4096 + 15) & ~15ull);
+        s.par_seq_cap = chunk_cap / 3 + 64;
+        if ((e = rt::malloc_device((void**)&s.par_meta, (size_t)max_batch * s.blocks_per_chunk * sizeof(ZdBlkMeta) + 256))) return e;
+        if ((e = rt::malloc_device((void**)&s.par_lits, (size_t)max_batch * s.par_lit_cap + 256))) return e;
+        if ((e = rt::malloc_device((void**)&s.par_seqs, (size_t)max_batch * s.par_seq_cap * 8 + 256))) return e;
+    }
     return nullptr;
 }
 inline void zstd_dec_scratch_free(ZstdDecScratch& s) {
     rt::free_device(s.blk_off); rt::free_device(s.info); rt::free_device(s.lits_fast); rt::free_device(s.lits_general);
-    rt::free_device(s.pos_tmp);
+    rt::free_device(s.pos_tmp); rt::free_device(s.par_meta); rt::free_device(s.par_lits); rt::free_device(s.par_seqs);
     s = ZstdDecScratch{};
 }
 
@@ -558,6 +804,8 @@ inline const char* zstd_kernels_configure() {
     if ((e = rt::allow_smem(zstd_enc_entropy_kernel, ZE_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_blocks_kernel, ZD_WPB_FAST * ZD_FAST_WARP_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_frames_kernel, ZD_SMEM_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_dec_par_entropy_kernel, ZD_SMEM_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_dec_par_execute_kernel, ZD_SMEM_BYTES))) return e;
     return nullptr;
 }
 
@@ -574,6 +822,8 @@ inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8
     A.out_base = out_base; A.out_off = d_out_off; A.out_len = d_out_len; A.status = d_status;
     A.blk_off = s.blk_off; A.info = s.info; A.lits_fast = s.lits_fast; A.lits_general = s.lits_general;
     A.blocks_per_chunk = s.blocks_per_chunk; A.chunk_cap = chunk_cap; A.n_chunks = n_chunks;
+    A.par = s.par ? 1u : 0u; A.par_meta = s.par_meta; A.par_lits = s.par_lits; A.par_seqs = s.par_seqs;
+    A.par_lit_cap = s.par_lit_cap; A.par_seq_cap = s.par_seq_cap;
     const char* e;
     TS_LAUNCH_P(prof, "zstd_dec_index", zstd_dec_index_kernel, dim3((n_chunks + 3) / 4), dim3(128), 0, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
@@ -586,6 +836,15 @@ inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8
     TS_LAUNCH_P(prof, "zstd_dec_blocks", zstd_dec_blocks_kernel, dim3((bpc + ZD_WPB_FAST - 1) / ZD_WPB_FAST, n_chunks), dim3(ZD_WPB_FAST * 32),
                 ZD_WPB_FAST * ZD_FAST_WARP_BYTES, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
+    if (s.par) {
+        const uint32_t pb = bpc < ZD_PAR_MAX_BLOCKS ? bpc : ZD_PAR_MAX_BLOCKS;
+        TS_LAUNCH_P(prof, "zstd_dec_par_entropy", zstd_dec_par_entropy_kernel, dim3((pb + ZD_WPB - 1) / ZD_WPB, n_chunks), dim3(ZD_WPB * 32),
+                    ZD_SMEM_BYTES, st, A);
+        if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
+        TS_LAUNCH_P(prof, "zstd_dec_par_execute", zstd_dec_par_execute_kernel, dim3((n_chunks + ZD_WPB - 1) / ZD_WPB), dim3(ZD_WPB * 32),
+                    ZD_SMEM_BYTES, st, A);
+        if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
+    }
     TS_LAUNCH_P(prof, "zstd_dec_frames", zstd_dec_frames_kernel, dim3((n_chunks + ZD_WPB - 1) / ZD_WPB), dim3(ZD_WPB * 32),
                 ZD_SMEM_BYTES, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
