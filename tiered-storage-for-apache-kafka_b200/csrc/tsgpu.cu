@@ -298,11 +298,12 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
     }
     if (flags & TSGPU_FLAG_AES) {
         const bool key_ready = w.key_valid && memcmp(&w.key_rk, &rk, sizeof rk) == 0;
-        w.key_rk = rk; w.key_valid = true;
+        w.key_rk = rk; w.key_valid = false;                  // valid again once the stage has been enqueued
         { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }                                  // d_xf is the final buffer
         int rc = gcm_stage<true>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, w.d_xf, w.dd.c_off, w.dd.c_len,
                                  w.dd.ivs, w.dd.aad, aad_len, w.dd.status, nb, cur_max, w.d_partials, w.max_ranges);
         if (rc) return rc;
+        w.key_valid = true;
         cur_len = w.dd.c_len;
         xb.final_base = w.d_xf; xb.final_stride = c->slot_stride; xb.final_head = TSGPU_SLOT_HEAD;
     }
@@ -471,11 +472,12 @@ static int detransform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_
         const uint64_t* oo = z ? w.dd.b_off : w.dd.a_off;
         uint32_t* ol = z ? w.dd.b_len : w.dd.a_len;
         const bool key_ready = w.key_valid && memcmp(&w.key_rk, &rk, sizeof rk) == 0;
-        w.key_rk = rk; w.key_valid = true;
+        w.key_rk = rk; w.key_valid = false;                  // valid again once the stage has been enqueued
         if (!z) { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }                          // d_orig is the final buffer
         int rc = gcm_stage<false>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
                                   w.dd.status, nb, max_t, w.d_partials, w.max_ranges);
         if (rc) return rc;
+        w.key_valid = true;
         cur_base = ob; cur_off = oo; cur_len = ol;
     }
     if (flags & TSGPU_FLAG_ZSTD) {
