@@ -398,10 +398,22 @@ __device__ __forceinline__ uint32_t zd_block_tables(const uint8_t* blk, uint32_t
     return 0;
 }
 
+// Only the Huffman tree of a Compressed_Block with Compressed_Literals (what treeless blocks after it inherit).
+__device__ __forceinline__ uint32_t zd_block_huf_only(const uint8_t* blk, uint32_t bsize, ZdWarpCtx* cx, uint32_t lane) {
+    const uint32_t limit = zf::BLOCK_MAX, litcap = zf::BLOCK_MAX;
+    const bool fast_nonfirst = false;
+#include "zd_blk_lit_header.inc"
+    if (ltype == 2) zd_fill_huf_warp(cx, lane);
+    __syncwarp();
+    (void)lhs; (void)regen; (void)lcomp; (void)streams; (void)tree;
+    return 0;
+}
+
 // Does the block use a table it does not define itself (treeless literals / Repeat_Mode)?  Malformed headers answer yes:
 // the replay or the block's own decode will then report the error.  Lane 0 parses, the warp gets the answer.
-__device__ __forceinline__ bool zd_block_inherits(const uint8_t* blk, uint32_t bsize, uint32_t lane) {
-    uint32_t r = 1;
+// Returns a mask: bit 0 = the Huffman tree is inherited, bit 1 = at least one FSE table is.
+__device__ __forceinline__ uint32_t zd_block_inherits(const uint8_t* blk, uint32_t bsize, uint32_t lane) {
+    uint32_t r = 3;
     if (lane == 0) {
         do {
             if (bsize < 2) break;
@@ -413,7 +425,7 @@ __device__ __forceinline__ bool zd_block_inherits(const uint8_t* blk, uint32_t b
                 else { if (bsize < 3) break; hs = 3; regen = (b0 >> 4) | ((uint32_t)blk[1] << 4) | ((uint32_t)blk[2] << 12); }
                 comp = type == 0 ? regen : 1;
             } else {
-                if (type == 3 || bsize < 5) break;                           // treeless: inherits the Huffman table
+                if (bsize < 5) break;
                 const uint32_t h = blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
                 if (sf <= 1) { hs = 3; comp = (h >> 14) & 0x3ff; }
                 else if (sf == 2) { hs = 4; comp = h >> 18; }
@@ -424,13 +436,14 @@ __device__ __forceinline__ bool zd_block_inherits(const uint8_t* blk, uint32_t b
             const uint32_t ssize = bsize - hs - comp;
             uint32_t nseq = sp[0], sh = 1;
             if (nseq >= 128) { sh = nseq == 255 ? 3 : 2; if (ssize < sh) break; nseq = 1; }
-            if (nseq == 0) { r = 0; break; }
+            const uint32_t huf = type == 3 ? 1u : 0u;                        // treeless literals
+            if (nseq == 0) { r = huf; break; }
             if (ssize < sh + 1) break;
             const uint32_t modes = sp[sh];
-            r = ((modes >> 6) == 3 || ((modes >> 4) & 3) == 3 || ((modes >> 2) & 3) == 3) ? 1u : 0u;
+            r = huf | (((modes >> 6) == 3 || ((modes >> 4) & 3) == 3 || ((modes >> 2) & 3) == 3) ? 2u : 0u);
         } while (false);
     }
-    return __shfl_sync(TS_FULL, r, 0) != 0;
+    return __shfl_sync(TS_FULL, r, 0);
 }
 
 // Entropy stage of one Compressed_Block: literals into the frame's literal arena (unless Raw / RLE), sequences as
@@ -696,7 +709,23 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_entropy_kernel(const
     if (pos + 3 + bsz > n || bsz > zf::BLOCK_MAX) { if (lane == 0) meta->status = 2; return; }
     if (lane == 0) { cx->err = 0; cx->huf_valid = 0; cx->ll_valid = 0; cx->ml_valid = 0; cx->of_valid = 0; }
     __syncwarp();
-    if (zd_block_inherits(p + pos + 3, bsz, lane)) {
+    const uint32_t inherits = zd_block_inherits(p + pos + 3, bsz, lane);
+    if (inherits == 1) {
+        // only the Huffman tree (what libzstd writes in nearly every block after the first): the latest block with
+        // Compressed_Literals defines it
+        bool found = false;
+        for (uint32_t j = b; j-- > 0 && !found; ) {
+            const uint32_t pj = bo[j];
+            const uint32_t hj = p[pj] | (p[pj + 1] << 8) | ((uint32_t)p[pj + 2] << 16);
+            const uint32_t bj = hj >> 3;
+            if (((hj >> 1) & 3) != 2 || bj < 1 || (p[pj + 3] & 3) != 2) continue;
+            found = true;
+            if (bj > zf::BLOCK_MAX) { if (lane == 0) cx->err = -1; __syncwarp(); break; }
+            zd_block_huf_only(p + pj + 3, bj, cx, lane);
+            __syncwarp();
+        }
+        if (!found && !cx->err) { if (lane == 0) cx->err = -1; __syncwarp(); }      // treeless without any tree before it
+    } else if (inherits) {
         // replay the table definitions of every earlier Compressed_Block, in order (the index pass checked their bounds)
         for (uint32_t j = 0; j < b; j++) {
             const uint32_t pj = bo[j];
