@@ -53,7 +53,8 @@ const char* tsgpu_version(void);
  * 8 of them in flight per device (work slots, allocated on first use; each has a compute stream and a copy-out stream).
  * With 4 MiB chunks `max_batch = 4` measured best through PCIe; device-resident callers pass whole segments.
  * Environment (read once by tsgpu_create; tuning only): TSGPU_SLOTS=1..16 slots per device, TSGPU_SPLIT_OUT=0 puts the
- * copies-out back on the compute stream.
+ * copies-out back on the compute stream.  Variants that are off by default and not yet timed:
+ * TSGPU_ENC_SPLIT=1 (compressor as two launches), TSGPU_DEC_PARALLEL=1 (libzstd-shaped frames: entropy stage per block).
  * --------------------------------------------------------------------------------------------------------- */
 int  tsgpu_create(const int* device_ids, int n_devices, uint32_t max_chunk_bytes, uint32_t max_batch,
                   tsgpu_ctx** out);
