@@ -156,6 +156,15 @@ static void gpuChainTests(tsgpu_ctx* ctx) {
             Bytes round;
             while (de.hasMoreElements()) { Bytes c = de.nextElement(); round.insert(round.end(), c.begin(), c.end()); }
             CHECK(round.size() == (size_t)use_n && memcmp(round.data(), src.data(), use_n) == 0);
+            {   // DetransformFinisher: the same bytes as one stream
+                std::istringstream fin2(std::string((const char*)obj.data(), obj.size()));
+                DetransformChunkEnumeration de2(ctx, &fin2, chunks, mode & 1, (mode & 2) ? &km : nullptr, cs ? (uint32_t)std::min(cs, use_n) : use_n, 3);
+                DetransformFinisher df(&de2);
+                Bytes all = df.readAll();
+                CHECK(all.size() == (size_t)use_n && memcmp(all.data(), src.data(), use_n) == 0);
+                CHECK(!df.hasMoreElements());
+                CHECK(throwsWith<NoSuchElementException>([&] { df.nextElement(); }, "NoSuchElementException"));
+            }
             // truncated stream: "Stream has fewer bytes than expected" (BaseDetransformChunkEnumerationTest.java:100-117)
             std::istringstream tin(std::string((const char*)obj.data(), obj.size() - 1));
             DetransformChunkEnumeration dt(ctx, &tin, chunks, mode & 1, (mode & 2) ? &km : nullptr, cs ? (uint32_t)std::min(cs, use_n) : use_n, 1024);

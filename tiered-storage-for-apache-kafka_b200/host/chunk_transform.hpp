@@ -383,6 +383,20 @@ private:
     DataKeyAndAAD km; std::vector<Bytes> ready;
 };
 
+// DetransformFinisher.java:30-55: the enumeration of byte[] as ONE stream of original bytes (the reference concatenates
+// ByteArrayInputStreams in a SequenceInputStream; with no transform at all the input stream is passed through untouched).
+class DetransformFinisher {
+public:
+    explicit DetransformFinisher(DetransformChunkEnumeration* inner) : inner(inner) {
+        if (!inner) throw NullPointerException("inner cannot be null");
+    }
+    bool hasMoreElements() { return inner->hasMoreElements(); }
+    Bytes nextElement() { return inner->nextElement(); }
+    Bytes readAll() { Bytes all; while (hasMoreElements()) { Bytes c = nextElement(); all.insert(all.end(), c.begin(), c.end()); } return all; }
+private:
+    DetransformChunkEnumeration* inner;
+};
+
 // FetchChunkEnumeration.java:54-138: which chunks cover [from, to] and how much of the first / last one to keep.
 struct FetchPiece { int chunkId, skip, take; };
 inline std::vector<FetchPiece> fetchPlan(const ChunkIndex& index, int from, int to) {
