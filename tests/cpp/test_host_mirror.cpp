@@ -198,6 +198,22 @@ static Bytes recordV1(int codec, const std::string& payload) {
     return b;
 }
 
+static void bytesRangeTests() {                              // storage/core/T/.../BytesRangeTest.java
+    CHECK(throwsWith<IllegalArgumentException>([] { BytesRange::of(-1, 1); }, "from cannot be negative, -1 given"));
+    CHECK(throwsWith<IllegalArgumentException>([] { BytesRange::of(2, 1); }, "to cannot be less than from, from=2, to=1 given"));
+    CHECK(BytesRange::of(1, 1).size() == 1 && BytesRange::of(0, 9).size() == 10 && BytesRange::of(3, 9).lastPosition() == 9);
+    CHECK(BytesRange::empty(5).isEmpty() && BytesRange::empty(5).size() == 0 && BytesRange::ofFromPositionAndSize(5, 0) == BytesRange::empty(5));
+    CHECK(BytesRange::ofFromPositionAndSize(1, 2) == BytesRange::of(1, 2));
+    CHECK(throwsWith<IllegalStateException>([] { BytesRange::empty(0).lastPosition(); }, "No last position, range is empty"));
+    CHECK(BytesRange::of(10, 19).toString() == "BytesRange{position=10, size=10}");
+    auto idx = VariableSizeChunkIndex(100, 250, {10, 20, 30});
+    auto r = transformedRange(idx.chunksForRange(BytesRange::of(100, 249).from, BytesRange::of(100, 249).to));
+    CHECK(r == BytesRange::of(10, 59));                      // chunks 1 and 2: transformed bytes [10, 60)
+    // the reference steps by the chunk's size from the RANGE start (AbstractChunkIndex.java:113-123), so an unaligned
+    // start can stop before the last chunk the range touches; the mirror keeps that behaviour
+    CHECK(idx.chunksForRange(150, 249).size() == 1 && idx.chunksForRange(150, 250).size() == 1 && idx.chunksForRange(100, 200).size() == 2);
+}
+
 static void uploadSideTests() {
     // checksum known answers (the "check" values of the CRC catalogue): pins both polynomials and the reflection
     CHECK(crc32c((const uint8_t*)"123456789", 9) == 0xE3069283u);
@@ -307,6 +323,7 @@ static void segmentUploadTests(tsgpu_ctx* ctx) {
 
 int main(int argc, char** argv) {
     builderTests();
+    bytesRangeTests();
     uploadSideTests();
     manifestTests();
     baseAndFinisherTests();

@@ -397,6 +397,33 @@ private:
     DetransformChunkEnumeration* inner;
 };
 
+// storage/core/src/main/java/io/aiven/kafka/tieredstorage/storage/BytesRange.java:26-113: inclusive on both ends, `to == -1`
+// is the empty range.
+struct BytesRange {
+    int from, to;
+    static BytesRange of(int from, int to) {
+        if (from < 0) throw IllegalArgumentException("from cannot be negative, " + std::to_string(from) + " given");
+        if (to != -1 && to < from)
+            throw IllegalArgumentException("to cannot be less than from, from=" + std::to_string(from) + ", to=" + std::to_string(to) + " given");
+        return BytesRange{from, to};
+    }
+    static BytesRange empty(int from) { return of(from, -1); }
+    static BytesRange ofFromPositionAndSize(int from, int size) { return size == 0 ? empty(from) : of(from, from + size - 1); }
+    int firstPosition() const { return from; }
+    bool isEmpty() const { return to == -1; }
+    int lastPosition() const { if (isEmpty()) throw IllegalStateException("No last position, range is empty"); return to; }
+    int size() const { return isEmpty() ? 0 : to - from + 1; }
+    bool operator==(const BytesRange& o) const { return from == o.from && to == o.to; }
+    std::string toString() const { return "BytesRange{position=" + std::to_string(from) + ", size=" + std::to_string(size()) + "}"; }
+};
+// The ONE ranged GET that covers consecutive chunks (what a batched DefaultChunkManager issues): from the
+// first chunk's transformed position to the last chunk's last transformed byte (Chunk.range(), core/M/Chunk.java:21-36).
+inline BytesRange transformedRange(const std::vector<Chunk>& consecutive) {
+    if (consecutive.empty()) throw IllegalArgumentException("no chunks");
+    const Chunk& a = consecutive.front(); const Chunk& b = consecutive.back();
+    return BytesRange::of(a.transformedPosition, b.transformedPosition + b.transformedSize - 1);
+}
+
 // FetchChunkEnumeration.java:54-138: which chunks cover [from, to] and how much of the first / last one to keep.
 struct FetchPiece { int chunkId, skip, take; };
 inline std::vector<FetchPiece> fetchPlan(const ChunkIndex& index, int from, int to) {
