@@ -156,6 +156,25 @@ static void gpuChainTests(tsgpu_ctx* ctx) {
             Bytes round;
             while (de.hasMoreElements()) { Bytes c = de.nextElement(); round.insert(round.end(), c.begin(), c.end()); }
             CHECK(round.size() == (size_t)use_n && memcmp(round.data(), src.data(), use_n) == 0);
+            {   // FetchChunkEnumerationTest.java:105-145 on real transformed data: one ranged GET, batched detransform
+                int gets = 0;
+                auto fetcher = [&](const BytesRange& r) { gets++; return Bytes(obj.begin() + r.from, obj.begin() + r.to + 1); };
+                const int last = use_n - 1;
+                const int ranges[][2] = {{0, last}, {last, last}, {0, 0}, {use_n / 3, use_n / 3 + 2}, {use_n / 2, last + 1000}, {1, std::max(1, last - 1)}};
+                for (auto& rg : ranges) {
+                    if (rg[0] > last) continue;
+                    gets = 0;
+                    FetchChunkEnumeration fe(ctx, *idx, BytesRange::of(rg[0], rg[1]), fetcher, mode & 1, (mode & 2) ? &km : nullptr, 4);
+                    Bytes got = fe.readAll();
+                    const int to = std::min(rg[1], last);
+                    CHECK(gets == 1);
+                    CHECK(got.size() == (size_t)(to - rg[0] + 1) && memcmp(got.data(), src.data() + rg[0], got.size()) == 0);
+                }
+                CHECK(throwsWith<IllegalArgumentException>([&] { FetchChunkEnumeration(ctx, *idx, BytesRange::of(use_n, use_n + 5), fetcher, mode & 1, (mode & 2) ? &km : nullptr); },
+                                                           "Invalid start position"));
+                CHECK(throwsWith<IllegalArgumentException>([&] { FetchChunkEnumeration(ctx, *idx, BytesRange::empty(0), fetcher, mode & 1, (mode & 2) ? &km : nullptr); },
+                                                           "range cannot be empty"));
+            }
             {   // DetransformFinisher: the same bytes as one stream
                 std::istringstream fin2(std::string((const char*)obj.data(), obj.size()));
                 DetransformChunkEnumeration de2(ctx, &fin2, chunks, mode & 1, (mode & 2) ? &km : nullptr, cs ? (uint32_t)std::min(cs, use_n) : use_n, 3);

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <functional>
+#include <sstream>
 #include <istream>
 #include <memory>
 #include <optional>
@@ -446,6 +447,47 @@ inline std::vector<FetchPiece> fetchPlan(const ChunkIndex& index, int from, int 
     }
     return plan;
 }
+
+// FetchChunkEnumeration + DefaultChunkManager, batched: the reference asks its ChunkManager for one chunk
+// at a time (one ranged GET and one detransform each, DefaultChunkManager.java:50-70); here the chunks the range touches
+// are fetched with ONE ranged GET and detransformed in batches, then served with the reference's skip / bound rules.
+class FetchChunkEnumeration {
+public:
+    using RangeFetcher = std::function<Bytes(const BytesRange&)>;       // ObjectFetcher.fetch(key, range)
+    FetchChunkEnumeration(tsgpu_ctx* ctx, const ChunkIndex& index, const BytesRange& range, RangeFetcher fetcher, bool decompress,
+                          const DataKeyAndAAD* decryptWith, uint32_t batchChunks = 32)
+        : ctx(ctx), decompress(decompress), batch(batchChunks ? batchChunks : 1) {
+        if (!ctx) throw NullPointerException("chunkManager cannot be null");
+        if (!fetcher) throw NullPointerException("objectKey cannot be null");
+        if (range.isEmpty()) throw IllegalArgumentException("range cannot be empty");
+        if (decryptWith) { km = *decryptWith; decrypt = true; }
+        plan = fetchPlan(index, range.firstPosition(), range.lastPosition());
+        uint32_t maxOriginal = 1;
+        for (const FetchPiece& pc : plan) {
+            chunks.push_back(index.chunks()[pc.chunkId]);
+            maxOriginal = std::max<uint32_t>(maxOriginal, (uint32_t)chunks.back().originalSize);
+        }
+        object = fetcher(transformedRange(chunks));
+        if (object.size() != (size_t)transformedRange(chunks).size()) throw std::runtime_error("Stream has fewer bytes than expected");
+        stream = std::make_unique<std::istringstream>(std::string((const char*)object.data(), object.size()));
+        inner = std::make_unique<DetransformChunkEnumeration>(ctx, stream.get(), chunks, decompress, decrypt ? &km : nullptr, maxOriginal, batch);
+    }
+    bool hasMoreElements() const { return next < plan.size(); }
+    Bytes nextElement() {
+        if (!hasMoreElements()) throw NoSuchElementException();
+        Bytes chunk = inner->nextElement();
+        const FetchPiece& pc = plan[next++];
+        if ((size_t)pc.skip > chunk.size()) return Bytes();
+        const size_t take = std::min<size_t>((size_t)pc.take, chunk.size() - (size_t)pc.skip);
+        return Bytes(chunk.begin() + pc.skip, chunk.begin() + pc.skip + take);
+    }
+    Bytes readAll() { Bytes all; while (hasMoreElements()) { Bytes c = nextElement(); all.insert(all.end(), c.begin(), c.end()); } return all; }
+    size_t chunkCount() const { return plan.size(); }
+private:
+    tsgpu_ctx* ctx; bool decompress, decrypt = false; uint32_t batch;
+    DataKeyAndAAD km; std::vector<FetchPiece> plan; std::vector<Chunk> chunks; Bytes object;
+    std::unique_ptr<std::istringstream> stream; std::unique_ptr<DetransformChunkEnumeration> inner; size_t next = 0;
+};
 
 // ------------------------------------------------------------------ SegmentManifestV1 JSON
 // Writer for the exact on-disk form of core/M/manifest/SegmentManifestV1.java:37-91 with the property order Jackson
