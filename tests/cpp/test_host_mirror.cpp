@@ -86,6 +86,24 @@ static void manifestTests() {
     CHECK(segmentManifestV1Json(idx, with, false, std::nullopt, &aad, m) ==
           HEAD + "\"transaction\":{\"position\":4,\"size\":1}},\"compression\":false,\"encryption\":{\"aad\":\"CgsMDQ==\"},\"remoteLogSegmentMetadata\":" + META + "}");
     CHECK(segmentManifestV1Json(idx, with, true, std::string("key1:AAEC"), &aad, m).find("\"compression\":true,\"encryption\":{\"dataKey\":\"key1:AAEC\",\"aad\":\"CgsMDQ==\"}") != std::string::npos);
+    // reader: the golden strings parse back to what they were written from, and re-serialise to themselves
+    for (int v = 0; v < 4; v++) {
+        const std::string text = v == 0 ? segmentManifestV1Json(idx, with, false, std::nullopt, nullptr, m)
+                               : v == 1 ? segmentManifestV1Json(idx, without, false, std::nullopt, nullptr, m)
+                               : v == 2 ? segmentManifestV1Json(idx, with, false, std::nullopt, &aad, m)
+                                        : segmentManifestV1Json(idx, with, true, std::string("key1:AAEC"), &aad, m);
+        SegmentManifestV1 r = parseSegmentManifestV1(text, nullptr);
+        CHECK(r.chunkIndex->toJson() == idx.toJson() && r.compression == (v == 3));
+        CHECK(r.segmentIndexes.transaction.has_value() == (v != 1) && r.segmentIndexes.leaderEpoch.position == 3);
+        CHECK(r.aad.has_value() == (v >= 2) && (!r.aad || *r.aad == aad));
+        CHECK(r.wrappedDataKey.has_value() == (v == 3) && (!r.wrappedDataKey || *r.wrappedDataKey == "key1:AAEC"));
+        CHECK(r.remoteLogSegmentMetadata.topic == "topic1" && r.remoteLogSegmentMetadata.partition == 42 && r.remoteLogSegmentMetadata.segmentLeaderEpochs.size() == 3);
+        CHECK(segmentManifestV1Json(*r.chunkIndex, r.segmentIndexes, r.compression, r.wrappedDataKey, r.aad ? &*r.aad : nullptr, r.remoteLogSegmentMetadata) == text);
+    }
+    CHECK(throwsWith<IllegalArgumentException>([&] { parseSegmentManifestV1("{\"version\":\"2\"}", nullptr); }, "unsupported version"));
+    CHECK(throwsWith<IllegalArgumentException>([&] { parseSegmentManifestV1("{\"version\":\"1\",\"extra\":1}", nullptr); }, "unknown property 'extra'"));
+    CHECK(throwsWith<IllegalArgumentException>([&] { parseSegmentManifestV1("{\"version\":\"1\"", nullptr); }, "manifest JSON"));
+    CHECK(base64StdDecode("CgsMDQ==") == aad);
     // core/IT/RemoteStorageManagerTest.java:117-120 style key
     CHECK(objectKey("test/", m, Suffix::LOG) == "test/topic1-lZ6vvmajTWKDBUTV6SQAtQ/42/00000000000000000000-adh9f8BMS4anaUnD8KWfWg.log");
     CHECK(objectKey("", m, Suffix::MANIFEST) == "topic1-lZ6vvmajTWKDBUTV6SQAtQ/42/00000000000000000000-adh9f8BMS4anaUnD8KWfWg.rsm-manifest");
@@ -156,6 +174,19 @@ static void gpuChainTests(tsgpu_ctx* ctx) {
             Bytes round;
             while (de.hasMoreElements()) { Bytes c = de.nextElement(); round.insert(round.end(), c.begin(), c.end()); }
             CHECK(round.size() == (size_t)use_n && memcmp(round.data(), src.data(), use_n) == 0);
+            {   // the manifest a segment like this one would get: written, read back (variable indexes decode their size list on the device)
+                RemoteLogSegmentMetadataJson md{"lZ6vvmajTWKDBUTV6SQAtQ", "topic1", 7, "adh9f8BMS4anaUnD8KWfWg", 0, 99, 1, 2, 3, {{0, 0}}};
+                SegmentIndexesV1 six{{0, 10}, {10, 10}, {20, 10}, {30, 10}, std::nullopt};
+                const std::string text = segmentManifestV1Json(*idx, six, mode & 1, (mode & 2) ? std::optional<std::string>("k:AAEC") : std::nullopt,
+                                                               (mode & 2) ? &km.aad : nullptr, md);
+                SegmentManifestV1 back = parseSegmentManifestV1(text, ctx);
+                CHECK(back.chunkIndex->chunks().size() == idx->chunks().size());
+                bool same = true;
+                for (size_t k = 0; k < idx->chunks().size(); k++)
+                    same = same && back.chunkIndex->chunks()[k].transformedPosition == idx->chunks()[k].transformedPosition &&
+                           back.chunkIndex->chunks()[k].transformedSize == idx->chunks()[k].transformedSize;
+                CHECK(same && back.compression == ((mode & 1) != 0) && back.aad.has_value() == ((mode & 2) != 0));
+            }
             {   // FetchChunkEnumerationTest.java:105-145 on real transformed data: one ranged GET, batched detransform
                 int gets = 0;
                 auto fetcher = [&](const BytesRange& r) { gets++; return Bytes(obj.begin() + r.from, obj.begin() + r.to + 1); };
@@ -303,6 +334,28 @@ static void uploadSideTests() {
 
 // RemoteStorageManager.uploadSegmentLog through the GPU chain: heuristic decides the flags, parts arrive in order, the
 // object equals what the reference-side reader expects, the chunk index is the reference's
+// A manifest as the REFERENCE writes it: the size list compressed by libzstd (oracle), read back through the device decoder
+static void referenceManifestTests(tsgpu_ctx* ctx) {
+    std::vector<int32_t> sizes;
+    for (int i = 0; i < 600; i++) sizes.push_back(1000000 + (i * 7919) % 5000);
+    std::vector<char> b64(64 * 1024);
+    const int64_t n = ora_transformed_chunks_serialize(sizes.data(), (int32_t)sizes.size(), b64.data(), b64.size());
+    CHECK(n > 0);
+    const std::string text = std::string("{\"version\":\"1\",\"chunkIndex\":{\"type\":\"variable\",\"originalChunkSize\":1048576,\"originalFileSize\":")
+        + std::to_string(599LL * 1048576 + 1) + ",\"transformedChunks\":\"" + std::string(b64.data(), (size_t)n) + "\"},\"segmentIndexes\":{\"offset\":{\"position\":0,\"size\":1},"
+        "\"timestamp\":{\"position\":1,\"size\":1},\"producerSnapshot\":{\"position\":2,\"size\":1},\"leaderEpoch\":{\"position\":3,\"size\":1},\"transaction\":null},"
+        "\"compression\":true,\"encryption\":{\"dataKey\":\"k1:AAEC\",\"aad\":\"CgsMDQ==\"}}";
+    SegmentManifestV1 m = parseSegmentManifestV1(text, ctx);
+    auto* v = dynamic_cast<VariableSizeChunkIndex*>(m.chunkIndex.get());
+    CHECK(v != nullptr && v->transformedChunks == sizes && m.compression && m.wrappedDataKey && *m.wrappedDataKey == "k1:AAEC");
+    CHECK(m.chunkIndex->chunks().size() == 600 && m.chunkIndex->chunks()[599].originalSize == 1);
+    // the golden variable index of ChunkIndexSerializationTest.java:63-74
+    SegmentManifestV1 g = parseSegmentManifestV1("{\"version\":\"1\",\"chunkIndex\":{\"type\":\"variable\",\"originalChunkSize\":100,\"originalFileSize\":250,"
+        "\"transformedChunks\":\"KLUv/SAPeQAAAAAAAwAAAAoBAAoAAAAe\"},\"segmentIndexes\":{\"offset\":{\"position\":0,\"size\":1},\"timestamp\":{\"position\":1,\"size\":1},"
+        "\"producerSnapshot\":{\"position\":2,\"size\":1},\"leaderEpoch\":{\"position\":3,\"size\":1},\"transaction\":null},\"compression\":false}", ctx);
+    CHECK(g.chunkIndex->chunks().size() == 3 && g.chunkIndex->chunks()[2].transformedPosition == 30 && g.chunkIndex->chunks()[2].transformedSize == 30);
+}
+
 static void segmentUploadTests(tsgpu_ctx* ctx) {
     std::mt19937 rng(5);
     for (int codec : {0, 4}) for (int enc = 0; enc < 2; enc++) {
@@ -352,6 +405,7 @@ int main(int argc, char** argv) {
         if (rc) { printf("tsgpu_create failed: %s\n", tsgpu_last_error()); return 2; }
         gpuChainTests(ctx);
         segmentUploadTests(ctx);
+        referenceManifestTests(ctx);
         tsgpu_destroy(ctx);
     }
     printf("%s: %d checks, %d failures\n", failures ? "FAILED" : "OK", checks, failures);

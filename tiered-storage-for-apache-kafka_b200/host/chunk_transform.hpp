@@ -538,6 +538,151 @@ inline std::string segmentManifestV1Json(const ChunkIndex& chunkIndex, const Seg
     return s + "}}}";
 }
 
+// Reader for the same form (the reference reads it with Jackson; a C++ fetch-side consumer needs the chunk index, the
+// compression flag, the AAD and the wrapped data key — unwrapping the key stays with the host's RsaEncryptionProvider).
+// Unknown properties are an error, as with the reference's ObjectMapper (FAIL_ON_UNKNOWN_PROPERTIES is Jackson's default).
+namespace json {
+struct Value {
+    enum Kind { Null, Bool, Number, String, Object, Array } kind = Null;
+    bool b = false; long long num = 0; std::string str;
+    std::vector<std::pair<std::string, Value>> obj; std::vector<Value> arr;
+    const Value* get(const std::string& k) const { for (auto& kv : obj) if (kv.first == k) return &kv.second; return nullptr; }
+};
+struct Parser {
+    const std::string& s; size_t p = 0;
+    explicit Parser(const std::string& s) : s(s) {}
+    [[noreturn]] void fail(const char* what) const { throw IllegalArgumentException(std::string("manifest JSON: ") + what + " at " + std::to_string(p)); }
+    void ws() { while (p < s.size() && (s[p] == ' ' || s[p] == '\n' || s[p] == '\t' || s[p] == '\r')) p++; }
+    bool eat(char c) { ws(); if (p < s.size() && s[p] == c) { p++; return true; } return false; }
+    std::string string() {
+        if (!eat('"')) fail("string expected");
+        std::string o;
+        while (p < s.size() && s[p] != '"') {
+            if (s[p] == '\\') {
+                if (++p >= s.size()) fail("bad escape");
+                const char c = s[p++];
+                if (c == 'n') o += '\n'; else if (c == 't') o += '\t'; else if (c == 'r') o += '\r'; else if (c == 'b') o += '\b'; else if (c == 'f') o += '\f';
+                else if (c == 'u') { if (p + 4 > s.size()) fail("bad \\u"); o += (char)std::stoi(s.substr(p, 4), nullptr, 16); p += 4; }
+                else o += c;
+            } else o += s[p++];
+        }
+        if (p >= s.size()) fail("unterminated string");
+        p++;
+        return o;
+    }
+    Value value() {
+        ws();
+        Value v;
+        if (p >= s.size()) fail("value expected");
+        const char c = s[p];
+        if (c == '{') {
+            p++; v.kind = Value::Object;
+            if (eat('}')) return v;
+            do { std::string k = string(); if (!eat(':')) fail("':' expected"); v.obj.emplace_back(std::move(k), value()); } while (eat(','));
+            if (!eat('}')) fail("'}' expected");
+        } else if (c == '[') {
+            p++; v.kind = Value::Array;
+            if (eat(']')) return v;
+            do { v.arr.push_back(value()); } while (eat(','));
+            if (!eat(']')) fail("']' expected");
+        } else if (c == '"') { v.kind = Value::String; v.str = string(); }
+        else if (s.compare(p, 4, "true") == 0) { v.kind = Value::Bool; v.b = true; p += 4; }
+        else if (s.compare(p, 5, "false") == 0) { v.kind = Value::Bool; p += 5; }
+        else if (s.compare(p, 4, "null") == 0) { p += 4; }
+        else {
+            size_t q = p; if (q < s.size() && s[q] == '-') q++;
+            while (q < s.size() && s[q] >= '0' && s[q] <= '9') q++;
+            if (q == p || (q == p + 1 && s[p] == '-')) fail("unexpected character");
+            v.kind = Value::Number; v.num = std::stoll(s.substr(p, q - p)); p = q;
+        }
+        return v;
+    }
+};
+}  // namespace json
+
+inline Bytes base64StdDecode(const std::string& in) {
+    Bytes o; uint32_t acc = 0; int bits = 0;
+    for (char c : in) {
+        int v = c >= 'A' && c <= 'Z' ? c - 'A' : c >= 'a' && c <= 'z' ? c - 'a' + 26 : c >= '0' && c <= '9' ? c - '0' + 52 : c == '+' ? 62 : c == '/' ? 63 : -1;
+        if (c == '=') break;
+        if (v < 0) throw IllegalArgumentException("Illegal base64 character");
+        acc = acc << 6 | (uint32_t)v; bits += 6;
+        if (bits >= 8) { bits -= 8; o.push_back((uint8_t)(acc >> bits)); }
+    }
+    return o;
+}
+
+struct SegmentManifestV1 {
+    std::shared_ptr<ChunkIndex> chunkIndex;
+    SegmentIndexesV1 segmentIndexes{};
+    bool compression = false;
+    std::optional<std::string> wrappedDataKey;       // "<keyId>:<base64>" as written; unwrapping is the host's business
+    std::optional<Bytes> aad;
+    RemoteLogSegmentMetadataJson remoteLogSegmentMetadata{};
+};
+// `ctx` is needed for variable indexes: the size list is a zstd frame (possibly libzstd-compressed) decoded on the device.
+inline SegmentManifestV1 parseSegmentManifestV1(const std::string& text, tsgpu_ctx* ctx) {
+    using json::Value;
+    json::Parser ps(text);
+    const Value root = ps.value();
+    ps.ws();
+    if (ps.p != text.size() || root.kind != Value::Object) throw IllegalArgumentException("manifest JSON: one object expected");
+    auto need = [](const Value& o, const char* k, Value::Kind kind) -> const Value& {
+        const Value* v = o.get(k);
+        if (!v || v->kind != kind) throw IllegalArgumentException(std::string("manifest JSON: missing or mistyped property '") + k + "'");
+        return *v;
+    };
+    auto only = [](const Value& o, std::initializer_list<const char*> allowed) {
+        for (auto& kv : o.obj) { bool ok = false; for (const char* a : allowed) ok = ok || kv.first == a; if (!ok) throw IllegalArgumentException("manifest JSON: unknown property '" + kv.first + "'"); }
+    };
+    only(root, {"version", "chunkIndex", "segmentIndexes", "compression", "encryption", "remoteLogSegmentMetadata"});
+    if (need(root, "version", Value::String).str != "1") throw IllegalArgumentException("manifest JSON: unsupported version");
+    SegmentManifestV1 m;
+    const Value& ci = need(root, "chunkIndex", Value::Object);
+    const std::string type = need(ci, "type", Value::String).str;
+    const int ocs = (int)need(ci, "originalChunkSize", Value::Number).num, ofs = (int)need(ci, "originalFileSize", Value::Number).num;
+    if (type == "fixed") {
+        only(ci, {"type", "originalChunkSize", "originalFileSize", "transformedChunkSize", "finalTransformedChunkSize"});
+        m.chunkIndex = std::make_shared<FixedSizeChunkIndex>(ocs, ofs, (int)need(ci, "transformedChunkSize", Value::Number).num,
+                                                             (int)need(ci, "finalTransformedChunkSize", Value::Number).num);
+    } else if (type == "variable") {
+        only(ci, {"type", "originalChunkSize", "originalFileSize", "transformedChunks"});
+        const std::string& b64 = need(ci, "transformedChunks", Value::String).str;
+        std::vector<int32_t> sizes(b64.size() * 2 + 1024);          // every size takes >= 1 byte of the decoded frame, Base64 inflates by 4/3
+        uint32_t n = (uint32_t)sizes.size();
+        int rc = tsgpu_transformed_chunks_deserialize(ctx, b64.c_str(), sizes.data(), &n);
+        if (rc == TSGPU_E_SHORT) { sizes.resize((size_t)ofs / std::max(1, ocs) + 2); n = (uint32_t)sizes.size(); rc = tsgpu_transformed_chunks_deserialize(ctx, b64.c_str(), sizes.data(), &n); }
+        if (rc) throw IllegalArgumentException(tsgpu_last_error());
+        sizes.resize(n);
+        m.chunkIndex = std::make_shared<VariableSizeChunkIndex>(ocs, ofs, sizes);
+    } else throw IllegalArgumentException("manifest JSON: unknown chunk index type '" + type + "'");
+    const Value& si = need(root, "segmentIndexes", Value::Object);
+    only(si, {"offset", "timestamp", "producerSnapshot", "leaderEpoch", "transaction"});
+    auto one = [&](const char* k) { const Value& v = need(si, k, Value::Object); return SegmentIndexV1{(int)need(v, "position", Value::Number).num, (int)need(v, "size", Value::Number).num}; };
+    m.segmentIndexes.offset = one("offset"); m.segmentIndexes.timestamp = one("timestamp");
+    m.segmentIndexes.producerSnapshot = one("producerSnapshot"); m.segmentIndexes.leaderEpoch = one("leaderEpoch");
+    if (const Value* t = si.get("transaction")) if (t->kind == Value::Object) m.segmentIndexes.transaction = one("transaction");
+    m.compression = need(root, "compression", Value::Bool).b;
+    if (const Value* e = root.get("encryption")) if (e->kind == Value::Object) {
+        only(*e, {"dataKey", "aad"});
+        if (const Value* k = e->get("dataKey")) if (k->kind == Value::String) m.wrappedDataKey = k->str;
+        m.aad = base64StdDecode(need(*e, "aad", Value::String).str);
+    }
+    if (const Value* r = root.get("remoteLogSegmentMetadata")) if (r->kind == Value::Object) {
+        auto& o = m.remoteLogSegmentMetadata;
+        const Value& id = need(*r, "remoteLogSegmentId", Value::Object);
+        const Value& tip = need(id, "topicIdPartition", Value::Object);
+        const Value& tp = need(tip, "topicPartition", Value::Object);
+        o.topicId = need(tip, "topicId", Value::String).str; o.topic = need(tp, "topic", Value::String).str;
+        o.partition = (int)need(tp, "partition", Value::Number).num; o.id = need(id, "id", Value::String).str;
+        o.startOffset = need(*r, "startOffset", Value::Number).num; o.endOffset = need(*r, "endOffset", Value::Number).num;
+        o.maxTimestampMs = need(*r, "maxTimestampMs", Value::Number).num; o.brokerId = (int)need(*r, "brokerId", Value::Number).num;
+        o.eventTimestampMs = need(*r, "eventTimestampMs", Value::Number).num;
+        for (auto& kv : need(*r, "segmentLeaderEpochs", Value::Object).obj) o.segmentLeaderEpochs.emplace_back(std::stoi(kv.first), kv.second.num);
+    }
+    return m;
+}
+
 // Object keys (core/M/ObjectKeyFactory.java:43-53, 81-124): "<prefix><topic>-<topicId>/<partition>/<startOffset %020d>-<segmentId>.<suffix>"
 enum class Suffix { LOG, INDEXES, MANIFEST };
 inline std::string objectKey(const std::string& prefix, const RemoteLogSegmentMetadataJson& m, Suffix suffix) {
