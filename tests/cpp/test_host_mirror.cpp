@@ -334,6 +334,42 @@ static void uploadSideTests() {
 
 // RemoteStorageManager.uploadSegmentLog through the GPU chain: heuristic decides the flags, parts arrive in order, the
 // object equals what the reference-side reader expects, the chunk index is the reference's
+// RemoteStorageManager.uploadIndexes / fetchIndexBytes: five index files, one ragged AES batch, positions as the reference records them
+static void indexFileTests(tsgpu_ctx* ctx) {
+    // SegmentIndexesV1BuilderTest-style state machine
+    CHECK(throwsWith<IllegalStateException>([] { SegmentIndexesV1Builder().add(IndexType::OFFSET, 1).add(IndexType::OFFSET, 1); }, "Index OFFSET is already added"));
+    CHECK(throwsWith<IllegalStateException>([] { SegmentIndexesV1Builder().add(IndexType::OFFSET, 1).add(IndexType::TIMESTAMP, 1).build(); },
+                                            "Not enough indexes have been added; at least 4 required. Indexes included: [OFFSET, TIMESTAMP]"));
+    CHECK(throwsWith<IllegalStateException>([] { SegmentIndexesV1Builder().add(IndexType::OFFSET, 1).add(IndexType::TIMESTAMP, 1).add(IndexType::PRODUCER_SNAPSHOT, 1)
+                                                     .add(IndexType::TRANSACTION, 1).build(); }, "OFFSET, TIMESTAMP, PRODUCER_SNAPSHOT, and LEADER_EPOCH indexes are required"));
+    SegmentIndexesV1 plain = SegmentIndexesV1Builder().add(IndexType::OFFSET, 10).add(IndexType::TIMESTAMP, 20).add(IndexType::PRODUCER_SNAPSHOT, 0)
+                                 .add(IndexType::LEADER_EPOCH, 5).build();
+    CHECK(plain.timestamp.position == 10 && plain.producerSnapshot.position == 30 && plain.leaderEpoch.position == 30 && !plain.transaction);
+    std::mt19937 rng(11);
+    auto blob = [&](size_t n) { Bytes b(n); for (auto& x : b) x = (uint8_t)rng(); return b; };
+    DataKeyAndAAD km; km.dataKey = blob(32); km.aad = blob(32);
+    for (int enc = 0; enc < 2; enc++) for (int txn = 0; txn < 2; txn++) {
+        std::vector<std::pair<IndexType, Bytes>> blobs = {{IndexType::OFFSET, blob(10485)}, {IndexType::TIMESTAMP, blob(9000)}, {IndexType::PRODUCER_SNAPSHOT, blob(0)},
+                                                          {IndexType::LEADER_EPOCH, blob(126)}};
+        if (txn) blobs.push_back({IndexType::TRANSACTION, blob(2048)});
+        Bytes ivs = blob(12 * 4);
+        SegmentIndexesUpload up = uploadIndexes(ctx, blobs, enc != 0, enc ? &km : nullptr, enc ? ivs.data() : nullptr);
+        const int ov = enc ? 28 : 0;
+        CHECK(up.segmentIndexes.offset.position == 0 && up.segmentIndexes.offset.size == 10485 + ov);
+        CHECK(up.segmentIndexes.timestamp.position == 10485 + ov && up.segmentIndexes.producerSnapshot.size == 0);
+        CHECK(up.segmentIndexes.leaderEpoch.position == 10485 + 9000 + 2 * ov && up.segmentIndexes.transaction.has_value() == (txn != 0));
+        CHECK(up.object.size() == (size_t)(10485 + 9000 + 126 + (txn ? 2048 : 0) + ov * (3 + txn)));
+        if (enc) {                                           // bit-exact with the reference-side cipher, blob by blob
+            Bytes want(10485 + 28);
+            CHECK(ora_aesgcm_encrypt_chunk(km.dataKey.data(), ivs.data(), km.aad.data(), 32, blobs[0].second.data(), 10485, want.data()) == 0);
+            CHECK(memcmp(want.data(), up.object.data(), want.size()) == 0);
+        }
+        const SegmentIndexV1 all[] = {up.segmentIndexes.offset, up.segmentIndexes.timestamp, up.segmentIndexes.producerSnapshot, up.segmentIndexes.leaderEpoch};
+        for (int k = 0; k < 4; k++) CHECK(fetchIndexBytes(ctx, up.object, all[k], enc ? &km : nullptr) == blobs[k].second);
+        if (txn) CHECK(fetchIndexBytes(ctx, up.object, *up.segmentIndexes.transaction, enc ? &km : nullptr) == blobs[4].second);
+    }
+}
+
 // A manifest as the REFERENCE writes it: the size list compressed by libzstd (oracle), read back through the device decoder
 static void referenceManifestTests(tsgpu_ctx* ctx) {
     std::vector<int32_t> sizes;
@@ -406,6 +442,7 @@ int main(int argc, char** argv) {
         gpuChainTests(ctx);
         segmentUploadTests(ctx);
         referenceManifestTests(ctx);
+        indexFileTests(ctx);
         tsgpu_destroy(ctx);
     }
     printf("%s: %d checks, %d failures\n", failures ? "FAILED" : "OK", checks, failures);

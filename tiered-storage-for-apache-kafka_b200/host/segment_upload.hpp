@@ -226,4 +226,78 @@ private:
     RateLimitBucket* bucket;
 };
 
+// ------------------------------------------------------------------ index files
+// RemoteStorageManager.uploadIndexes / transformIndex (RemoteStorageManager.java:287-354, :455-490): every Kafka index is
+// ONE chunk (chunking disabled), encryption only; the `.indexes` object is their concatenation in the order OFFSET,
+// TIMESTAMP, PRODUCER_SNAPSHOT, LEADER_EPOCH, [TRANSACTION] and SegmentIndexesV1 records (position, size) of each
+// transformed blob.  Here the non-empty blobs of a segment ride ONE ragged AES batch (tsgpu_transform_chunks).
+enum class IndexType { OFFSET, TIMESTAMP, PRODUCER_SNAPSHOT, LEADER_EPOCH, TRANSACTION };
+inline const char* indexTypeName(IndexType t) {
+    static const char* N[] = {"OFFSET", "TIMESTAMP", "PRODUCER_SNAPSHOT", "LEADER_EPOCH", "TRANSACTION"};
+    return N[(int)t];
+}
+class SegmentIndexesV1Builder {                      // core/M/manifest/SegmentIndexesV1Builder.java:27-64
+public:
+    SegmentIndexesV1Builder& add(IndexType type, int size) {
+        if (have[(int)type]) throw IllegalStateException(std::string("Index ") + indexTypeName(type) + " is already added");
+        have[(int)type] = true; idx[(int)type] = SegmentIndexV1{currentPosition, size};
+        currentPosition += size;
+        return *this;
+    }
+    std::string indexes() const {                    // sorted by enum order, like the reference's list
+        std::string s = "[";
+        for (int t = 0; t < 5; t++) if (have[t]) { if (s.size() > 1) s += ", "; s += indexTypeName((IndexType)t); }
+        return s + "]";
+    }
+    SegmentIndexesV1 build() const {
+        int n = 0; for (bool h : have) n += h ? 1 : 0;
+        if (n < 4) throw IllegalStateException("Not enough indexes have been added; at least 4 required. Indexes included: " + indexes());
+        if (n == 4 && have[(int)IndexType::TRANSACTION]) throw IllegalStateException("OFFSET, TIMESTAMP, PRODUCER_SNAPSHOT, and LEADER_EPOCH indexes are required");
+        SegmentIndexesV1 r{idx[0], idx[1], idx[2], idx[3], std::nullopt};
+        if (have[4]) r.transaction = idx[4];
+        return r;
+    }
+private:
+    bool have[5] = {false, false, false, false, false};
+    SegmentIndexV1 idx[5] = {};
+    int currentPosition = 0;
+};
+
+struct SegmentIndexesUpload { Bytes object; SegmentIndexesV1 segmentIndexes; };
+// `blobs`: the index files in the reference's order (the transaction index may be absent); `ivs`: 12 bytes per NON-EMPTY blob.
+inline SegmentIndexesUpload uploadIndexes(tsgpu_ctx* ctx, const std::vector<std::pair<IndexType, Bytes>>& blobs, bool encryptionEnabled,
+                                          const DataKeyAndAAD* key, const uint8_t* ivs) {
+    if (!ctx) throw NullPointerException("ctx cannot be null");
+    if (encryptionEnabled && (!key || !ivs)) throw NullPointerException("cipherSupplier cannot be null");
+    SegmentIndexesV1Builder builder;
+    SegmentIndexesUpload r;
+    Bytes src; std::vector<uint32_t> lens;
+    for (auto& b : blobs) if (!b.second.empty()) { src.insert(src.end(), b.second.begin(), b.second.end()); lens.push_back((uint32_t)b.second.size()); }
+    std::vector<uint32_t> tsz(lens.size());
+    if (encryptionEnabled && !lens.empty()) {
+        r.object.resize(src.size() + 28 * lens.size());
+        const int rc = tsgpu_transform_chunks(ctx, TSGPU_FLAG_AES, src.data(), lens.data(), (uint32_t)lens.size(), key->dataKey.data(), key->aad.data(),
+                                              (uint32_t)key->aad.size(), ivs, r.object.data(), r.object.size(), tsz.data());
+        if (rc) throw std::runtime_error(tsgpu_last_error());
+    } else { r.object = src; tsz = lens; }
+    size_t k = 0;
+    for (auto& b : blobs) builder.add(b.first, b.second.empty() ? 0 : (int)tsz[k++]);     // transformIndex: size 0 -> empty stream, size 0
+    r.segmentIndexes = builder.build();
+    return r;
+}
+// RemoteStorageManager.fetchIndexBytes (:624-652): the index's transformed range of the `.indexes` object, decrypted.
+inline Bytes fetchIndexBytes(tsgpu_ctx* ctx, const Bytes& indexesObject, const SegmentIndexV1& index, const DataKeyAndAAD* decryptWith) {
+    if (index.size == 0) return Bytes();
+    if ((size_t)index.position + (size_t)index.size > indexesObject.size()) throw std::runtime_error("Error fetching index from remote storage");
+    const uint8_t* p = indexesObject.data() + index.position;
+    if (!decryptWith) return Bytes(p, p + index.size);
+    const uint32_t t = (uint32_t)index.size;
+    Bytes out((size_t)index.size + 64); uint32_t osz = 0;
+    const int rc = tsgpu_detransform(ctx, TSGPU_FLAG_AES, p, t, &t, 1, decryptWith->dataKey.data(), decryptWith->aad.data(), (uint32_t)decryptWith->aad.size(),
+                                     out.data(), out.size(), &osz);
+    if (rc) throw std::runtime_error(std::string("Error reading de-transformed index bytes: ") + tsgpu_last_error());
+    out.resize(osz);
+    return out;
+}
+
 }  // namespace tieredstorage
