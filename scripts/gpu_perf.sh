@@ -1,5 +1,6 @@
 # quick perf probe: correctness subset + kernel breakdown (no e2e / cpu arms)
 set -x
+TSGPU_TEST_EXPERIMENTAL=1 python -m pytest tests/test_zz_gpu_experimental.py -m gpu -q 2>&1 | tail -3     # off-by-default variants
 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "zstd or full_pipeline or grid or ranged" 2>&1 | tail -4
 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
 import sys, json

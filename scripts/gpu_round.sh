@@ -2,6 +2,7 @@
 set -x
 R=${1:-r01}
 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
+TSGPU_TEST_EXPERIMENTAL=1 python -m pytest tests/test_zz_gpu_experimental.py -m gpu -q 2>&1 | tail -5     # off-by-default variants
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_${R}_zstdaes_K.json 2> gpurun_out/bench_${R}.err; tail -c 1200 gpurun_out/bench_${R}_zstdaes_K.json
 python bench.py --corpus R --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${R}_zstdaes_R.json 2>/dev/null
 python bench.py --workload aes --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${R}_aes_K.json 2>/dev/null

@@ -1,7 +1,15 @@
-"""Variants that are off by default and have not been timed yet (they sort last on purpose): the two-launch compressor
-(TSGPU_ENC_SPLIT=1) must produce frames the oracle reads and this library's fetch side reads."""
+"""Variants that are off by default and have not been timed yet: the two-launch compressor (TSGPU_ENC_SPLIT=1, DESIGN.md
+§4.2) and the parallel general decode path (TSGPU_DEC_PARALLEL=1, §4.3).  They have only ever run on the emulator, so their
+B200 tests are opt-in (TSGPU_TEST_EXPERIMENTAL=1; `scripts/gpu_round.sh` sets it) until a GPU run has seen them pass —
+an unverified variant must not be able to turn the default suite red.  The key-table test below is default behaviour and
+always runs."""
+import os
+
 import numpy as np
 import pytest
+
+experimental = pytest.mark.skipif(os.environ.get("TSGPU_TEST_EXPERIMENTAL", "") != "1",
+                                  reason="opt-in: variant not yet verified on a GPU (set TSGPU_TEST_EXPERIMENTAL=1)")
 
 from oracle import oracle as ora
 import tsgpu
@@ -11,6 +19,7 @@ Z, A = tsgpu.FLAG_ZSTD, tsgpu.FLAG_AES
 
 
 @pytest.mark.gpu
+@experimental
 def test_gpu_two_launch_compressor(monkeypatch):
     monkeypatch.setenv("TSGPU_ENC_SPLIT", "1")
     ctx = tsgpu.Context(max_chunk_bytes=1 << 20, max_batch=8)
@@ -51,6 +60,7 @@ def test_gpu_key_tables_follow_the_key_across_calls():
 
 
 @pytest.mark.gpu
+@experimental
 def test_gpu_parallel_general_path(monkeypatch):
     # TSGPU_DEC_PARALLEL=1: libzstd-written frames, entropy stage per block in parallel + execution per frame
     monkeypatch.setenv("TSGPU_DEC_PARALLEL", "1")
