@@ -35,25 +35,47 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tsgpu", choices=["tsgpu", "reference"])
-    ap.add_argument("--workload", default="zstd+aes", choices=["zstd+aes", "aes", "zstd"])
+    ap.add_argument("--workload", default="zstd+aes", choices=["zstd+aes", "aes", "zstd", "none"])
     ap.add_argument("--corpus", default="K", choices=["K", "R", "Z"])
     ap.add_argument("--segment-mib", type=int, default=1024)
     ap.add_argument("--chunk-mib", type=int, default=4)
     ap.add_argument("--cpu-sample-mib", type=int, default=0, help="0 = auto (aim for ~10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--direction", default="transform", choices=["transform", "fetch"],
+                    help="fetch = BASELINE configs[4]: ranged fetchLogSegment, 16 MiB windows of a 1 GiB segment")
+    ap.add_argument("--frames", default="own", choices=["own", "libzstd"],
+                    help="fetch only: who wrote the segment (libzstd = the reference's writer, via the CPU arm)")
+    ap.add_argument("--window-mib", type=int, default=16)
+    ap.add_argument("--config", type=int, default=None, choices=[0, 1, 2, 3, 4],
+                    help="shorthand for BASELINE.json configs[N] (0: 256 MiB no transform, 1: zstd, 2: aes, 3: zstd+aes, 4: ranged fetch)")
+    a = ap.parse_args()
+    if a.config is not None:
+        if a.config == 0:
+            a.workload, a.segment_mib = "none", 256
+        elif a.config == 4:
+            a.workload, a.direction = "zstd+aes", "fetch"
+        else:
+            a.workload = {1: "zstd", 2: "aes", 3: "zstd+aes"}[a.config]
+    return a
 
 
 def flags_of(workload):
-    return {"zstd+aes": 3, "aes": 2, "zstd": 1}[workload]
+    return {"zstd+aes": 3, "aes": 2, "zstd": 1, "none": 0}[workload]
+
+
+def config_index(args):
+    if args.direction == "fetch":
+        return 4
+    return {"zstd+aes": 3, "aes": 2, "zstd": 1, "none": 0}[args.workload]
 
 
 def config_of(args, n_gpus):
     return {
-        "workload": "%d MiB segment per GPU, %d MiB chunks, %s, corpus %s (BASELINE configs[%d])" % (
-            args.segment_mib, args.chunk_mib, args.workload, args.corpus,
-            {"zstd+aes": 3, "aes": 2, "zstd": 1}[args.workload]),
+        "workload": "%s%d MiB segment per GPU, %d MiB chunks, %s, corpus %s (BASELINE configs[%d])" % (
+            ("ranged fetch of %d MiB windows (%s-written frames) from a " % (args.window_mib, args.frames)) if args.direction == "fetch" else "",
+            args.segment_mib, args.chunk_mib, args.workload, args.corpus, config_index(args)),
         "segment_bytes": args.segment_mib * MIB, "chunk_bytes": args.chunk_mib * MIB,
         "transform": args.workload, "corpus": args.corpus,
         "parallelism": "segments sharded across %d GPU(s), no data-path collective" % n_gpus,
@@ -157,7 +179,13 @@ _POOL_STATE = {}
 def _pool_job(r):
     st = _POOL_STATE
     c0 = time.process_time()
-    cpu_transform_chunks(st["ora"], st["flags"], st["src"], st["cs"], st["key"], st["aad"], st["ivs"], r[0], r[1])
+    if st.get("objects") is not None:            # fetch direction: decrypt + decompress chunk by chunk (DefaultChunkManager.getChunk)
+        objs = st["objects"]
+        for v in range(r[0], r[1]):
+            t = objs[v % len(objs)]
+            st["ora"].detransform_chunks(st["flags"], t, [t.size], st["cs"], st["key"], st["aad"])
+    else:
+        cpu_transform_chunks(st["ora"], st["flags"], st["src"], st["cs"], st["key"], st["aad"], st["ivs"], r[0], r[1])
     return time.process_time() - c0
 
 
@@ -168,17 +196,23 @@ class CpuArm:
     the forked page tables before anything is timed).  Every worker gets at least `min_chunks_per_worker` chunks
     per step (the sample is passed over several times if needed) so that dispatch latency does not dominate."""
 
-    def __init__(self, args, flags, src, threads, sample_bytes, min_chunks_per_worker=1):
+    def __init__(self, args, flags, src, threads, sample_bytes, min_chunks_per_worker=1, fetch=False):
         from oracle import oracle as ora
         from tsgpu import corpus
         self.cs = args.chunk_mib * MIB
         self.nch = max(1, min(src.size, sample_bytes) // self.cs)
         key, aad, ivs = corpus.fixed_key_material(self.nch)
+        objects = None
+        if fetch:                                # the reference-written chunks to be fetched (produced before anything is timed)
+            objects = []
+            for i in range(self.nch):
+                t, _ = ora.transform_segment(flags, src[i * self.cs:(i + 1) * self.cs], self.cs, key, aad, ivs[12 * i:12 * i + 12])
+                objects.append(np.array(t, copy=True))
         self.rounds = max(1, -(-min_chunks_per_worker * threads // self.nch)) if threads > 1 else 1
         total = self.nch * self.rounds
         per = (total + threads - 1) // threads
         self.ranges = [(k * per, min(total, (k + 1) * per)) for k in range(threads) if k * per < total]
-        _POOL_STATE.update(ora=ora, flags=flags, src=src[:self.nch * self.cs], cs=self.cs, key=key, aad=aad, ivs=ivs)
+        _POOL_STATE.update(ora=ora, flags=flags, src=src[:self.nch * self.cs], cs=self.cs, key=key, aad=aad, ivs=ivs, objects=objects)
         self.pool = None
         self.cpu_seconds = 0.0
         if len(self.ranges) > 1:
@@ -218,7 +252,7 @@ def main_reference(args):
     seg_args = argparse.Namespace(**vars(args))
     seg_args.segment_mib = sample_mib
     src = make_segment(seg_args, 0)
-    arm = CpuArm(args, flags, src, threads, src.size, min_chunks_per_worker=8)
+    arm = CpuArm(args, flags, src, threads, src.size, min_chunks_per_worker=8, fetch=args.direction == "fetch")
     for _ in range(max(1, args.warmup)):
         arm.step()
     arm.cpu_seconds = 0.0
@@ -232,7 +266,8 @@ def main_reference(args):
     arm.close()
     val = b_tot / GIB / t_tot
     line = {
-        "metric": METRIC, "value": val, "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "metric": "ranged_fetch_GiB_per_s" if args.direction == "fetch" else METRIC, "value": val, "unit": "GiB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "impl": "reference", "config": config_of(args, args.gpus),
         "cpu_baseline": {"value": val, "unit": "GiB/s", "cores": used, "kind": "port",
@@ -245,6 +280,213 @@ def main_reference(args):
     }
     print(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------------------------------ fetch direction (configs[4])
+def fetch_windows(nch, wch):
+    """first chunk of each window: start, middle, end of the segment, then a sweep"""
+    firsts = [0, nch // 2, nch - wch] + [(k * 37) % (nch - wch + 1) for k in range(1, 14)]
+    return firsts
+
+
+def make_object(args, flags, src_np, ctx_host, key, aad, ivs):
+    """the uploaded .log object of the segment and its chunk sizes, written by this library or by the reference's
+    writer (libzstd level 3 + JCE stand-in: the CPU arm — used only to PRODUCE a reference-written object, never timed)"""
+    cs = args.chunk_mib * MIB
+    if args.frames == "own":
+        return ctx_host.transform(flags, src_np, cs, key, aad, ivs)
+    from oracle import oracle as ora
+    return ora.transform_segment(flags, src_np, cs, key, aad, ivs)
+
+
+def main_fetch(args):
+    """BASELINE configs[4]: ranged fetchLogSegment — decrypt + decompress the chunks covering a 16 MiB window of a 1 GiB
+    segment.  A step = one window.  value: transformed chunks resident in HBM (detransform_device, CUDA events);
+    e2e: tsgpu_detransform with host buffers (H2D of the transformed chunks, kernels, D2H of the window)."""
+    import torch
+    import torch.distributed as dist
+    import tsgpu
+    from tsgpu import corpus
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl tsgpu needs a GPU: libtsgpu has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    bind_to_gpu_numa_node(torch, local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    flags = flags_of(args.workload)
+    seg, cs = args.segment_mib * MIB, args.chunk_mib * MIB
+    nch, wch = seg // cs, max(1, args.window_mib // args.chunk_mib)
+    key, aad, ivs = corpus.fixed_key_material(nch)
+    src_np = make_segment(args, rank)
+    hctx = tsgpu.Context(max_chunk_bytes=cs, max_batch=max(wch + 1, 4), devices=[local])
+    obj, tsz = make_object(args, flags, src_np, hctx, key, aad, ivs)
+    pos = np.concatenate([[0], np.cumsum(np.asarray(tsz, dtype=np.int64))])
+    ctx = tsgpu.Context(max_chunk_bytes=cs, max_batch=wch, devices=[local])
+    stride = ctx.slot_stride(flags, cs)
+    firsts = fetch_windows(nch, wch)
+    # device-resident: every window's chunks sit in slots
+    wins = []
+    for f in firsts:
+        slots = np.zeros(wch * stride, dtype=np.uint8)
+        for k in range(wch):
+            slots[k * stride + 4:k * stride + 4 + tsz[f + k]] = obj[pos[f + k]:pos[f + k + 1]]
+        wins.append((torch.from_numpy(slots).to(dev), torch.tensor(tsz[f:f + wch], dtype=torch.int32, device=dev)))
+    d_dst = torch.zeros(wch * cs, dtype=torch.uint8, device=dev)
+    d_osz = torch.zeros(wch, dtype=torch.int32, device=dev); d_st = torch.zeros(wch, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 * MIB, dtype=torch.uint8, device=dev)      # > 126 MB L2: written between timed windows
+
+    def step_device(i):
+        d_slots, d_sizes = wins[i % len(wins)]
+        ctx.detransform_device(flags, d_slots.data_ptr(), stride, d_sizes.data_ptr(), wch, cs, key, aad, d_dst.data_ptr(),
+                               d_osz.data_ptr(), d_st.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    l0 = ctx.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    sampler.begin()
+    ok = True
+    for i in range(args.steps):
+        flush.fill_(i & 255)                                              # L2 flush, outside the per-step events
+        evs[i][0].record()
+        step_device(i)
+        evs[i][1].record()
+        evs[i][1].synchronize()
+        f = firsts[i % len(firsts)]
+        ok = ok and int(d_st.abs().sum().item()) == 0
+    barrier()
+    sampler.end()
+    ok = ok and bool(np.array_equal(d_dst.cpu().numpy(), src_np[f * cs:(f + wch) * cs]))      # last window, checked after timing
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    win_bytes = wch * cs
+    value = world * win_bytes * args.steps / GIB / (ms_max / 1000.0)
+
+    ctx.profile_enable(True)
+    step_device(0)
+    rep = ctx.profile_report()
+    ctx.profile_enable(False)
+    kernels = {k: {"launches": v["launches"], "ms": v["ms"]} for k, v in rep.items()} if rep else None
+    roofline = None
+    if rep:
+        name, rec = max(rep.items(), key=lambda kv: kv[1]["ms"])
+        ms_k = rec["ms"] / rec["launches"]
+        tbytes = int(sum(tsz[firsts[0]:firsts[0] + wch]))
+        alg = tbytes + win_bytes                                          # transformed in + original out (SURVEY.md §8d)
+        peak, how = load_peaks()
+        roofline = {"bound": "hbm", "kernel": name, "achieved": alg / 1e9 / (ms_k / 1000.0), "peak": peak, "unit": "GB/s",
+                    "frac": alg / 1e9 / (ms_k / 1000.0) / peak, "traffic": None, "peak_source": how,
+                    "algorithmic_bytes_per_launch": alg, "kernel_ms": ms_k}
+
+    e2e = None
+    if not args.no_e2e:
+        h_out = torch.empty(win_bytes, dtype=torch.uint8).pin_memory()
+        h_in = torch.empty(int(max(pos[f + wch] - pos[f] for f in firsts)) + 64, dtype=torch.uint8).pin_memory()
+        out_np, in_np = h_out.numpy(), h_in.numpy()
+        def step_host(i):
+            f = firsts[i % len(firsts)]
+            n = int(pos[f + wch] - pos[f])
+            in_np[:n] = obj[pos[f]:pos[f + wch]]                          # the bytes of the ranged GET, landing in pinned memory
+            hctx.detransform(flags, in_np[:n], tsz[f:f + wch], win_bytes, key, aad, dst=out_np)
+            return f, n
+        for i in range(max(1, args.warmup)):
+            step_host(i)
+        barrier()
+        h2d = 0
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            f, n = step_host(i); h2d += n
+        dt = time.perf_counter() - t0
+        ok = ok and bool(np.array_equal(out_np, src_np[f * cs:(f + wch) * cs]))
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * win_bytes * args.steps / GIB / float(tt.item()), "unit": "GiB/s",
+               "ms_per_window": 1000.0 * float(tt.item()) / args.steps,
+               "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": win_bytes,
+               "timer": "host wall clock around tsgpu_detransform (it synchronises internally), max over ranks"}
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as ora
+        f = firsts[0]
+        part = obj[pos[f]:pos[f + wch]]
+        ora.detransform_chunks(flags, part, tsz[f:f + wch], win_bytes, key, aad)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 5.0:
+            ora.detransform_chunks(flags, part, tsz[f:f + wch], win_bytes, key, aad); reps += 1
+        dtc = (time.perf_counter() - t0) / reps
+        cpu = {"value": win_bytes / GIB / dtc, "unit": "GiB/s", "cores": 1, "kind": "port", "ms_per_window": 1000.0 * dtc,
+               "sample": "%d x one %d MiB window, chunk-sequential on 1 thread like DefaultChunkManager.getChunk; libzstd %s + "
+                         "OpenSSL EVP standing in for zstd-jni + SunJCE" % (reps, args.window_mib, ora.lib().ora_zstd_version().decode())}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "ranged_fetch_GiB_per_s", "value": value, "unit": "GiB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": dict(config_of(args, world),
+                l2_policy="256 MiB written between timed windows (L2 flush), outside the per-window events"),
+            "frames_written_by": args.frames, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "kernels_ms_per_step": kernels, "verified": {"windows_bit_exact": bool(ok)}}))
+    if not ok:
+        raise SystemExit("bench.py: a fetched window differs from the segment")
+    ctx.close(); hctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ configs[0]: ChunkIndex plumbing
+def main_plumbing(args):
+    """BASELINE configs[0]: 256 MiB segment, no compression / encryption (TransformFinisher's no-transform fast path,
+    TransformFinisher.java:124-140): the bytes pass through unchanged, the fixed ChunkIndex is computed arithmetically and
+    serialised.  The reference runs this on the CPU and so does the library (flags == 0 never touches the GPU), so this
+    line has gpu_launches 0 by design; it exists so that every BASELINE config has a driver-runnable line."""
+    import tsgpu
+    from tsgpu import binding
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    seg, cs = args.segment_mib * MIB, args.chunk_mib * MIB
+    src = make_segment(args, 0)
+    ctx = tsgpu.Context(max_chunk_bytes=cs, max_batch=4)
+    dst = np.empty(seg + 64, dtype=np.uint8)
+    def step():
+        out, sizes = ctx.transform(0, src, cs, dst=dst)
+        js = binding.chunk_index_json(cs, seg, cs, sizes[-1])
+        return out, sizes, js
+    for _ in range(max(1, args.warmup)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out, sizes, js = step()
+    dt = time.perf_counter() - t0
+    ok = bool(np.array_equal(out, src)) and js == ('{"type":"fixed","originalChunkSize":%d,"originalFileSize":%d,'
+                                                   '"transformedChunkSize":%d,"finalTransformedChunkSize":%d}' % (cs, seg, cs, cs))
+    v = seg * args.steps / GIB / dt
+    print(json.dumps({"metric": METRIC, "value": v, "unit": "GiB/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "u8", "data": "synthetic", "config": config_of(args, 1),
+                      "e2e": {"value": v, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0, "note": "no-transform fast path: host memcpy + ChunkIndex arithmetic, no GPU work by design",
+                      "chunk_index": js, "verified": {"bytes_unchanged_and_index_json": ok}}))
+    ctx.close()
+    return 0 if ok else 1
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -333,6 +575,24 @@ def main_tsgpu(args):
     sizes = d_sizes.cpu().numpy().astype(np.int64)
     transformed_total = int(sizes.sum())
 
+    # ---- verify what was timed (after the timed region): the slots the LAST timed step left behind go back through the
+    # device detransform and must equal the segment byte for byte; a seeded sample of chunks is also decoded by the CPU
+    # chain (libzstd + OpenSSL) in the cpu_baseline leg below
+    verified = None
+    if not args.no_verify:
+        d_back = torch.zeros(seg, dtype=torch.uint8, device=dev)
+        d_osz = torch.zeros(nch, dtype=torch.int32, device=dev)
+        d_stat = torch.full((nch,), 9, dtype=torch.int32, device=dev)
+        ctx.detransform_device(flags, d_slots.data_ptr(), stride, d_sizes.data_ptr(), nch, cs, key, aad, d_back.data_ptr(),
+                               d_osz.data_ptr(), d_stat.data_ptr(), stream)
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(d_back, d_src)) and int(d_stat.abs().sum().item()) == 0 and \
+            d_osz.cpu().numpy().tolist() == [min(cs, seg - i * cs) for i in range(nch)]
+        verified = {"device_roundtrip_whole_segment": ok}
+        del d_back
+        if not ok:
+            raise SystemExit("bench.py: the timed step's output does not detransform back to the input")
+
     # ---- roofline: per-kernel CUDA-event timing, separate steps so the events do not perturb `value`
     roofline, kernels = None, None
     ctx.profile_enable(True)
@@ -361,10 +621,15 @@ def main_tsgpu(args):
         if os.path.exists(tpath):
             try:
                 traffic = json.load(open(tpath)).get(name)
+                if isinstance(traffic, dict):
+                    traffic = traffic.get("bytes")
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": how,
+                    "traffic_source": None if traffic is None else
+                    "STATIC: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture "
+                    "named in profiles/traffic.json (not measured in this run)",
                     "algorithmic_bytes_per_launch": alg, "kernel_ms": ms_k,
                     "note": "integer/LDS-bound kernels: see DESIGN.md for the ALU/shared-memory ceilings"}
 
@@ -407,7 +672,33 @@ def main_tsgpu(args):
         arm = CpuArm(args, flags, src_np, 1, sample)
         nbytes, dt = arm.step()
         v = nbytes / GIB / dt
-        cpu = {"value": v, "unit": "GiB/s", "cores": 1, "kind": "port",
+        # Kafka's copier pool: T = min(nproc, 10) segments in flight (README.md:221 of the reference), one chain per thread
+        T = min(os.cpu_count() or 1, 10)
+        pool = None
+        if T > 1:
+            parm = CpuArm(args, flags, src_np, T, min(seg, 8 * T * cs), min_chunks_per_worker=4)
+            parm.step()
+            parm.cpu_seconds = 0.0
+            pb2, pdt2 = parm.step()
+            pool = {"value": pb2 / GIB / pdt2, "unit": "GiB/s", "cores": parm.cores,
+                    "effective_cores": round(parm.cpu_seconds / pdt2, 1) if pdt2 > 0 else None,
+                    "sample": "T = min(nproc, 10) = %d worker processes, %d MiB per step" % (parm.cores, pb2 // MIB)}
+            parm.close()
+        if verified is not None:
+            # the checker: a seeded sample of the last timed step's chunks decoded by libzstd + OpenSSL
+            rng = np.random.default_rng(11)
+            pick = sorted(set([0, nch - 1] + rng.choice(nch, min(nch, 6), replace=False).tolist()))
+            slots_np = d_slots.cpu().numpy().reshape(nch, stride)
+            sz_now = d_sizes.cpu().numpy().astype(np.int64)      # the slots as they are now (profiling steps re-ran the path)
+            good = True
+            for i in pick:
+                t = slots_np[i, 4:4 + int(sz_now[i])]
+                back, osz = ora.detransform_chunks(flags, t, [int(sz_now[i])], cs, key, aad)
+                good = good and np.array_equal(back, src_np[i * cs:(i + 1) * cs])
+            verified["cpu_chain_decodes_sample_chunks"] = {"chunks": pick, "ok": bool(good)}
+            if not good:
+                raise SystemExit("bench.py: libzstd + OpenSSL do not decode the timed step's output")
+        cpu = {"value": v, "unit": "GiB/s", "cores": 1, "kind": "port", "copier_pool": pool,
                "sample": "first %d MiB of the same segment, chunk-sequential on 1 thread (the reference's per-segment "
                          "pipeline is single-threaded); libzstd %s level 3 + OpenSSL EVP AES-256-GCM standing in for "
                          "zstd-jni 1.5.6-9 + SunJCE; %.1f s" % (nbytes // MIB, ora.lib().ora_zstd_version().decode(), dt)}
@@ -420,7 +711,7 @@ def main_tsgpu(args):
             "compression_ratio": seg / max(1, transformed_total - (28 * nch if flags & 2 else 0)) if flags & 1 else None,
             "transformed_bytes_per_segment": transformed_total,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "cpu_baseline": cpu, "kernels_ms_per_step": kernels,
+            "cpu_baseline": cpu, "kernels_ms_per_step": kernels, "verified": verified,
         }
         print(json.dumps(line))
     ctx.close()
@@ -431,4 +722,8 @@ def main_tsgpu(args):
 
 if __name__ == "__main__":
     a = parse()
-    sys.exit(main_reference(a) if a.impl == "reference" else main_tsgpu(a))
+    if a.impl == "reference":
+        sys.exit(main_reference(a))
+    if a.workload == "none":
+        sys.exit(main_plumbing(a))
+    sys.exit(main_fetch(a) if a.direction == "fetch" else main_tsgpu(a))

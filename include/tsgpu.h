@@ -123,7 +123,11 @@ int tsgpu_detransform(tsgpu_ctx* ctx, uint32_t flags,
  *   transformed side  one slot per chunk, slot i at i * slot_stride; the chunk's bytes start at
  *                     slot + TSGPU_SLOT_HEAD so that the ciphertext / frame body is 16-byte aligned
  * All pointers are device pointers except key/aad/ivs (host).  `stream` is a cudaStream_t (0 = default).
- * The calls enqueue work and return without synchronising; sizes/status land in device memory.
+ * The calls enqueue work and return without synchronising; sizes/status land in device memory.  Consecutive device
+ * calls on one context may use different streams: the library orders each call behind the previous one with events
+ * (they share one descriptor block and scratch arena per device), so they execute back to back, never concurrently.
+ * Sizes read from device memory are untrusted: a chunk larger than its slot / destination is reported in d_status
+ * (1 for the AES stage, 2 for zstd) and nothing is written for it.
  * --------------------------------------------------------------------------------------------------------- */
 #define TSGPU_SLOT_HEAD 4
 uint64_t tsgpu_slot_stride(uint32_t flags, uint32_t chunk_size);
@@ -148,7 +152,8 @@ int tsgpu_profile_report(tsgpu_ctx* ctx, char* out, uint32_t* out_len);
 /* ---------------------------------------------------------------------------------------------------------
  * ChunkIndex plumbing (host side; tiny, integer only).
  *   tsgpu_chunk_positions      exclusive prefix sums of AbstractChunkIndex.materializeChunks (AbstractChunkIndex.java:52-72);
- *                              runs the warp-shuffle scan kernel (K5) on device 0 of the context
+ *                              runs the warp-shuffle scan kernel (K5) on device 0 of the context.  `positions` receives
+ *                              n + 1 values: positions[i] = start of chunk i, positions[n] = total — allocate n + 1 entries
  *   tsgpu_chunk_sizes_encode / decode   ChunkSizesBinaryCodec.encode/decode (ChunkSizesBinaryCodec.java:104-202)
  *   tsgpu_transformed_chunks_serialize / deserialize   TransformedChunksSerializer / Deserializer (:30-52 / :36-49)
  *   tsgpu_chunk_index_json     Jackson form of Fixed/VariableSizeChunkIndex (ChunkIndexSerializationTest.java:63-74)

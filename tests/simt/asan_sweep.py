@@ -47,4 +47,19 @@ try:
 except tsgpu.TsgpuError:
     pass
 c.close()
+# chunks larger than the reading context's chunk size — as a tampered manifest or a config mismatch
+# would present them — must be refused before the GCM kernel writes plaintext anywhere (AES only: 4 x 65856 B plaintexts
+# into a context sized for 65536 B chunks used to overrun d_orig by 592 B).
+big = tsgpu.Context(max_chunk_bytes=1 << 17, max_batch=4, lib_path=lib)
+small = tsgpu.Context(max_chunk_bytes=65536, max_batch=4, lib_path=lib)
+src = rng.integers(0, 256, 4 * 65856, dtype=np.uint8)
+out, sizes = big.transform(2, src, 65856, key, aad, rng.bytes(48))
+for flags in (2, 3):
+    try:
+        small.detransform(flags, out, sizes, src.size + 4096, key, aad)
+        raise SystemExit("oversize chunk accepted (flags %d)" % flags)
+    except tsgpu.TsgpuError as e:
+        # AES only: refused up front; AES+zstd: the decrypted bytes still fit a frame slot but are no zstd frame
+        assert e.code == (tsgpu.binding.E_ARG if flags == 2 else tsgpu.binding.E_CORRUPT), e
+big.close(); small.close()
 print("sanitizer sweep ok", len(cases))

@@ -63,6 +63,7 @@ struct Block {
     int cur = 0;
     int alive = 0;
     int bar_count = 0, bar_gen = 0;
+    int or_acc[3] = {0, 0, 0}, or_gen = 0;
     uint3 bid{};
     dim3 bdim, gdim;
     uint8_t* dyn_smem = nullptr;
@@ -110,6 +111,14 @@ template <class T> inline T xchg(T v, int src) {
 #define warpSize 32
 
 static inline void __syncthreads() { simt::block_barrier(); }
+static inline int __syncthreads_or(int pred) {
+    simt::Block& b = *simt::g_blk;
+    const int my = b.bar_gen, k = b.or_gen;          // or_gen moves only when an or-barrier completes
+    if (pred) b.or_acc[k % 3] = 1;
+    if (++b.bar_count >= b.alive) { b.bar_count = 0; b.or_acc[(k + 1) % 3] = 0; b.or_gen++; b.bar_gen++; }
+    else while (b.bar_gen == my) simt::yield();
+    return b.or_acc[k % 3];
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_barrier(); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}

@@ -202,6 +202,8 @@ struct GcmBatch {
     uint4* partials; uint32_t max_ranges;
     uint32_t* status;            // DEC: 0 ok, 1 tag mismatch / malformed
     uint32_t n_chunks;
+    uint32_t out_cap;            // DEC: plaintext bytes the destination holds per chunk; a longer chunk is rejected
+                                 //      (status 1) BEFORE anything is written — sizes may come from a tampered manifest
 };
 
 __device__ __forceinline__ uint32_t ld_le32_bytes(const uint8_t* p) {
@@ -229,6 +231,7 @@ gcm_main_kernel(const __grid_constant__ Aes256RoundKeys rk, const GcmKeyCtx* __r
     const uint32_t m = (n + 15) >> 4;
     const uint32_t b0 = range * GH_RANGE_BLOCKS;
     if (b0 >= m) return;                                   // uniform for the CTA
+    if (!ENC && n > B.out_cap) return;                     // oversize chunk: finalize reports it, nothing is written
     const uint32_t b1 = min(b0 + GH_RANGE_BLOCKS, m);
 
 #if TS_DEVICE_ASM
@@ -309,7 +312,7 @@ gcm_finalize_kernel(const __grid_constant__ Aes256RoundKeys rk, const GcmKeyCtx*
     const uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (chunk >= B.n_chunks) return;                       // whole warp leaves together
     const uint32_t len = B.in_len[chunk];
-    const bool malformed = !ENC && len < GCM_IV + GCM_TAG;
+    const bool malformed = !ENC && (len < GCM_IV + GCM_TAG || len - (GCM_IV + GCM_TAG) > B.out_cap);
     const uint32_t n = ENC ? len : (malformed ? 0 : len - (GCM_IV + GCM_TAG));
     const uint32_t m = (n + 15) >> 4;
     const uint32_t nr = (m + GH_RANGE_BLOCKS - 1) / GH_RANGE_BLOCKS;

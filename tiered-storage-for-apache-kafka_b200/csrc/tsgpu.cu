@@ -56,6 +56,8 @@ struct Work {
     int device = 0;
     rt::stream_t stream{}, out_stream{};   // out_stream: copies of finished chunks back to the host
     rt::event_t ev_sizes{}, ev_done{};
+    rt::event_t ev_dev_desc{}, ev_dev_done{};   // device API: descriptor upload of / end of the previous call on this slot
+    bool dev_pending = false;
     bool out_pending = false;              // a copy-out on out_stream still reads this slot's final buffer
     bool busy = false, ready = false;
     Aes256RoundKeys key_rk{};      // the key this slot's GcmKeyCtx (H powers, Shoup table) was built for
@@ -115,6 +117,8 @@ static int work_init_impl(tsgpu_ctx* c, Work& w, int device) {
     RT(rt::stream_create(&w.out_stream));
     RT(rt::event_create(&w.ev_sizes));
     RT(rt::event_create(&w.ev_done));
+    RT(rt::event_create(&w.ev_dev_desc));
+    RT(rt::event_create(&w.ev_dev_done));
     const uint64_t nb = c->max_batch;
     RT(rt::malloc_device((void**)&w.d_orig, nb * align_up(c->chunk_cap, 16) + 256));
     RT(rt::malloc_device((void**)&w.d_frames, nb * c->frame_stride + 256));
@@ -146,6 +150,7 @@ static void work_free(Work& w) {
     zstd_enc_scratch_free(w.zenc); zstd_dec_scratch_free(w.zdec);
     memset(&w.key_rk, 0, sizeof w.key_rk); w.key_valid = false;
     rt::event_destroy(w.ev_sizes); rt::event_destroy(w.ev_done);
+    rt::event_destroy(w.ev_dev_desc); rt::event_destroy(w.ev_dev_done);
     rt::stream_destroy(w.stream); rt::stream_destroy(w.out_stream);
 }
 
@@ -195,9 +200,10 @@ extern "C" int tsgpu_create(const int* device_ids, int n_devices, uint32_t max_c
     }
     for (size_t l = 0; l < ids.size(); l++) {           // opt in to > 48 KiB dynamic shared memory, per device
         rt::set_device(ids[l]);
-        RT(rt::allow_smem(gcm_main_kernel<true>, GCM_SMEM_BYTES));
-        RT(rt::allow_smem(gcm_main_kernel<false>, GCM_SMEM_BYTES));
-        const char* e = zstd_kernels_configure();
+        const char* e = rt::allow_smem(gcm_main_kernel<true>, GCM_SMEM_BYTES);
+        if (!e) e = rt::allow_smem(gcm_main_kernel<false>, GCM_SMEM_BYTES);
+        if (e) { tsgpu_destroy(c); return fail(TSGPU_E_CUDA, "gcm kernel attributes: %s", e); }
+        e = zstd_kernels_configure();
         if (e) { tsgpu_destroy(c); return fail(TSGPU_E_CUDA, "zstd kernel attributes: %s", e); }
     }
     *out = c;
@@ -225,7 +231,7 @@ static int gcm_stage(tsgpu_ctx* c, Work& w, rt::stream_t st, const Aes256RoundKe
                      const uint8_t* in_base, const uint64_t* d_in_off, const uint32_t* d_in_len,
                      uint8_t* out_base, const uint64_t* d_out_off, uint32_t* d_out_len,
                      const uint8_t* d_ivs, const uint8_t* d_aad, uint32_t aad_len, uint32_t* d_status,
-                     uint32_t n_chunks, uint32_t max_payload, uint4* d_partials, uint32_t max_ranges) {
+                     uint32_t n_chunks, uint32_t max_payload, uint4* d_partials, uint32_t max_ranges, uint32_t out_cap = 0xffffffffu) {
     if (!key_ready) {
         TS_LAUNCH_P(c->prof, "gcm_key_setup", gcm_key_setup_kernel, dim3(1), dim3(GH_T), 0, st, rk, w.d_keyctx);
         CHECK_LAUNCH("gcm_key_setup_kernel");
@@ -234,7 +240,7 @@ static int gcm_stage(tsgpu_ctx* c, Work& w, rt::stream_t st, const Aes256RoundKe
     B.in_base = in_base; B.in_off = d_in_off; B.in_len = d_in_len;
     B.out_base = out_base; B.out_off = d_out_off; B.out_len = d_out_len;
     B.ivs = d_ivs; B.aad = d_aad; B.aad_len = aad_len;
-    B.partials = d_partials; B.max_ranges = max_ranges; B.status = d_status; B.n_chunks = n_chunks;
+    B.partials = d_partials; B.max_ranges = max_ranges; B.status = d_status; B.n_chunks = n_chunks; B.out_cap = out_cap;
     uint32_t ranges = (uint32_t)(((uint64_t)max_payload + 15) / 16 + GH_RANGE_BLOCKS - 1) / GH_RANGE_BLOCKS;
     if (ranges > max_ranges) return fail(TSGPU_E_ARG, "chunk too large for this context");
     if (ranges) {
@@ -332,7 +338,7 @@ static int transform_args_ok(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, u
 
 extern "C" int tsgpu_transform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, uint64_t src_len, uint32_t chunk_size,
                                const uint8_t key[32], const uint8_t* aad, uint32_t aad_len, const uint8_t* ivs,
-                               uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes, uint32_t* n_chunks) {
+                               uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes, uint32_t* n_chunks) try {
     int rc = transform_args_ok(c, flags, src, src_len, key, aad, aad_len, ivs, transformed_sizes, n_chunks);
     if (rc) return rc;
     // BaseTransformChunkEnumeration: originalChunkSize 0 disables chunking (one chunk = whole stream)
@@ -346,14 +352,14 @@ extern "C" int tsgpu_transform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src,
     std::vector<uint32_t> len(n64);
     for (uint64_t i = 0; i < n64; i++) { off[i] = i * cs; len[i] = (uint32_t)std::min<uint64_t>(cs, src_len - i * cs); }
     return transform_common(c, flags, src, src_len, off, len, cs, key, aad, aad_len, ivs, dst, dst_cap, transformed_sizes, n_chunks);
-}
+} catch (const std::bad_alloc&) { return fail(TSGPU_E_NOMEM, "out of memory"); }
 
 // Ragged variant: chunk i is the next chunk_lens[i] bytes of src.  This is what RemoteStorageManager.transformIndex
 // (RemoteStorageManager.java:455-490) needs: every Kafka index file is ONE chunk (chunking disabled), AES only, and the
 // five of them ride in a single batch.
 extern "C" int tsgpu_transform_chunks(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, const uint32_t* chunk_lens, uint32_t n,
                                       const uint8_t key[32], const uint8_t* aad, uint32_t aad_len, const uint8_t* ivs,
-                                      uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes) {
+                                      uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes) try {
     uint32_t cap = n;
     if (n && !chunk_lens) return fail(TSGPU_E_ARG, "chunk_lens cannot be null");
     uint64_t total = 0; uint32_t mx = 0;
@@ -368,7 +374,7 @@ extern "C" int tsgpu_transform_chunks(tsgpu_ctx* c, uint32_t flags, const uint8_
     if (n == 0) return TSGPU_OK;
     if (mx > c->chunk_cap) return fail(TSGPU_E_ARG, "chunk size %u exceeds the context's max_chunk_bytes %u", mx, c->chunk_cap);
     return transform_common(c, flags, src, total, off, len, mx, key, aad, aad_len, ivs, dst, dst_cap, transformed_sizes, &cap);
-}
+} catch (const std::bad_alloc&) { return fail(TSGPU_E_NOMEM, "out of memory"); }
 
 static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, uint64_t src_len, const std::vector<uint64_t>& off,
                             const std::vector<uint32_t>& len, uint32_t cs, const uint8_t key[32], const uint8_t* aad, uint32_t aad_len,
@@ -451,7 +457,13 @@ static int detransform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_
     uint32_t max_t = 0;
     for (uint32_t i = 0; i < nb; i++) {
         const uint32_t t = tsizes[c0 + i];
-        if (t > c->slot_stride - TSGPU_SLOT_HEAD - 16) return fail(TSGPU_E_ARG, "transformed chunk of %u bytes exceeds the context's capacity", t);
+        // Sizes come from a manifest, i.e. from outside: bound them per mode BEFORE any kernel writes (the GCM kernel
+        // releases plaintext into the next buffer before the tag is checked).  AES only: plaintext lands in d_orig
+        // (chunk_cap per chunk); AES+zstd: in a d_frames slot; zstd only: the frame is read in place from d_xf.
+        const uint64_t payload = (flags & TSGPU_FLAG_AES) ? (t >= 28 ? t - 28 : 0) : t;
+        const uint64_t room = (flags & TSGPU_FLAG_ZSTD) ? c->frame_stride - 16 : c->chunk_cap;
+        if (payload > room || t > c->slot_stride - TSGPU_SLOT_HEAD - 16)
+            return fail(TSGPU_E_ARG, "transformed chunk of %u bytes exceeds the context's capacity", t);
         w.hd.c_off[i] = (uint64_t)i * c->slot_stride + TSGPU_SLOT_HEAD;
         w.hd.c_len[i] = t;
         w.hd.b_off[i] = (uint64_t)i * c->frame_stride;
@@ -475,7 +487,8 @@ static int detransform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_
         w.key_rk = rk; w.key_valid = false;                  // valid again once the stage has been enqueued
         if (!z) { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }                          // d_orig is the final buffer
         int rc = gcm_stage<false>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
-                                  w.dd.status, nb, max_t, w.d_partials, w.max_ranges);
+                                  w.dd.status, nb, max_t, w.d_partials, w.max_ranges,
+                                  z ? (uint32_t)(c->frame_stride - 16) : c->chunk_cap);
         if (rc) return rc;
         w.key_valid = true;
         cur_base = ob; cur_off = oo; cur_len = ol;
@@ -497,7 +510,7 @@ static int detransform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_
 extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, uint64_t src_len,
                                  const uint32_t* transformed_sizes, uint32_t n_chunks,
                                  const uint8_t key[32], const uint8_t* aad, uint32_t aad_len,
-                                 uint8_t* dst, uint64_t dst_cap, uint32_t* original_sizes) {
+                                 uint8_t* dst, uint64_t dst_cap, uint32_t* original_sizes) try {
     if (!c) return fail(TSGPU_E_ARG, "ctx cannot be null");
     if (n_chunks == 0) return TSGPU_OK;
     if (!src) return fail(TSGPU_E_ARG, "inputStream cannot be null");
@@ -576,9 +589,22 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
         memset(dst, 0, (size_t)dst_off);
     }
     return rc;
-}
+} catch (const std::bad_alloc&) { return fail(TSGPU_E_NOMEM, "out of memory"); }
 
 // ------------------------------------------------------------------------------------------ device-resident API
+// The device API reuses slot 0's pinned descriptor block and scratch arenas.  Two events make back-to-back calls safe on
+// any streams: the host waits until the previous call's descriptor upload has left the pinned block before rewriting it,
+// and the new call's stream waits for the previous call's kernels before touching the shared scratch.
+static int dev_call_begin(Work& w, rt::stream_t st) {
+    if (w.dev_pending) { RT(rt::event_sync(w.ev_dev_desc)); RT(rt::stream_wait_event(st, w.ev_dev_done)); }
+    return TSGPU_OK;
+}
+static int dev_call_end(Work& w, rt::stream_t st) {
+    RT(rt::event_record(w.ev_dev_done, st));
+    w.dev_pending = true;
+    return TSGPU_OK;
+}
+
 static int pick_work(tsgpu_ctx* c, int device_index, Work** w) {
     if (!c) return fail(TSGPU_E_ARG, "ctx cannot be null");
     if (device_index < 0 || device_index >= (int)c->lanes.size()) return fail(TSGPU_E_ARG, "device_index %d out of range", device_index);
@@ -603,6 +629,7 @@ extern "C" int tsgpu_transform_device(tsgpu_ctx* c, int device_index, uint32_t f
     std::lock_guard<std::mutex> lock(c->mu);
     RT(rt::set_device(w.device));
     rt::stream_t st = (rt::stream_t)stream;
+    { int rb = dev_call_begin(w, st); if (rb) return rb; }
     for (uint32_t i = 0; i < nb; i++) {
         w.hd.a_off[i] = (uint64_t)i * cs;
         w.hd.a_len[i] = (uint32_t)std::min<uint64_t>(cs, src_len - (uint64_t)i * cs);
@@ -615,9 +642,10 @@ extern "C" int tsgpu_transform_device(tsgpu_ctx* c, int device_index, uint32_t f
         memcpy(w.hd.ivs, ivs, (size_t)nb * TSGPU_IV_SIZE);
         if (aad_len) memcpy(w.hd.aad, aad, aad_len);
     }
-    // NOTE: the pinned descriptor block is reused by the next call on this slot; callers of the device API
-    // serialise calls per context (bench.py does), matching the one-chain-per-thread use of the reference.
     RT(rt::h2d(w.d_desc, w.h_desc, w.desc_bytes, st));
+    RT(rt::event_record(w.ev_dev_desc, st));
+    w.dev_pending = true;                                    // from here on the next call must order itself behind this one
+    RT(rt::event_record(w.ev_dev_done, st));
     const uint8_t* cur_base = d_src; const uint64_t* cur_off = w.dd.a_off; const uint32_t* cur_len = w.dd.a_len;
     uint32_t cur_max = cs;
     if (flags & TSGPU_FLAG_ZSTD) {
@@ -635,7 +663,7 @@ extern "C" int tsgpu_transform_device(tsgpu_ctx* c, int device_index, uint32_t f
                              w.dd.ivs, w.dd.aad, aad_len, w.dd.status, nb, cur_max, w.d_partials, w.max_ranges);
         if (rc) return rc;
     }
-    return TSGPU_OK;
+    return dev_call_end(w, st);
 }
 
 extern "C" int tsgpu_detransform_device(tsgpu_ctx* c, int device_index, uint32_t flags, const uint8_t* d_slots,
@@ -649,9 +677,12 @@ extern "C" int tsgpu_detransform_device(tsgpu_ctx* c, int device_index, uint32_t
     if (n_chunks == 0) return TSGPU_OK;
     if (n_chunks > c->max_batch) return fail(TSGPU_E_ARG, "%u chunks exceed the context's max_batch %u", n_chunks, c->max_batch);
     if ((flags & TSGPU_FLAG_AES) && (!key || aad_len > MAX_AAD)) return fail(TSGPU_E_ARG, "key/aad invalid");
+    if (slot_stride < tsgpu_slot_stride(flags, chunk_size) || (slot_stride & 15)) return fail(TSGPU_E_ARG, "slot_stride too small or not a multiple of 16");
+    if (!d_slots || !d_transformed_sizes || !d_dst || !d_original_sizes || !d_status) return fail(TSGPU_E_ARG, "null device pointer");
     std::lock_guard<std::mutex> lock(c->mu);
     RT(rt::set_device(w.device));
     rt::stream_t st = (rt::stream_t)stream;
+    { int rb = dev_call_begin(w, st); if (rb) return rb; }
     for (uint32_t i = 0; i < n_chunks; i++) {
         w.hd.c_off[i] = (uint64_t)i * slot_stride + TSGPU_SLOT_HEAD;
         w.hd.b_off[i] = (uint64_t)i * c->frame_stride;
@@ -660,7 +691,12 @@ extern "C" int tsgpu_detransform_device(tsgpu_ctx* c, int device_index, uint32_t
     Aes256RoundKeys rk{};
     if (flags & TSGPU_FLAG_AES) { rk = aes256_expand_key(key); if (aad_len) memcpy(w.hd.aad, aad, aad_len); }
     RT(rt::h2d(w.d_desc, w.h_desc, w.desc_bytes, st));
+    RT(rt::event_record(w.ev_dev_desc, st));
+    w.dev_pending = true;
+    RT(rt::event_record(w.ev_dev_done, st));
     RT(rt::memset_async(d_status, 0, 4ull * n_chunks, st));
+    // sizes are device-resident (possibly from a manifest): the kernels bound them against these capacities
+    const uint32_t in_room = (uint32_t)std::min<uint64_t>(slot_stride - TSGPU_SLOT_HEAD, 0xffffffffu);
     const uint8_t* cur_base = d_slots; const uint64_t* cur_off = w.dd.c_off; const uint32_t* cur_len = d_transformed_sizes;
     if (flags & TSGPU_FLAG_AES) {
         const bool z = flags & TSGPU_FLAG_ZSTD;
@@ -669,17 +705,19 @@ extern "C" int tsgpu_detransform_device(tsgpu_ctx* c, int device_index, uint32_t
         uint32_t* ol = z ? w.dd.b_len : d_original_sizes;
         uint32_t max_t = (uint32_t)(slot_stride - TSGPU_SLOT_HEAD);
         w.key_valid = false;
+        const uint32_t out_room = z ? (uint32_t)std::min<uint64_t>(c->frame_stride - 16, in_room - 28) : chunk_size;
         rc = gcm_stage<false>(c, w, st, rk, false, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
-                              d_status, n_chunks, max_t, w.d_partials, w.max_ranges);
+                              d_status, n_chunks, max_t, w.d_partials, w.max_ranges, out_room);
         if (rc) return rc;
         cur_base = ob; cur_off = oo; cur_len = ol;
     }
     if (flags & TSGPU_FLAG_ZSTD) {
+        const uint32_t zin_room = (flags & TSGPU_FLAG_AES) ? (uint32_t)(c->frame_stride - 16) : in_room;
         int zr = zstd_decompress_batch(w.zdec, st, cur_base, cur_off, cur_len, n_chunks, chunk_size,
-                                       d_dst, w.dd.a_off, d_original_sizes, d_status, /*compute_offsets=*/false, c->prof);
+                                       d_dst, w.dd.a_off, d_original_sizes, d_status, /*compute_offsets=*/false, c->prof, zin_room);
         if (zr) return fail(zr, "zstd decompress: %s", zstd_last_error());
     }
-    return TSGPU_OK;
+    return dev_call_end(w, st);
 }
 
 // ------------------------------------------------------------------------------------------ profiling
@@ -707,11 +745,13 @@ extern "C" int tsgpu_chunk_positions(tsgpu_ctx* c, const uint32_t* sizes, uint32
     Work& w = c->lanes[0].w[0];
     RT(rt::set_device(w.device));
     uint32_t* d_sizes = nullptr; uint64_t* d_pos = nullptr;
-    RT(rt::malloc_device((void**)&d_sizes, 4ull * (n + 1)));
-    RT(rt::malloc_device((void**)&d_pos, 8ull * (n + 1)));
-    if (n) RT(rt::h2d(d_sizes, sizes, 4ull * n, w.stream));
-    TS_LAUNCH_P(c->prof, "chunk_index_scan", chunk_index_scan_kernel, dim3(1), dim3(32), 0, w.stream, d_sizes, n, d_pos);
-    const char* e = rt::last_error();
+    const char* e = rt::malloc_device((void**)&d_sizes, 4ull * (n + 1));
+    if (!e) e = rt::malloc_device((void**)&d_pos, 8ull * (n + 1));
+    if (!e && n) e = rt::h2d(d_sizes, sizes, 4ull * n, w.stream);
+    if (!e) {
+        TS_LAUNCH_P(c->prof, "chunk_index_scan", chunk_index_scan_kernel, dim3(1), dim3(32), 0, w.stream, d_sizes, n, d_pos);
+        e = rt::last_error();
+    }
     if (!e) e = rt::d2h(positions, d_pos, 8ull * (n + 1), w.stream);
     if (!e) e = rt::stream_sync(w.stream);
     rt::free_device(d_sizes); rt::free_device(d_pos);

@@ -74,6 +74,7 @@ struct ZstdDecArgs {
     uint8_t* out_base; const uint64_t* out_off; uint32_t* out_len; uint32_t* status;
     uint32_t* blk_off; uint32_t* info; uint8_t* lits_fast; uint8_t* lits_general;
     uint32_t blocks_per_chunk, chunk_cap, n_chunks;
+    uint32_t in_cap;                 // bytes a frame can occupy in its input slot: a longer in_len (device-resident, untrusted) is corrupt
     uint32_t par; uint8_t* par_meta; uint8_t* par_lits; uint64_t* par_seqs; uint32_t par_lit_cap, par_seq_cap;
 };
 constexpr int ZD_INFO = 8;     // fcs, nblk, fast-path eligible, need_general / failed, header size, parallel-general, literal bump, sequence bump
@@ -381,9 +382,18 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
 // tables a block inherits (treeless literals, Repeat_Mode) are rebuilt by replaying the table definitions of the blocks
 // before it; offsets stay unresolved offset VALUES.  One warp per frame then resolves repeat offsets and executes the
 // sequences in order.  The stages are the same textual includes the serial decoder is made of.
-struct ZdBlkMeta { uint32_t status, lit_kind, lit_off, regen, nseq, seq_off; };     // status 1 = decoded, 2 = failed; lit_kind 0 arena, 1 in the block, 2 RLE
+// Sequence word of the arenas: bits 0..29 offset field, 30..46 literal length, 47..63 match length - 3.
+// Offset field: a concrete offset (< 2^29), or — when the sequence used a repeat offset that reaches back to the state the
+// block STARTED with, which the entropy stage cannot know — bit 29 set, bits 27..28 = which of the three initial repeat
+// offsets (1..3), bits 0..26 = how much was subtracted from it (the "rep1 - 1" form, RFC 8878 §3.1.1.5).
+constexpr uint32_t ZD_OFF_SYM = 1u << 29;
+struct ZdBlkMeta {
+    uint32_t status;                 // 1 decoded, 2 failed, 3 = needs the serial path (a field does not fit the sequence word)
+    uint32_t lit_kind, lit_off, regen, nseq, seq_off;      // lit_kind 0 arena, 1 in the block, 2 RLE
+    uint32_t rep[3];                 // repeat offsets after the block, in the offset-field encoding above
+    uint32_t pad[3];
+};
 struct ZdParIO { uint8_t* lit_arena; uint32_t lit_cap; uint32_t* lit_bump; uint64_t* seq_arena; uint32_t seq_cap; uint32_t* seq_bump; };
-constexpr uint32_t ZD_PAR_MAX_BLOCKS = 128;
 
 // Table definitions of one Compressed_Block only (Huffman tree, the three FSE tables): what a later block may inherit.
 __device__ __forceinline__ uint32_t zd_block_tables(const uint8_t* blk, uint32_t bsize, ZdWarpCtx* cx, uint32_t lane) {
@@ -409,9 +419,12 @@ __device__ __forceinline__ uint32_t zd_block_huf_only(const uint8_t* blk, uint32
     return 0;
 }
 
-// Does the block use a table it does not define itself (treeless literals / Repeat_Mode)?  Malformed headers answer yes:
-// the replay or the block's own decode will then report the error.  Lane 0 parses, the warp gets the answer.
-// Returns a mask: bit 0 = the Huffman tree is inherited, bit 1 = at least one FSE table is.
+// What a Compressed_Block inherits and what it defines.  Lane 0 parses, the warp gets the answer as a mask:
+//   bit 0  literals are treeless (the Huffman tree comes from an earlier block)
+//   bit 1  at least one FSE table is in Repeat_Mode
+//   bit 2  the block has no sequences (its sequences section defines no table)
+//   bit 3  the block carries a Huffman tree (Compressed_Literals)
+// Malformed headers answer "inherits everything": the replay or the block's own decode then reports the error.
 __device__ __forceinline__ uint32_t zd_block_inherits(const uint8_t* blk, uint32_t bsize, uint32_t lane) {
     uint32_t r = 3;
     if (lane == 0) {
@@ -436,8 +449,8 @@ __device__ __forceinline__ uint32_t zd_block_inherits(const uint8_t* blk, uint32
             const uint32_t ssize = bsize - hs - comp;
             uint32_t nseq = sp[0], sh = 1;
             if (nseq >= 128) { sh = nseq == 255 ? 3 : 2; if (ssize < sh) break; nseq = 1; }
-            const uint32_t huf = type == 3 ? 1u : 0u;                        // treeless literals
-            if (nseq == 0) { r = huf; break; }
+            const uint32_t huf = (type == 3 ? 1u : 0u) | (type == 2 ? 8u : 0u);
+            if (nseq == 0) { r = huf | 4u; break; }
             if (ssize < sh + 1) break;
             const uint32_t modes = sp[sh];
             r = huf | (((modes >> 6) == 3 || ((modes >> 4) & 3) == 3 || ((modes >> 2) & 3) == 3) ? 2u : 0u);
@@ -447,7 +460,13 @@ __device__ __forceinline__ uint32_t zd_block_inherits(const uint8_t* blk, uint32
 }
 
 // Entropy stage of one Compressed_Block: literals into the frame's literal arena (unless Raw / RLE), sequences as
-// packed (offset value : 30, literal length : 17, match length - 3 : 17) into the frame's sequence arena.
+// packed words (see ZD_OFF_SYM) into the frame's sequence arena.  Repeat offsets are resolved HERE, per block and in
+// parallel across blocks: the three repeat offsets a block starts with are unknown to it, so they are carried as symbols
+// (initial offset k, minus d) until real offsets have pushed them out; the execution stage substitutes them.
+__device__ __forceinline__ uint32_t zd_rep_sub1(uint32_t v) {            // "rep1 - 1" on an offset field; 0 = invalid
+    if (v & ZD_OFF_SYM) return (v & 0x7ffffffu) == 0x7ffffffu ? 0u : v + 1;   // symbolic: one more subtracted
+    return v - 1;                                                        // concrete: 0 when the offset was 1 (corrupt)
+}
 __device__ __forceinline__ uint32_t zd_block_entropy(const uint8_t* blk, uint32_t bsize, ZdWarpCtx* cx, const ZdParIO& io,
                                                      ZdBlkMeta* meta, uint32_t lane) {
     const uint32_t limit = zf::BLOCK_MAX, litcap = zf::BLOCK_MAX;
@@ -472,6 +491,7 @@ __device__ __forceinline__ uint32_t zd_block_entropy(const uint8_t* blk, uint32_
         const uint32_t o = atomicAdd(io.seq_bump, nseq);
         cx->tmp[7] = o;
         if ((uint64_t)o + nseq > io.seq_cap) cx->err = -1;
+        cx->rep[0] = ZD_OFF_SYM | (1u << 27); cx->rep[1] = ZD_OFF_SYM | (2u << 27); cx->rep[2] = ZD_OFF_SYM | (3u << 27);
     }
     __syncwarp();
     if (cx->err) return 0;
@@ -481,46 +501,306 @@ __device__ __forceinline__ uint32_t zd_block_entropy(const uint8_t* blk, uint32_
     for (uint32_t s0 = 0; s0 < nseq; s0 += 32) {
         const uint32_t cnt = min(32u, nseq - s0);
 #include "zd_blk_decode_batch.inc"
-        const bool wide = mine && (ofv >= (1u << 30) || ll >= (1u << 17) || ml - 3 >= (1u << 17));
-        if (__ballot_sync(TS_FULL, wide)) { if (lane == 0) cx->err = -1; __syncwarp(); return 0; }
-        if (mine) sq[s0 + lane] = (uint64_t)ofv | ((uint64_t)ll << 30) | ((uint64_t)(ml - 3) << 47);
-        (void)off;
+        const bool wide = mine && ((ofv > 3 && ofv - 3 >= ZD_OFF_SYM) || ll >= (1u << 17) || ml - 3 >= (1u << 17));
+        if (__ballot_sync(TS_FULL, wide)) { if (lane == 0) cx->err = 2; __syncwarp(); return 0; }    // does not fit the word: serial path
+        // offset field of every sequence of the batch (concrete or symbolic), and the repeat-offset state after it
+        uint32_t of = off;                                   // ofv - 3 for real offsets
+        const uint32_t rep_mask = __ballot_sync(TS_FULL, mine && ofv <= 3);
+        if (rep_mask == 0) {
+            const uint32_t o1 = __shfl_sync(TS_FULL, of, cnt - 1), o2 = __shfl_sync(TS_FULL, of, cnt >= 2 ? cnt - 2 : 0),
+                           o3 = __shfl_sync(TS_FULL, of, cnt >= 3 ? cnt - 3 : 0);
+            if (lane == 0) {
+                const uint32_t r0 = cx->rep[0], r1 = cx->rep[1];
+                cx->rep[2] = cnt >= 3 ? o3 : cnt == 2 ? r0 : r1;
+                cx->rep[1] = cnt >= 2 ? o2 : r0;
+                cx->rep[0] = o1;
+            }
+        } else {
+            __syncwarp();
+            cx->s_off[lane] = ofv; cx->s_ml[lane] = ll;
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t r0 = cx->rep[0], r1 = cx->rep[1], r2 = cx->rep[2];
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const uint32_t v = cx->s_off[i];
+                    uint32_t o;
+                    if (v > 3) { o = v - 3; r2 = r1; r1 = r0; r0 = o; }
+                    else {
+                        const uint32_t idx = v - 1 + (cx->s_ml[i] == 0 ? 1 : 0);     // 0: rep1, 1: rep2, 2: rep3, 3: rep1 - 1
+                        if (idx == 0) o = r0;
+                        else {
+                            const uint32_t t = idx == 1 ? r1 : idx == 2 ? r2 : zd_rep_sub1(r0);
+                            if (t == 0) { cx->err = -1; break; }
+                            if (idx != 1) r2 = r1;
+                            r1 = r0; r0 = t; o = t;
+                        }
+                    }
+                    cx->s_off[i] = o;
+                }
+                cx->rep[0] = r0; cx->rep[1] = r1; cx->rep[2] = r2;
+            }
+            __syncwarp();
+            if (cx->err) return 0;
+            of = mine ? cx->s_off[lane] : 1;
+        }
+        if (mine) sq[s0 + lane] = (uint64_t)of | ((uint64_t)ll << 30) | ((uint64_t)(ml - 3) << 47);
+        __syncwarp();
     }
     (void)op; (void)lp; (void)lit;
     if (lane == 0) {
         meta->lit_kind = ltype == 0 ? 1u : ltype == 1 ? 2u : 0u;
         meta->lit_off = ltype == 0 ? lhs : ltype == 1 ? rle_lit : lit_at;
         meta->regen = regen; meta->nseq = nseq; meta->seq_off = seq_at;
+        if (nseq) { meta->rep[0] = cx->rep[0]; meta->rep[1] = cx->rep[1]; meta->rep[2] = cx->rep[2]; }
+        else { meta->rep[0] = ZD_OFF_SYM | (1u << 27); meta->rep[1] = ZD_OFF_SYM | (2u << 27); meta->rep[2] = ZD_OFF_SYM | (3u << 27); }
     }
     return 0;
 }
 
-// Execution stage of one Compressed_Block from what zd_block_entropy left: repeat offsets, literal runs, matches.
-__device__ __forceinline__ uint32_t zd_block_execute(const uint8_t* blk, uint8_t* dst, uint64_t hist, uint32_t limit, ZdWarpCtx* cx,
-                                                     const ZdBlkMeta m, const uint8_t* lit_arena, const uint64_t* seq_arena,
-                                                     uint32_t lane) {
-    const bool fast_nonfirst = false;
-    const uint32_t regen = m.regen, nseq = m.nseq;
-    const uint8_t* lit = nullptr;
-    uint32_t rle_lit = 0x100;
-    if (m.lit_kind == 1) lit = blk + m.lit_off;
-    else if (m.lit_kind == 2) rle_lit = m.lit_off & 0xff;
-    else lit = lit_arena + m.lit_off;
-    const uint64_t* sq = seq_arena + m.seq_off;
-    uint32_t op = 0, lp = 0;
-    for (uint32_t s0 = 0; s0 < nseq; s0 += 32) {
-        const uint32_t cnt = min(32u, nseq - s0);
-        const bool mine = lane < cnt;
-        uint32_t ll = 0, ml = 0, off = 1, ofv = 4;
-        if (mine) {
-            const uint64_t v = sq[s0 + lane];
-            ofv = (uint32_t)v & 0x3fffffffu; ll = (uint32_t)(v >> 30) & 0x1ffffu; ml = (uint32_t)(v >> 47) + 3;
-            off = ofv - 3;
-        }
-#include "zd_blk_exec_batch.inc"
+// ------------------------------------------------------------------------------------------ execution stage, one CTA
+// Executes the sequences the entropy stage left in the arenas, blocks [b_first, b_last) in order, into out[0..) (generic
+// pointer: HBM for whole frames, shared memory for self-contained regions).  ZX_T sequences are taken per step:
+//   * positions by a CTA-wide prefix sum of literal and match lengths,
+//   * every literal run copied at once (they depend on nothing),
+//   * matches by EXACT dependency tracking: a match waits only for the earlier matches of the same step whose
+//     destination overlaps its source (found by binary search in the step's positions); everything before the step is
+//     complete.  Rounds of "copy what is ready, barrier" run until the step is done — the depth of the real dependency
+//     chains, not the number of sequences, bounds the number of rounds.
+constexpr int ZX_T = 512;
+constexpr uint32_t ZX_DEP_SPAN = 6;          // producers checked individually; wider sources wait to be first in line
+struct ZxShared {
+    uint32_t ostart[ZX_T + 1];               // output position of each sequence of the step (+ end)
+    uint32_t mlen[ZX_T];
+    uint8_t done[ZX_T];
+    uint64_t wsum[ZX_T / 32];
+    uint32_t wpend[ZX_T / 32];
+    uint64_t tot;
+    uint32_t rep[3];
+    int32_t err;
+};
+
+__device__ __forceinline__ uint64_t zx_block_scan(uint64_t v, uint32_t tid, ZxShared* sh, uint64_t* total) {
+    const uint32_t lane = tid & 31, w = tid >> 5;
+    uint64_t inc = warp_inclusive_scan_u64(v, lane);
+    if (lane == 31) sh->wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const uint64_t x = lane < ZX_T / 32 ? sh->wsum[lane] : 0;
+        const uint64_t xi = warp_inclusive_scan_u64(x, lane);
+        if (lane < ZX_T / 32) sh->wsum[lane] = xi - x;
+        if (lane == ZX_T / 32 - 1) sh->tot = xi;
     }
-#include "zd_blk_trailing.inc"
-    __syncwarp();
+    __syncthreads();
+    inc += sh->wsum[w];
+    *total = sh->tot;
+    return inc;
+}
+
+// Cooperative copy by the calling WARP: n bytes from src to dst (no overlap), any alignment.
+__device__ __forceinline__ void zx_warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) {
+    for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
+}
+
+// Returns bytes produced (the new output position) or sets sh->err (<0 corrupt / contract violated).
+// base_hist: bytes of history before out[0] that may be referenced (0 for regions and frames).
+__device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, const uint32_t* bo, const ZdBlkMeta* meta,
+                                                      uint32_t b_first, uint32_t b_last, uint8_t* out, uint32_t out_cap,
+                                                      const uint8_t* lit_arena, const uint64_t* seq_arena, uint32_t frame_len,
+                                                      ZxShared* sh, uint32_t tid) {
+    const uint32_t lane = tid & 31, w = tid >> 5;
+    uint32_t op = 0;
+    if (tid == 0) { sh->rep[0] = 1; sh->rep[1] = 4; sh->rep[2] = 8; sh->err = 0; }
+    __syncthreads();
+    for (uint32_t b = b_first; b < b_last; b++) {
+        const uint32_t pos = bo[b];
+        const uint32_t h = frame[pos] | (frame[pos + 1] << 8) | ((uint32_t)frame[pos + 2] << 16);
+        const uint32_t type = (h >> 1) & 3, bsz = h >> 3;
+        const uint32_t room = min((uint32_t)zf::BLOCK_MAX, out_cap - op);
+        if (type == 0) {
+            if (bsz > room || pos + 3 + bsz > frame_len) { if (tid == 0) sh->err = -1; __syncthreads(); return op; }
+            for (uint32_t k = tid; k < bsz; k += ZX_T) out[op + k] = frame[pos + 3 + k];
+            op += bsz;
+            __syncthreads();
+            continue;
+        }
+        if (type == 1) {
+            if (bsz > room || pos + 4 > frame_len) { if (tid == 0) sh->err = -1; __syncthreads(); return op; }
+            const uint8_t v = frame[pos + 3];
+            for (uint32_t k = tid; k < bsz; k += ZX_T) out[op + k] = v;
+            op += bsz;
+            __syncthreads();
+            continue;
+        }
+        const ZdBlkMeta m = meta[b];
+        if (m.status != 1) { if (tid == 0) sh->err = m.status == 3 ? 3 : -1; __syncthreads(); return op; }
+        const uint8_t* blk = frame + pos + 3;
+        const uint8_t* lit = nullptr;
+        uint32_t rle_lit = 0x100;
+        if (m.lit_kind == 1) lit = blk + m.lit_off;
+        else if (m.lit_kind == 2) rle_lit = m.lit_off & 0xff;
+        else lit = lit_arena + m.lit_off;
+        const uint64_t* sq = seq_arena + m.seq_off;
+        const uint32_t N = m.nseq, regen = m.regen;
+        const uint32_t R0 = sh->rep[0], R1 = sh->rep[1], R2 = sh->rep[2];     // repeat offsets at the start of the block
+        const uint32_t blk_op0 = op;
+        uint32_t lp = 0;
+        for (uint32_t base = 0; base < N; base += ZX_T) {
+            const uint32_t i = base + tid;
+            const bool mine = i < N;
+            uint32_t ll = 0, ml = 0, off = 1;
+            bool bad = false;
+            if (mine) {
+                const uint64_t v = sq[i];
+                const uint32_t of = (uint32_t)v & 0x3fffffffu;
+                ll = (uint32_t)(v >> 30) & 0x1ffffu; ml = (uint32_t)(v >> 47) + 3;
+                if (of & ZD_OFF_SYM) {
+                    const uint32_t k = (of >> 27) & 3, d = of & 0x7ffffffu;
+                    const uint32_t r = k == 1 ? R0 : k == 2 ? R1 : R2;
+                    if (r <= d) bad = true; else off = r - d;
+                } else off = of;
+                if (off == 0) bad = true;
+            }
+            uint64_t tot;
+            const uint64_t inc = zx_block_scan(((uint64_t)(ll + ml) << 32) | ll, tid, sh, &tot);
+            const uint32_t tot_o = (uint32_t)(tot >> 32), tot_l = (uint32_t)tot;
+            const uint32_t o_start = op + (uint32_t)(inc >> 32) - ll - ml, l_start = lp + (uint32_t)inc - ll, m_start = o_start + ll;
+            if (mine && off > m_start) bad = true;
+            sh->ostart[tid] = mine ? o_start : op + tot_o;
+            sh->mlen[tid] = mine ? ml : 0;
+            sh->done[tid] = (!mine || ml == 0) ? 1 : 0;
+            if (tid == 0) sh->ostart[ZX_T] = op + tot_o;
+            const bool any_bad = __syncthreads_or(bad) != 0;
+            if (any_bad || lp + tot_l > regen || (uint64_t)(op - blk_op0) + tot_o > zf::BLOCK_MAX || (uint64_t)op + tot_o > out_cap) {
+                if (tid == 0) sh->err = -1;
+                __syncthreads();
+                return op;
+            }
+            // ---- literal runs: short ones by their own thread, long ones by the warp
+            {
+                const uint32_t quick = min(ll, 32u);
+                uint8_t* ld = out + o_start;
+                if (rle_lit < 0x100) { for (uint32_t k = 0; k < quick; k++) ld[k] = (uint8_t)rle_lit; }
+                else {
+                    const uint8_t* ls = lit + l_start;
+                    uint32_t k = 0;
+                    for (; k + 4 <= quick; k += 4) {
+                        const uint8_t b0 = ls[k], b1 = ls[k + 1], b2 = ls[k + 2], b3 = ls[k + 3];
+                        ld[k] = b0; ld[k + 1] = b1; ld[k + 2] = b2; ld[k + 3] = b3;
+                    }
+                    for (; k < quick; k++) ld[k] = ls[k];
+                }
+                uint32_t longs = __ballot_sync(TS_FULL, ll > 32);
+                while (longs) {
+                    const uint32_t f = (uint32_t)__ffs((int)longs) - 1;
+                    longs &= longs - 1;
+                    const uint32_t fo = __shfl_sync(TS_FULL, o_start, f), fl = __shfl_sync(TS_FULL, l_start, f), fn = __shfl_sync(TS_FULL, ll, f);
+                    if (rle_lit < 0x100) { for (uint32_t k = 32 + lane; k < fn; k += 32) out[fo + k] = (uint8_t)rle_lit; }
+                    else { for (uint32_t k = 32 + lane; k < fn; k += 32) out[fo + k] = lit[fl + k]; }
+                }
+            }
+            // ---- producers of this match inside the step: sequences [ja, jb] cover its source bytes
+            const uint32_t s_lo = m_start - off;                          // first source byte
+            const uint32_t s_hi = min(s_lo + ml, m_start);                // one past the last source byte written by someone else
+            uint32_t ja = 0, jb = 0;
+            bool inside = false;                                          // does the source reach into this step's output?
+            if (mine && ml && s_hi > op) {
+                inside = true;
+                uint32_t lo = 0, hi = tid;                                // last j <= tid with ostart[j] <= x
+                const uint32_t x = max(s_lo, op);
+                while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] <= x) lo = mid; else hi = mid - 1; }
+                ja = lo;
+                lo = ja; hi = tid;
+                while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] < s_hi) lo = mid; else hi = mid - 1; }
+                jb = lo;
+                if (jb == tid) jb = tid ? tid - 1 : 0;                    // own literals precede the match: never a producer
+                if (ja > jb) inside = false;
+            }
+            __syncthreads();                                              // literals, ostart/mlen/done visible
+            bool done = !mine || ml == 0;
+            uint8_t* d = out + m_start;
+            const uint8_t* msrc = d - off;
+            while (true) {
+                // first pending sequence of the step (for sources too wide to check producer by producer)
+                const uint32_t pend = __ballot_sync(TS_FULL, !done);
+                if (lane == 0) sh->wpend[w] = pend;
+                __syncthreads();
+                bool ready = false;
+                if (!done) {
+                    if (!inside) ready = true;
+                    else if (jb - ja < ZX_DEP_SPAN) {
+                        ready = true;
+                        for (uint32_t j = ja; j <= jb; j++) {
+                            if (sh->done[j]) continue;
+                            const uint32_t pm = sh->ostart[j + 1] - sh->mlen[j];      // producer's match bytes [pm, ostart[j+1])
+                            if (sh->ostart[j + 1] > s_lo && pm < s_hi) { ready = false; break; }
+                        }
+                    } else {
+                        uint32_t first = ZX_T;
+                        for (uint32_t q = 0; q < ZX_T / 32; q++) { const uint32_t pm = sh->wpend[q]; if (pm) { first = q * 32 + (uint32_t)__ffs((int)pm) - 1; break; } }
+                        ready = first == tid;
+                    }
+                }
+                if (ready && ml <= 64) {
+                    uint32_t k = 0;
+                    if (off >= 4) {
+                        for (; k + 4 <= ml; k += 4) {
+                            const uint8_t b0 = msrc[k], b1 = msrc[k + 1], b2 = msrc[k + 2], b3 = msrc[k + 3];
+                            d[k] = b0; d[k + 1] = b1; d[k + 2] = b2; d[k + 3] = b3;
+                        }
+                    }
+                    for (; k < ml; k++) d[k] = msrc[k];
+                }
+                uint32_t big = __ballot_sync(TS_FULL, ready && ml > 64);
+                while (big) {                                             // long matches: 32 lanes per match
+                    const uint32_t f = (uint32_t)__ffs((int)big) - 1;
+                    big &= big - 1;
+                    const uint32_t fm = __shfl_sync(TS_FULL, m_start, f), fl = __shfl_sync(TS_FULL, ml, f), fo = __shfl_sync(TS_FULL, off, f);
+                    uint8_t* dd = out + fm;
+                    const uint8_t* mm = dd - fo;
+                    if (fo >= 32) {
+                        for (uint32_t k0 = 0; k0 < fl; k0 += 32) {
+                            const uint32_t k = k0 + lane;
+                            if (k < fl) dd[k] = mm[k];
+                            if (fo < fl) __syncwarp();
+                        }
+                    } else {
+                        for (uint32_t k = lane; k < fl; k += 32) dd[k] = mm[k % fo];
+                    }
+                }
+                __syncthreads();                                          // copies of this round complete before anyone is told so
+                if (ready) { sh->done[tid] = 1; done = true; }
+                if (!__syncthreads_or(!done)) break;
+            }
+            op += tot_o; lp += tot_l;
+        }
+        // trailing literals of the block
+        {
+            if (lp > regen || (uint64_t)(op - blk_op0) + (regen - lp) > zf::BLOCK_MAX || (uint64_t)op + (regen - lp) > out_cap) {
+                if (tid == 0) sh->err = -1;
+                __syncthreads();
+                return op;
+            }
+            const uint32_t ll = regen - lp;
+            if (rle_lit < 0x100) { for (uint32_t k = tid; k < ll; k += ZX_T) out[op + k] = (uint8_t)rle_lit; }
+            else { for (uint32_t k = tid; k < ll; k += ZX_T) out[op + k] = lit[lp + k]; }
+            op += ll;
+        }
+        __syncthreads();
+        if (tid == 0) {                                                   // repeat offsets after the block
+            uint32_t nr[3];
+            for (int k = 0; k < 3; k++) {                                 // an offset that underflowed is only an error if it is used
+                const uint32_t of = m.rep[k];
+                if (of & ZD_OFF_SYM) {
+                    const uint32_t q = (of >> 27) & 3, dd = of & 0x7ffffffu;
+                    const uint32_t r = q == 1 ? R0 : q == 2 ? R1 : R2;
+                    nr[k] = r > dd ? r - dd : 0;
+                } else nr[k] = of;
+            }
+            sh->rep[0] = nr[0]; sh->rep[1] = nr[1]; sh->rep[2] = nr[2];
+        }
+        __syncthreads();
+        if (sh->err) return op;
+    }
     return op;
 }
 
@@ -559,6 +839,7 @@ __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_consta
     uint64_t fcs = 0;
     info[0] = 0; info[1] = 0; info[2] = 0; info[3] = 0; info[4] = 0; info[5] = 0; info[6] = 0; info[7] = 0;
     if (A.status[chunk] != 0) { A.out_len[chunk] = 0; info[3] = 2; return; }      // e.g. tag mismatch upstream: nothing to decode
+    if (n > A.in_cap) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; info[3] = 2; return; }
     const uint32_t hs = zd_frame_header(p, n, &fcs);
     // "Invalid decompressed size" (DecompressionChunkEnumeration.java:41-44): no FCS, or larger than a chunk can be
     if (!hs || fcs == 0xffffffffffffffffull || fcs > A.chunk_cap) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; info[3] = 2; return; }
@@ -584,7 +865,7 @@ __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_consta
     info[1] = nblk;
     info[2] = (last && nblk == want && nblk <= A.blocks_per_chunk) ? 1 : 0;      // eligible for the per-block path
     // libzstd-shaped frames (few large blocks): entropy-decode the blocks in parallel when that variant is switched on
-    info[5] = (A.par && !info[2] && last && nblk <= A.blocks_per_chunk && nblk <= ZD_PAR_MAX_BLOCKS) ? 1 : 0;
+    info[5] = (A.par && !info[2] && last && nblk <= A.blocks_per_chunk) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------ kernel 2: per-block fast path
@@ -691,6 +972,17 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_frames_kernel(const __gr
 }
 
 // ------------------------------------------------------------------------------------------ kernels 3a / 3b: parallel general path
+// 3a: one WARP per block — entropy stage.  Tables a block inherits are rebuilt by replaying table definitions, starting
+// at the nearest earlier block that defines all three FSE tables itself (and, for treeless literals, after loading the
+// latest Huffman tree): libzstd frames inherit the tree in nearly every block, frames of this library's compressor inherit
+// everything from the first block of their 64 KiB region.
+__device__ __forceinline__ bool zd_blk_hdr(const uint8_t* p, const uint32_t* bo, uint32_t j, uint32_t* pos, uint32_t* type, uint32_t* bsz) {
+    const uint32_t pj = bo[j];
+    const uint32_t hj = p[pj] | (p[pj + 1] << 8) | ((uint32_t)p[pj + 2] << 16);
+    *pos = pj; *type = (hj >> 1) & 3; *bsz = hj >> 3;
+    return *type == 2 && *bsz <= zf::BLOCK_MAX;
+}
+
 __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_entropy_kernel(const __grid_constant__ ZstdDecArgs A) {
     TS_DYN_SMEM(smem);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -702,40 +994,49 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_entropy_kernel(const
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t n = A.in_len[chunk];
     const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
-    const uint32_t pos = bo[b];
-    const uint32_t h = p[pos] | (p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
-    const uint32_t type = (h >> 1) & 3, bsz = h >> 3;
+    uint32_t pos, type, bsz;
+    const bool comp = zd_blk_hdr(p, bo, b, &pos, &type, &bsz);
     if (type != 2) { if (lane == 0) meta->status = 1; return; }           // Raw / RLE blocks need no entropy stage
-    if (pos + 3 + bsz > n || bsz > zf::BLOCK_MAX) { if (lane == 0) meta->status = 2; return; }
+    if (!comp || pos + 3 + bsz > n) { if (lane == 0) meta->status = 2; return; }
     if (lane == 0) { cx->err = 0; cx->huf_valid = 0; cx->ll_valid = 0; cx->ml_valid = 0; cx->of_valid = 0; }
     __syncwarp();
     const uint32_t inherits = zd_block_inherits(p + pos + 3, bsz, lane);
-    if (inherits == 1) {
-        // only the Huffman tree (what libzstd writes in nearly every block after the first): the latest block with
-        // Compressed_Literals defines it
-        bool found = false;
-        for (uint32_t j = b; j-- > 0 && !found; ) {
-            const uint32_t pj = bo[j];
-            const uint32_t hj = p[pj] | (p[pj + 1] << 8) | ((uint32_t)p[pj + 2] << 16);
-            const uint32_t bj = hj >> 3;
-            if (((hj >> 1) & 3) != 2 || bj < 1 || (p[pj + 3] & 3) != 2) continue;
-            found = true;
-            if (bj > zf::BLOCK_MAX) { if (lane == 0) cx->err = -1; __syncwarp(); break; }
-            zd_block_huf_only(p + pj + 3, bj, cx, lane);
-            __syncwarp();
+    if (inherits & 3) {
+        // j0: where the replay of FSE definitions has to start (none needed: j0 = b)
+        uint32_t j0 = b;
+        bool tree_in_replay = false;
+        if (inherits & 2) {
+            bool found = false;
+            while (j0 > 0 && !found) {
+                j0--;
+                uint32_t pj, tj, bj;
+                if (!zd_blk_hdr(p, bo, j0, &pj, &tj, &bj)) continue;
+                const uint32_t r = zd_block_inherits(p + pj + 3, bj, lane);
+                if ((r & 6) == 0) { found = true; tree_in_replay = (r & 8) != 0; }   // defines LL, OF and ML itself
+            }
+            if (!found) { if (lane == 0) cx->err = -1; __syncwarp(); }   // Repeat_Mode without any definition before it
         }
-        if (!found && !cx->err) { if (lane == 0) cx->err = -1; __syncwarp(); }      // treeless without any tree before it
-    } else if (inherits) {
-        // replay the table definitions of every earlier Compressed_Block, in order (the index pass checked their bounds)
-        for (uint32_t j = 0; j < b; j++) {
-            const uint32_t pj = bo[j];
-            const uint32_t hj = p[pj] | (p[pj + 1] << 8) | ((uint32_t)p[pj + 2] << 16);
-            if (((hj >> 1) & 3) != 2) continue;
-            const uint32_t bj = hj >> 3;
-            if (bj > zf::BLOCK_MAX) { if (lane == 0) cx->err = -1; __syncwarp(); break; }
-            zd_block_tables(p + pj + 3, bj, cx, lane);
+        // the Huffman tree: the latest block with Compressed_Literals before the replay range — unless the replay range
+        // starts with one (every treeless block inside it is then served by the replay itself)
+        if (!cx->err && !tree_in_replay && ((inherits & 1) || j0 < b)) {
+            bool found = false;
+            for (uint32_t j = j0; j-- > 0 && !found; ) {
+                uint32_t pj, tj, bj;
+                if (!zd_blk_hdr(p, bo, j, &pj, &tj, &bj) || bj < 1 || (p[pj + 3] & 3) != 2) continue;
+                found = true;
+                zd_block_huf_only(p + pj + 3, bj, cx, lane);
+                __syncwarp();
+            }
+            // not found: fine as long as nothing treeless shows up before a tree (the decode reports it otherwise)
+        }
+        for (uint32_t j = j0; j < b && !cx->err; j++) {
+            uint32_t pj, tj, bj;
+            if (!zd_blk_hdr(p, bo, j, &pj, &tj, &bj)) continue;
+            if ((inherits & 2) || (p[pj + 3] & 3) == 2) {                 // FSE replay, or at least the trees on the way
+                if (inherits & 2) zd_block_tables(p + pj + 3, bj, cx, lane);
+                else zd_block_huf_only(p + pj + 3, bj, cx, lane);
+            }
             __syncwarp();
-            if (cx->err) break;
         }
     }
     if (!cx->err) {
@@ -745,55 +1046,26 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_entropy_kernel(const
         zd_block_entropy(p + pos + 3, bsz, cx, io, meta, lane);
     }
     __syncwarp();
-    if (lane == 0) meta->status = cx->err ? 2u : 1u;
+    if (lane == 0) meta->status = cx->err == 0 ? 1u : cx->err == 2 ? 3u : 2u;
 }
 
-__global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
-    TS_DYN_SMEM(smem);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.x * ZD_WPB + warp;
-    if (chunk >= A.n_chunks) return;
+// 3b: one CTA per frame — execution stage (zx_execute_blocks) straight into the frame's output in HBM.
+__global__ void __launch_bounds__(ZX_T) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
+    __shared__ ZxShared sh;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t chunk = blockIdx.x;
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
     if (!info[5] || info[3] == 2) return;
-    ZdWarpCtx* cx = (ZdWarpCtx*)(smem + (size_t)warp * sizeof(ZdWarpCtx));
     const uint32_t fcs = info[0], nblk = info[1];
     const uint8_t* p = A.in_base + A.in_off[chunk];
-    const uint32_t n = A.in_len[chunk];
-    uint8_t* dst = A.out_base + A.out_off[chunk];
     const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
     const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
-    const uint8_t* lit_arena = A.par_lits + (size_t)chunk * A.par_lit_cap;
-    const uint64_t* seq_arena = A.par_seqs + (size_t)chunk * A.par_seq_cap;
-    if (lane == 0) { cx->err = 0; cx->rep[0] = 1; cx->rep[1] = 4; cx->rep[2] = 8; }
-    __syncwarp();
-    uint64_t op = 0;
-    bool bad = false;
-    for (uint32_t b = 0; b < nblk && !bad; b++) {
-        const uint32_t pos = bo[b];
-        const uint32_t h = p[pos] | (p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
-        const uint32_t type = (h >> 1) & 3, bsz = h >> 3;
-        const uint32_t room = (uint32_t)min((uint64_t)zf::BLOCK_MAX, (uint64_t)fcs - op);
-        if (type == 0) {
-            if (bsz > room || pos + 3 + bsz > n) { bad = true; break; }
-            for (uint32_t k = lane; k < bsz; k += 32) dst[op + k] = p[pos + 3 + k];
-            op += bsz;
-        } else if (type == 1) {
-            if (bsz > room || pos + 4 > n) { bad = true; break; }
-            const uint8_t v = p[pos + 3];
-            for (uint32_t k = lane; k < bsz; k += 32) dst[op + k] = v;
-            op += bsz;
-        } else {
-            const ZdBlkMeta m = meta[b];
-            if (m.status != 1) { bad = true; break; }
-            const uint32_t made = zd_block_execute(p + pos + 3, dst + op, op, room, cx, m, lit_arena, seq_arena, lane);
-            if (cx->err) { bad = true; break; }
-            op += made;
-        }
-        __syncwarp();
-        __threadfence_block();
-    }
-    if (lane == 0) {
-        if (bad || op != fcs) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; }
+    const uint32_t made = zx_execute_blocks(p, bo, meta, 0, nblk, A.out_base + A.out_off[chunk], fcs,
+                                            A.par_lits + (size_t)chunk * A.par_lit_cap, A.par_seqs + (size_t)chunk * A.par_seq_cap,
+                                            A.in_len[chunk], &sh, tid);
+    if (tid == 0) {
+        if (sh.err == 3) info[5] = 0;                                     // a field too wide for the sequence word: the serial kernel decodes this frame
+        else if (sh.err || made != fcs) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; }
     }
 }
 
@@ -808,9 +1080,9 @@ inline const char* zstd_dec_scratch_alloc(ZstdDecScratch& s, uint32_t chunk_cap,
     if ((e = rt::malloc_device((void**)&s.lits_fast, (size_t)max_batch * s.blocks_per_chunk * (ZB + 64) + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.lits_general, (size_t)max_batch * ZD_LIT_GENERAL + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.pos_tmp, (size_t)(max_batch + 1) * 8 + 256))) return e;
-    { const char* v = getenv("TSGPU_DEC_PARALLEL"); s.par = v && atoi(v) != 0; }
+    { const char* v = getenv("TSGPU_DEC_PARALLEL"); s.par = !(v && atoi(v) == 0); }     // on by default (TSGPU_DEC_PARALLEL=0: serial general path only)
     if (s.par) {
-        s.par_lit_cap = (uint32_t)(((uint64_t)chunk_cap + 16ull * (ZD_PAR_MAX_BLOCKS + 1) + 4096 + 15) & ~15ull);
+        s.par_lit_cap = (uint32_t)(((uint64_t)chunk_cap + 16ull * (s.blocks_per_chunk + 1) + 4096 + 15) & ~15ull);
         s.par_seq_cap = chunk_cap / 3 + 64;
         if ((e = rt::malloc_device((void**)&s.par_meta, (size_t)max_batch * s.blocks_per_chunk * sizeof(ZdBlkMeta) + 256))) return e;
         if ((e = rt::malloc_device((void**)&s.par_lits, (size_t)max_batch * s.par_lit_cap + 256))) return e;
@@ -834,7 +1106,6 @@ inline const char* zstd_kernels_configure() {
     if ((e = rt::allow_smem(zstd_dec_blocks_kernel, ZD_WPB_FAST * ZD_FAST_WARP_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_frames_kernel, ZD_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_par_entropy_kernel, ZD_SMEM_BYTES))) return e;
-    if ((e = rt::allow_smem(zstd_dec_par_execute_kernel, ZD_SMEM_BYTES))) return e;
     return nullptr;
 }
 
@@ -843,14 +1114,14 @@ inline const char* zstd_kernels_configure() {
 inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8_t* in_base, const uint64_t* d_in_off,
                                  const uint32_t* d_in_len, uint32_t n_chunks, uint32_t chunk_cap, uint8_t* out_base,
                                  uint64_t* d_out_off, uint32_t* d_out_len, uint32_t* d_status, bool compute_offsets,
-                                 LaunchProf& prof) {
+                                 LaunchProf& prof, uint32_t in_cap = 0xffffffffu) {
     if (n_chunks > s.max_batch) { g_zstd_err = "batch larger than the context"; return -1; }
     if (chunk_cap > s.chunk_cap) { g_zstd_err = "chunk larger than the context"; return -1; }
     ZstdDecArgs A;
     A.in_base = in_base; A.in_off = d_in_off; A.in_len = d_in_len;
     A.out_base = out_base; A.out_off = d_out_off; A.out_len = d_out_len; A.status = d_status;
     A.blk_off = s.blk_off; A.info = s.info; A.lits_fast = s.lits_fast; A.lits_general = s.lits_general;
-    A.blocks_per_chunk = s.blocks_per_chunk; A.chunk_cap = chunk_cap; A.n_chunks = n_chunks;
+    A.blocks_per_chunk = s.blocks_per_chunk; A.chunk_cap = chunk_cap; A.n_chunks = n_chunks; A.in_cap = in_cap;
     A.par = s.par ? 1u : 0u; A.par_meta = s.par_meta; A.par_lits = s.par_lits; A.par_seqs = s.par_seqs;
     A.par_lit_cap = s.par_lit_cap; A.par_seq_cap = s.par_seq_cap;
     const char* e;
@@ -866,12 +1137,10 @@ inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8
                 ZD_WPB_FAST * ZD_FAST_WARP_BYTES, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     if (s.par) {
-        const uint32_t pb = bpc < ZD_PAR_MAX_BLOCKS ? bpc : ZD_PAR_MAX_BLOCKS;
-        TS_LAUNCH_P(prof, "zstd_dec_par_entropy", zstd_dec_par_entropy_kernel, dim3((pb + ZD_WPB - 1) / ZD_WPB, n_chunks), dim3(ZD_WPB * 32),
+        TS_LAUNCH_P(prof, "zstd_dec_par_entropy", zstd_dec_par_entropy_kernel, dim3((bpc + ZD_WPB - 1) / ZD_WPB, n_chunks), dim3(ZD_WPB * 32),
                     ZD_SMEM_BYTES, st, A);
         if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
-        TS_LAUNCH_P(prof, "zstd_dec_par_execute", zstd_dec_par_execute_kernel, dim3((n_chunks + ZD_WPB - 1) / ZD_WPB), dim3(ZD_WPB * 32),
-                    ZD_SMEM_BYTES, st, A);
+        TS_LAUNCH_P(prof, "zstd_dec_par_execute", zstd_dec_par_execute_kernel, dim3(n_chunks), dim3(ZX_T), 0, st, A);
         if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     }
     TS_LAUNCH_P(prof, "zstd_dec_frames", zstd_dec_frames_kernel, dim3((n_chunks + ZD_WPB - 1) / ZD_WPB), dim3(ZD_WPB * 32),
