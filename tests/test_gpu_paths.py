@@ -1,43 +1,13 @@
-"""Variants that are off by default and have not been timed yet: the two-launch compressor (TSGPU_ENC_SPLIT=1, DESIGN.md
-§4.2) and the parallel general decode path (TSGPU_DEC_PARALLEL=1, §4.3).  They have only ever run on the emulator, so their
-B200 tests are opt-in (TSGPU_TEST_EXPERIMENTAL=1; `scripts/gpu_round.sh` sets it) until a GPU run has seen them pass —
-an unverified variant must not be able to turn the default suite red.  The key-table test below is default behaviour and
-always runs."""
-import os
-
+"""-m gpu tests of which path runs: key tables across calls, libzstd-written frames through the whole-frame executor, this
+library's frames region by region, identical frames on repeated runs."""
 import numpy as np
 import pytest
-
-experimental = pytest.mark.skipif(os.environ.get("TSGPU_TEST_EXPERIMENTAL", "") != "1",
-                                  reason="opt-in: variant not yet verified on a GPU (set TSGPU_TEST_EXPERIMENTAL=1)")
 
 from oracle import oracle as ora
 import tsgpu
 from tsgpu import corpus
 
 Z, A = tsgpu.FLAG_ZSTD, tsgpu.FLAG_AES
-
-
-@pytest.mark.gpu
-@experimental
-def test_gpu_two_launch_compressor(monkeypatch):
-    monkeypatch.setenv("TSGPU_ENC_SPLIT", "1")
-    ctx = tsgpu.Context(max_chunk_bytes=1 << 20, max_batch=8)
-    try:
-        ctx.profile_enable(True)
-        for kind, n, cs in (("K", 5 * (1 << 20) + 777, 1 << 20), ("R", 300000, 65536), ("Z", 70000, 0)):
-            src = corpus.gen_segment(kind, 3, n, cs if cs else n)
-            nch = (n + cs - 1) // cs if cs else 1
-            key, aad, ivs = corpus.fixed_key_material(nch)
-            out, sizes = ctx.transform(Z | A, src, cs, key, aad, ivs)
-            back, _ = ora.detransform_chunks(Z | A, out, sizes, n, key, aad)
-            assert np.array_equal(back, src)
-            mine, _ = ctx.detransform(Z | A, out, sizes, n, key, aad)
-            assert np.array_equal(mine, src)
-        names = set(ctx.profile_report())
-        assert "zstd_enc_parse" in names and "zstd_enc_entropy" in names and "zstd_enc_blocks" not in names
-    finally:
-        ctx.close()
 
 
 @pytest.mark.gpu
@@ -60,10 +30,8 @@ def test_gpu_key_tables_follow_the_key_across_calls():
 
 
 @pytest.mark.gpu
-@experimental
-def test_gpu_parallel_general_path(monkeypatch):
-    # TSGPU_DEC_PARALLEL=1: libzstd-written frames, entropy stage per block in parallel + execution per frame
-    monkeypatch.setenv("TSGPU_DEC_PARALLEL", "1")
+def test_gpu_decode_paths_libzstd_frames_and_own_regions():
+    # libzstd-written frames: entropy stage per block in parallel + one CTA executing the frame; own frames: region by region
     ctx = tsgpu.Context(max_chunk_bytes=4 << 20, max_batch=4)
     try:
         ctx.profile_enable(True)
@@ -72,6 +40,8 @@ def test_gpu_parallel_general_path(monkeypatch):
             frame = np.frombuffer(ora.zstd_compress_level(src, level), dtype=np.uint8)
             back, osz = ctx.detransform(Z, frame, [frame.size], n)
             assert osz == [n] and np.array_equal(back, src), (kind, n, level)
+        st0 = ctx.decode_path_stats()
+        assert st0["whole_frames"] == 5 and st0["regions"] == 0 and st0["serial_frames"] == 0
         srcs = [corpus.gen_chunk("K", 9 + i, 0, 1 << 20) for i in range(3)]
         frames = [np.frombuffer(ora.zstd_compress_chunk(s), dtype=np.uint8) for s in srcs]
         mine, msz = ctx.transform(Z, srcs[0], 0)
@@ -79,7 +49,9 @@ def test_gpu_parallel_general_path(monkeypatch):
         back, _ = ctx.detransform(Z, np.concatenate(frames), [f.size for f in frames], 4 << 20)
         assert np.array_equal(back, np.concatenate(srcs + [srcs[0]]))
         names = set(ctx.profile_report())
-        assert "zstd_dec_par_entropy" in names and "zstd_dec_par_execute" in names
+        assert "zstd_dec_entropy" in names and "zstd_dec_frame_exec" in names and "zstd_dec_regions" in names
+        st1 = ctx.decode_path_stats()
+        assert st1["whole_frames"] == 8 and st1["regions"] == 16 and st1["region_fallback_frames"] == 0
         rng = np.random.default_rng(4)
         for trial in range(40):
             bad = frames[1].copy()
@@ -88,5 +60,20 @@ def test_gpu_parallel_general_path(monkeypatch):
                 ctx.detransform(Z, bad, [bad.size], 1 << 20)
             except tsgpu.TsgpuError as e:
                 assert e.code == tsgpu.binding.E_CORRUPT
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_frames_are_identical_across_runs():
+    # hash-slot winners are deterministic (highest position of a step): the same input gives the same object every time
+    ctx = tsgpu.Context(max_chunk_bytes=4 << 20, max_batch=8)
+    try:
+        src = corpus.gen_segment("K", 5, 24 << 20, 4 << 20)
+        first, fs = ctx.transform(Z, src, 4 << 20)
+        first = first.copy()
+        for _ in range(4):
+            again, sz = ctx.transform(Z, src, 4 << 20)
+            assert sz == fs and np.array_equal(again, first)
     finally:
         ctx.close()

@@ -24,6 +24,7 @@ SYMBOLS = [
     "tsgpu_transform_device", "tsgpu_detransform_device", "tsgpu_launch_count", "tsgpu_chunk_positions",
     "tsgpu_chunk_sizes_encode", "tsgpu_chunk_sizes_decode", "tsgpu_transformed_chunks_serialize",
     "tsgpu_transformed_chunks_deserialize", "tsgpu_chunk_index_json", "tsgpu_profile_enable", "tsgpu_profile_report",
+    "tsgpu_decode_path_stats",
 ]
 
 
@@ -65,6 +66,7 @@ def load(path=None):
     L.tsgpu_detransform_device.argtypes = [vp, C.c_int, u32, vp, u64, vp, u32, u32, vp, vp, u32, vp, vp, vp, vp]
     L.tsgpu_launch_count.restype = u64
     L.tsgpu_launch_count.argtypes = [vp]
+    L.tsgpu_decode_path_stats.argtypes = [vp, vp]
     L.tsgpu_profile_enable.argtypes = [vp, C.c_int]
     L.tsgpu_profile_report.argtypes = [vp, C.c_char_p, C.POINTER(u32)]
     L.tsgpu_chunk_positions.argtypes = [vp, vp, u32, vp]
@@ -123,6 +125,12 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.tsgpu_launch_count(self._h))
+
+    def decode_path_stats(self):
+        """{'regions': n, 'region_fallback_frames': n, 'whole_frames': n, 'serial_frames': n} since the context was created"""
+        v = (C.c_uint64 * 4)()
+        self._check(self.lib.tsgpu_decode_path_stats(self._h, v))
+        return dict(zip(("regions", "region_fallback_frames", "whole_frames", "serial_frames"), [int(x) for x in v]))
 
     def profile_enable(self, on=True):
         self._check(self.lib.tsgpu_profile_enable(self._h, 1 if on else 0))

@@ -57,25 +57,26 @@ struct ZdWarpCtx {                        // per-warp shared-memory working set 
 struct ZstdDecScratch {
     uint32_t* blk_off = nullptr;     // n_chunks * (blocks_per_chunk + 1)
     uint32_t* info = nullptr;        // n_chunks * 8: fcs, nblk, eligible, need_general, first_block_off, ...
-    uint8_t* lits_fast = nullptr;    // n_chunks * blocks_per_chunk * (ZB + 64)
     uint8_t* lits_general = nullptr; // n_chunks * ZD_LIT_GENERAL
     uint64_t* pos_tmp = nullptr;     // n_chunks + 1
     uint32_t blocks_per_chunk = 0, max_batch = 0, chunk_cap = 0;
-    // parallel general path (TSGPU_DEC_PARALLEL=1): per-block results of the entropy stage + per-frame arenas
-    bool par = false;
+    // per-block results of the entropy stage + per-frame arenas
     uint8_t* par_meta = nullptr;     // n_chunks * blocks_per_chunk * sizeof(ZdBlkMeta)
     uint8_t* par_lits = nullptr;     // n_chunks * par_lit_cap
     uint64_t* par_seqs = nullptr;    // n_chunks * par_seq_cap
     uint32_t par_lit_cap = 0, par_seq_cap = 0;
+    unsigned long long* stats = nullptr;   // [0] regions executed in shared memory, [1] frames sent to the frame executor after a
+                                           // region refused, [2] frames executed whole (libzstd-shaped), [3] frames on the serial kernel
 };
 
 struct ZstdDecArgs {
     const uint8_t* in_base; const uint64_t* in_off; const uint32_t* in_len;
     uint8_t* out_base; const uint64_t* out_off; uint32_t* out_len; uint32_t* status;
-    uint32_t* blk_off; uint32_t* info; uint8_t* lits_fast; uint8_t* lits_general;
+    uint32_t* blk_off; uint32_t* info; uint8_t* lits_general;
     uint32_t blocks_per_chunk, chunk_cap, n_chunks;
     uint32_t in_cap;                 // bytes a frame can occupy in its input slot: a longer in_len (device-resident, untrusted) is corrupt
-    uint32_t par; uint8_t* par_meta; uint8_t* par_lits; uint64_t* par_seqs; uint32_t par_lit_cap, par_seq_cap;
+    uint8_t* par_meta; uint8_t* par_lits; uint64_t* par_seqs; uint32_t par_lit_cap, par_seq_cap;
+    unsigned long long* stats;
 };
 constexpr int ZD_INFO = 8;     // fcs, nblk, fast-path eligible, need_general / failed, header size, parallel-general, literal bump, sequence bump
 
@@ -606,7 +607,7 @@ __device__ __forceinline__ void zx_warp_copy(uint8_t* dst, const uint8_t* src, u
 __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, const uint32_t* bo, const ZdBlkMeta* meta,
                                                       uint32_t b_first, uint32_t b_last, uint8_t* out, uint32_t out_cap,
                                                       const uint8_t* lit_arena, const uint64_t* seq_arena, uint32_t frame_len,
-                                                      ZxShared* sh, uint32_t tid) {
+                                                      ZxShared* sh, uint32_t tid, bool no_carried_reps) {
     const uint32_t lane = tid & 31, w = tid >> 5;
     uint32_t op = 0;
     if (tid == 0) { sh->rep[0] = 1; sh->rep[1] = 4; sh->rep[2] = 8; sh->err = 0; }
@@ -656,7 +657,7 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
                 if (of & ZD_OFF_SYM) {
                     const uint32_t k = (of >> 27) & 3, d = of & 0x7ffffffu;
                     const uint32_t r = k == 1 ? R0 : k == 2 ? R1 : R2;
-                    if (r <= d) bad = true; else off = r - d;
+                    if (r <= d || no_carried_reps) bad = true; else off = r - d;      // a region cannot know what earlier regions left behind
                 } else off = of;
                 if (off == 0) bad = true;
             }
@@ -863,71 +864,25 @@ __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_consta
     }
     if (!ok) { A.status[chunk] = ZD_ST_CORRUPT; info[3] = 2; return; }
     info[1] = nblk;
-    info[2] = (last && nblk == want && nblk <= A.blocks_per_chunk) ? 1 : 0;      // eligible for the per-block path
-    // libzstd-shaped frames (few large blocks): entropy-decode the blocks in parallel when that variant is switched on
-    info[5] = (A.par && !info[2] && last && nblk <= A.blocks_per_chunk) ? 1 : 0;
+    // Frames whose blocks look like this library's (ceil(FCS / 8 KiB) blocks) are first tried region by region (64 KiB of
+    // output per CTA, assembled in shared memory); every assumption is verified while executing and a violation only sends
+    // the frame to the frame-level executor.
+    info[2] = (last && nblk == want && nblk <= A.blocks_per_chunk) ? 1 : 0;
+    info[5] = (last && nblk <= A.blocks_per_chunk) ? 1 : 0;                       // entropy stage per block + CTA executors (else: serial kernel)
 }
 
-// ------------------------------------------------------------------------------------------ kernel 2: per-block fast path
-// The block's output is assembled in shared memory (matches then read shared memory instead of paying an L2 round
-// trip per dependent copy) and flushed to HBM once, coalesced.
-constexpr int ZD_WPB_FAST = 1;
-constexpr uint32_t ZD_FAST_WARP_BYTES = (uint32_t)((sizeof(ZdWarpCtx) + 15) & ~15u) + ZB;
-__global__ void __launch_bounds__(ZD_WPB_FAST * 32) zstd_dec_blocks_kernel(const __grid_constant__ ZstdDecArgs A) {
-    TS_DYN_SMEM(smem);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t chunk = blockIdx.y, b = blockIdx.x * ZD_WPB_FAST + warp;
-    uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
-    if (!info[2] || info[3] == 2 || b >= info[1]) return;
-    ZdWarpCtx* cx = (ZdWarpCtx*)(smem + (size_t)warp * ZD_FAST_WARP_BYTES);
-    uint8_t* obuf = (uint8_t*)cx + ((sizeof(ZdWarpCtx) + 15) & ~15u);
-    const uint32_t fcs = info[0];
-    const uint8_t* p = A.in_base + A.in_off[chunk];
-    const uint32_t n = A.in_len[chunk];
-    const uint32_t pos = A.blk_off[(size_t)chunk * (A.blocks_per_chunk + 1) + b];
-    const uint32_t h = p[pos] | (p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16);
-    const uint32_t type = (h >> 1) & 3, bsz = h >> 3;
-    const uint32_t expect = min(ZB, fcs - b * ZB);
-    uint8_t* dst = A.out_base + A.out_off[chunk] + (size_t)b * ZB;
-    if (lane == 0) {
-        cx->err = 0; cx->huf_valid = 0; cx->ll_valid = 0; cx->ml_valid = 0; cx->of_valid = 0;
-        cx->rep[0] = 1; cx->rep[1] = 4; cx->rep[2] = 8;
-    }
-    __syncwarp();
-    uint32_t produced = 0;
-    if (type == 0) {                                     // Raw_Block
-        if (bsz != expect || pos + 3 + bsz > n) { if (lane == 0) cx->err = 1; }
-        else { for (uint32_t k = lane; k < bsz; k += 32) dst[k] = p[pos + 3 + k]; produced = bsz; }
-    } else if (type == 1) {                              // RLE_Block
-        if (bsz != expect) { if (lane == 0) cx->err = 1; }
-        else { const uint8_t v = p[pos + 3]; for (uint32_t k = lane; k < bsz; k += 32) dst[k] = v; produced = bsz; }
-    } else {
-        uint8_t* litbuf = A.lits_fast + ((size_t)chunk * A.blocks_per_chunk + b) * (ZB + 64);
-        produced = zd_compressed_block(p + pos + 3, bsz, obuf, 0, expect, cx, litbuf, ZB, b != 0, lane);
-        __syncwarp();
-        if (cx->err == 0 && produced == expect) {        // flush: 128-bit stores when the destination allows
-            if ((((uintptr_t)dst) & 15) == 0) {
-                for (uint32_t k = lane * 16; k + 16 <= produced; k += 512) *(uint4*)(dst + k) = *(const uint4*)(obuf + k);
-                for (uint32_t k = (produced & ~15u) + lane; k < produced; k += 32) dst[k] = obuf[k];
-            } else {
-                for (uint32_t k = lane; k < produced; k += 32) dst[k] = obuf[k];
-            }
-        }
-    }
-    __syncwarp();
-    if (lane == 0 && (cx->err != 0 || produced != expect)) atomicOr(&info[3], 1u);   // let the general path decide
-}
-
-// ------------------------------------------------------------------------------------------ kernel 3: general path
+// ------------------------------------------------------------------------------------------ kernel 4: serial fallback
+// One warp per frame, blocks in order.  Only frames the parallel stages hand back (a sequence field too wide for the packed
+// sequence word, more blocks than the index holds) come here.
 __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_frames_kernel(const __grid_constant__ ZstdDecArgs A) {
     TS_DYN_SMEM(smem);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * ZD_WPB + warp;
     if (chunk >= A.n_chunks) return;
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
-    if (info[3] == 2) return;                            // already failed in the index pass
-    if (info[2] && info[3] == 0) return;                 // the per-block path finished this frame
-    if (info[5]) return;                                 // the parallel general path owns this frame
+    if (info[3] & 2) return;                             // already failed in the index pass
+    if (info[5]) return;                                 // the parallel stages own this frame
+    if (lane == 0) atomicAdd(&A.stats[3], 1ull);
     ZdWarpCtx* cx = (ZdWarpCtx*)(smem + (size_t)warp * sizeof(ZdWarpCtx));
     const uint32_t fcs = info[0];
     const uint8_t* p = A.in_base + A.in_off[chunk];
@@ -1049,20 +1004,62 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_entropy_kernel(const
     if (lane == 0) meta->status = cx->err == 0 ? 1u : cx->err == 2 ? 3u : 2u;
 }
 
-// 3b: one CTA per frame — execution stage (zx_execute_blocks) straight into the frame's output in HBM.
-__global__ void __launch_bounds__(ZX_T) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
+// 3b: one CTA per 64 KiB REGION of frames that look like this library's: the region's 8 blocks are executed into shared
+// memory (matches never leave the region, so every dependent copy is a shared-memory access) and flushed with 128-bit
+// stores.  Anything unexpected — an offset reaching before the region, a repeat offset carried in from an earlier region,
+// a region that does not regenerate exactly its share — sends the whole frame to the frame-level executor below.
+constexpr uint32_t ZX_REGION_SMEM = ZR;
+__global__ void __launch_bounds__(ZX_T, 2) zstd_dec_regions_kernel(const __grid_constant__ ZstdDecArgs A) {
+    TS_DYN_SMEM(obuf);
+    __shared__ ZxShared sh;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t chunk = blockIdx.y, region = blockIdx.x;
+    uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
+    if (!info[5] || !info[2] || (info[3] & 2)) return;
+    const uint32_t fcs = info[0], nblk = info[1];
+    if ((uint64_t)region * ZR >= fcs) return;
+    const uint32_t want = min(ZR, fcs - region * ZR);
+    const uint32_t b0 = region * ZR_SLICES, b1 = min(nblk, b0 + ZR_SLICES);
+    const uint8_t* p = A.in_base + A.in_off[chunk];
+    const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
+    const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
+    const uint32_t made = zx_execute_blocks(p, bo, meta, b0, b1, obuf, want,
+                                            A.par_lits + (size_t)chunk * A.par_lit_cap, A.par_seqs + (size_t)chunk * A.par_seq_cap,
+                                            A.in_len[chunk], &sh, tid, region != 0);
+    if (sh.err || made != want) {
+        if (tid == 0) {
+            if (sh.err == 3) info[5] = 0;                                 // a field too wide for the sequence word: serial kernel
+            else atomicOr(&info[3], 1u);                                  // not regional after all (or corrupt): the frame executor decides
+        }
+        return;
+    }
+    if (tid == 0) atomicAdd(&A.stats[0], 1ull);
+    uint8_t* dst = A.out_base + A.out_off[chunk] + (size_t)region * ZR;
+    if ((((uintptr_t)dst) & 15) == 0) {
+        for (uint32_t k = tid * 16; k + 16 <= made; k += ZX_T * 16) stg128_stream((uint4*)(dst + k), *(const uint4*)(obuf + k));
+        for (uint32_t k = (made & ~15u) + tid; k < made; k += ZX_T) dst[k] = obuf[k];
+    } else {
+        for (uint32_t k = tid; k < made; k += ZX_T) dst[k] = obuf[k];
+    }
+}
+
+// 3c: one CTA per frame — execution stage straight into the frame's output in HBM (what libzstd-written frames need: their
+// matches reach back up to the whole window).
+__global__ void __launch_bounds__(ZX_T, 2) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
     __shared__ ZxShared sh;
     const uint32_t tid = threadIdx.x;
     const uint32_t chunk = blockIdx.x;
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
-    if (!info[5] || info[3] == 2) return;
+    if (!info[5] || (info[3] & 2)) return;
+    if (info[2] && !(info[3] & 1)) return;                                // the region executors finished this frame
+    if (tid == 0) atomicAdd(&A.stats[info[2] ? 1 : 2], 1ull);
     const uint32_t fcs = info[0], nblk = info[1];
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
     const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
     const uint32_t made = zx_execute_blocks(p, bo, meta, 0, nblk, A.out_base + A.out_off[chunk], fcs,
                                             A.par_lits + (size_t)chunk * A.par_lit_cap, A.par_seqs + (size_t)chunk * A.par_seq_cap,
-                                            A.in_len[chunk], &sh, tid);
+                                            A.in_len[chunk], &sh, tid, false);
     if (tid == 0) {
         if (sh.err == 3) info[5] = 0;                                     // a field too wide for the sequence word: the serial kernel decodes this frame
         else if (sh.err || made != fcs) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; }
@@ -1071,28 +1068,28 @@ __global__ void __launch_bounds__(ZX_T) zstd_dec_par_execute_kernel(const __grid
 
 // ------------------------------------------------------------------------------------------ host side
 inline const char* zstd_dec_scratch_alloc(ZstdDecScratch& s, uint32_t chunk_cap, uint32_t max_batch) {
-    s.blocks_per_chunk = (chunk_cap + ZB - 1) / ZB;
-    if (s.blocks_per_chunk == 0) s.blocks_per_chunk = 1;
+    s.blocks_per_chunk = ((chunk_cap + ZR - 1) / ZR) * ZR_SLICES;        // whole regions of 8 KiB blocks
+    if (s.blocks_per_chunk == 0) s.blocks_per_chunk = ZR_SLICES;
     s.max_batch = max_batch; s.chunk_cap = chunk_cap;
     const char* e;
     if ((e = rt::malloc_device((void**)&s.blk_off, (size_t)max_batch * (s.blocks_per_chunk + 1) * 4 + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.info, (size_t)max_batch * ZD_INFO * 4 + 256))) return e;
-    if ((e = rt::malloc_device((void**)&s.lits_fast, (size_t)max_batch * s.blocks_per_chunk * (ZB + 64) + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.lits_general, (size_t)max_batch * ZD_LIT_GENERAL + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.pos_tmp, (size_t)(max_batch + 1) * 8 + 256))) return e;
-    { const char* v = getenv("TSGPU_DEC_PARALLEL"); s.par = !(v && atoi(v) == 0); }     // on by default (TSGPU_DEC_PARALLEL=0: serial general path only)
-    if (s.par) {
-        s.par_lit_cap = (uint32_t)(((uint64_t)chunk_cap + 16ull * (s.blocks_per_chunk + 1) + 4096 + 15) & ~15ull);
-        s.par_seq_cap = chunk_cap / 3 + 64;
-        if ((e = rt::malloc_device((void**)&s.par_meta, (size_t)max_batch * s.blocks_per_chunk * sizeof(ZdBlkMeta) + 256))) return e;
-        if ((e = rt::malloc_device((void**)&s.par_lits, (size_t)max_batch * s.par_lit_cap + 256))) return e;
-        if ((e = rt::malloc_device((void**)&s.par_seqs, (size_t)max_batch * s.par_seq_cap * 8 + 256))) return e;
-    }
+    s.par_lit_cap = (uint32_t)(((uint64_t)chunk_cap + 16ull * (s.blocks_per_chunk + 1) + 4096 + 15) & ~15ull);
+    s.par_seq_cap = chunk_cap / 3 + 64;
+    if ((e = rt::malloc_device((void**)&s.par_meta, (size_t)max_batch * s.blocks_per_chunk * sizeof(ZdBlkMeta) + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.par_lits, (size_t)max_batch * s.par_lit_cap + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.par_seqs, (size_t)max_batch * s.par_seq_cap * 8 + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.stats, 64))) return e;
+    if ((e = rt::memset_async(s.stats, 0, 64, nullptr))) return e;
+    if ((e = rt::device_sync())) return e;                   // the work streams do not order themselves behind the null stream
     return nullptr;
 }
 inline void zstd_dec_scratch_free(ZstdDecScratch& s) {
-    rt::free_device(s.blk_off); rt::free_device(s.info); rt::free_device(s.lits_fast); rt::free_device(s.lits_general);
+    rt::free_device(s.blk_off); rt::free_device(s.info); rt::free_device(s.lits_general);
     rt::free_device(s.pos_tmp); rt::free_device(s.par_meta); rt::free_device(s.par_lits); rt::free_device(s.par_seqs);
+    rt::free_device(s.stats);
     s = ZstdDecScratch{};
 }
 
@@ -1100,12 +1097,10 @@ constexpr uint32_t ZD_SMEM_BYTES = ZD_WPB * sizeof(ZdWarpCtx);
 
 inline const char* zstd_kernels_configure() {
     const char* e;
-    if ((e = rt::allow_smem(zstd_enc_blocks_kernel, ZE_SMEM_BYTES))) return e;
-    if ((e = rt::allow_smem(zstd_enc_parse_kernel, ZE_SMEM_BYTES))) return e;
-    if ((e = rt::allow_smem(zstd_enc_entropy_kernel, ZE_SMEM_BYTES))) return e;
-    if ((e = rt::allow_smem(zstd_dec_blocks_kernel, ZD_WPB_FAST * ZD_FAST_WARP_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_enc_regions_kernel, ZE_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_frames_kernel, ZD_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_par_entropy_kernel, ZD_SMEM_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_dec_regions_kernel, ZX_REGION_SMEM))) return e;
     return nullptr;
 }
 
@@ -1120,10 +1115,10 @@ inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8
     ZstdDecArgs A;
     A.in_base = in_base; A.in_off = d_in_off; A.in_len = d_in_len;
     A.out_base = out_base; A.out_off = d_out_off; A.out_len = d_out_len; A.status = d_status;
-    A.blk_off = s.blk_off; A.info = s.info; A.lits_fast = s.lits_fast; A.lits_general = s.lits_general;
+    A.blk_off = s.blk_off; A.info = s.info; A.lits_general = s.lits_general;
     A.blocks_per_chunk = s.blocks_per_chunk; A.chunk_cap = chunk_cap; A.n_chunks = n_chunks; A.in_cap = in_cap;
-    A.par = s.par ? 1u : 0u; A.par_meta = s.par_meta; A.par_lits = s.par_lits; A.par_seqs = s.par_seqs;
-    A.par_lit_cap = s.par_lit_cap; A.par_seq_cap = s.par_seq_cap;
+    A.par_meta = s.par_meta; A.par_lits = s.par_lits; A.par_seqs = s.par_seqs;
+    A.par_lit_cap = s.par_lit_cap; A.par_seq_cap = s.par_seq_cap; A.stats = s.stats;
     const char* e;
     TS_LAUNCH_P(prof, "zstd_dec_index", zstd_dec_index_kernel, dim3((n_chunks + 3) / 4), dim3(128), 0, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
@@ -1132,18 +1127,16 @@ inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8
         if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
         if ((e = rt::d2d(d_out_off, s.pos_tmp, 8ull * n_chunks, st))) { g_zstd_err = e; return -7; }
     }
-    const uint32_t bpc = (chunk_cap + ZB - 1) / ZB;
-    TS_LAUNCH_P(prof, "zstd_dec_blocks", zstd_dec_blocks_kernel, dim3((bpc + ZD_WPB_FAST - 1) / ZD_WPB_FAST, n_chunks), dim3(ZD_WPB_FAST * 32),
-                ZD_WPB_FAST * ZD_FAST_WARP_BYTES, st, A);
+    const uint32_t rpc = (chunk_cap + ZR - 1) / ZR ? (chunk_cap + ZR - 1) / ZR : 1;
+    const uint32_t bpc = rpc * ZR_SLICES;
+    TS_LAUNCH_P(prof, "zstd_dec_entropy", zstd_dec_par_entropy_kernel, dim3((bpc + ZD_WPB - 1) / ZD_WPB, n_chunks), dim3(ZD_WPB * 32),
+                ZD_SMEM_BYTES, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
-    if (s.par) {
-        TS_LAUNCH_P(prof, "zstd_dec_par_entropy", zstd_dec_par_entropy_kernel, dim3((bpc + ZD_WPB - 1) / ZD_WPB, n_chunks), dim3(ZD_WPB * 32),
-                    ZD_SMEM_BYTES, st, A);
-        if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
-        TS_LAUNCH_P(prof, "zstd_dec_par_execute", zstd_dec_par_execute_kernel, dim3(n_chunks), dim3(ZX_T), 0, st, A);
-        if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
-    }
-    TS_LAUNCH_P(prof, "zstd_dec_frames", zstd_dec_frames_kernel, dim3((n_chunks + ZD_WPB - 1) / ZD_WPB), dim3(ZD_WPB * 32),
+    TS_LAUNCH_P(prof, "zstd_dec_regions", zstd_dec_regions_kernel, dim3(rpc, n_chunks), dim3(ZX_T), ZX_REGION_SMEM, st, A);
+    if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
+    TS_LAUNCH_P(prof, "zstd_dec_frame_exec", zstd_dec_par_execute_kernel, dim3(n_chunks), dim3(ZX_T), 0, st, A);
+    if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
+    TS_LAUNCH_P(prof, "zstd_dec_serial", zstd_dec_frames_kernel, dim3((n_chunks + ZD_WPB - 1) / ZD_WPB), dim3(ZD_WPB * 32),
                 ZD_SMEM_BYTES, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     return 0;

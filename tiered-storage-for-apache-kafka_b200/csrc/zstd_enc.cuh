@@ -6,18 +6,19 @@
 // Parity bar: libzstd decodes every frame to the original bytes and
 // ZSTD_getFrameContentSize(frame) == original size.  Compressed bytes are not expected to equal libzstd's.
 //
-// B200-first decomposition: a chunk is cut into ZB = 8 KiB zstd blocks that never reference each other
-// (no cross-block matches, no repeat offsets, no repeated tables), so a 1 GiB segment is 131,072 independent
-// units instead of 256 sequential ones.
-//   zstd_enc_blocks_kernel    one WARP per block: block staged in shared memory; 32 positions hashed and
-//                             verified per step against a per-warp hash table, greedy left-to-right selection
-//                             by ballot/ffs, match extension per lane then warp-wide; literals (Raw or
-//                             Huffman, see zstd_huf_enc.cuh) + sequences (predefined FSE tables; the three
-//                             state chains run on lanes 0-2, bit packing on all lanes with shuffle prefix sums)
-//   zstd_enc_assemble_kernel  one CTA per chunk: frame header (same form libzstd picks for the size), exclusive
-//                             scan of block sizes, byte-granular gather of the blocks into the frame
-// Everything is integer/byte work on the ALU and shared-memory pipes; there is no dense contraction to put
-// on tensor cores.
+// B200-first decomposition: a chunk is cut into REGIONS of 64 KiB that never reference each other, one CTA (8 warps) per
+// region; a region is 8 zstd blocks of 8 KiB, one warp each.  A 1 GiB segment is 16,384 independent regions / 131,072
+// warps instead of 256 sequential frames.  Inside a region
+//   * matches reach back across the whole region (one 64 KiB window in shared memory): every slice has its own running
+//     hash table (nearest earlier occurrence inside the slice) plus a history table = last occurrence in all EARLIER
+//     slices, built by a hashing pre-pass + an in-place cumulative merge, so that the 8 slices are parsed concurrently
+//     and the result does not depend on warp timing (hash-slot winners are the highest position, deterministically);
+//   * ONE Huffman tree and ONE set of FSE tables serve the region: the first block that needs them carries the
+//     descriptions, the others are Treeless / Repeat_Mode blocks (the statistics of 64 KiB instead of 8 KiB, table
+//     construction amortised 8x, ~100 bytes of descriptions saved per block);
+//   * the region claims its place in the frame by a look-back over the previous regions' sizes and writes its blocks
+//     straight into the frame — no assemble launch, no second pass over the compressed bytes.
+// Everything is integer/byte work on the ALU and shared-memory pipes; there is no dense contraction to put on tensor cores.
 #pragma once
 #include "ts_common.cuh"
 #include "rt.h"
@@ -27,52 +28,86 @@
 
 namespace ts {
 
-constexpr uint32_t ZB = 8192;                  // bytes of original data per zstd block
-#ifndef ZE_TUNE_HLOG                           // the ZE_TUNE_* macros exist for parameter studies (-DZE_TUNE_...=v); the defaults are the product
+constexpr uint32_t ZB = 8192;                  // bytes of original data per zstd block (= per warp)
+constexpr uint32_t ZR_SLICES = 8;              // blocks per region (= warps per CTA)
+constexpr uint32_t ZR = ZB * ZR_SLICES;        // 64 KiB region
+// the ZE_TUNE_* macros exist for parameter studies on the emulator (-DZE_TUNE_...=v); the defaults are the product
+#ifndef ZE_TUNE_HLOG
 #define ZE_TUNE_HLOG 10
+#endif
+#ifndef ZE_TUNE_HLOG_H
+#define ZE_TUNE_HLOG_H 11
+#endif
+#ifndef ZE_TUNE_MIN_MATCH
 #define ZE_TUNE_MIN_MATCH 5
+#endif
+#ifndef ZE_TUNE_LANE_EXT
 #define ZE_TUNE_LANE_EXT 12
 #endif
-constexpr int ZE_HLOG = ZE_TUNE_HLOG;          // per-warp hash table: 2^10 x u16 (position + 1)
+#ifndef ZE_TUNE_BOTH     // n > 0: the earlier slices are consulted even when this slice has a match, and win if n bytes longer
+#define ZE_TUNE_BOTH 2
+#endif
+#ifndef ZE_TUNE_LAZY     // n > 0: a match is passed over when the next position starts one at least n bytes longer
+#define ZE_TUNE_LAZY 1
+#endif
+#ifndef ZE_TUNE_BACK     // bytes a taken match may grow backwards over the literals of its step (libzstd's "catch up")
+#define ZE_TUNE_BACK 31
+#endif
+constexpr int ZE_HLOG = ZE_TUNE_HLOG;          // per-slice hash tables: 2^10 x u16 (region-relative position)
 constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
-constexpr int ZE_WPB = 4;                      // warps (= blocks in flight) per CTA
+constexpr int ZE_HLOG_H = ZE_TUNE_HLOG_H;      // history tables (last occurrence in all earlier slices): 7 of them
+constexpr uint32_t ZE_HSIZE_H = 1u << ZE_HLOG_H;
+constexpr uint32_t ZE_EMPTY = 0xffffu;         // no position: 65535 cannot start a 4-byte match in a 64 KiB region
 constexpr uint32_t ZE_MAXSEQ = ZB / 8;         // sequences kept per block; beyond that the rest goes out as literals
 constexpr uint32_t ZE_MIN_MATCH = ZE_TUNE_MIN_MATCH;   // 5: a 4-byte match costs more bits than four Huffman-coded literals (libzstd level 3 also uses 5)
 constexpr uint32_t ZE_LANE_EXT = ZE_TUNE_LANE_EXT;     // 12: bytes a lane extends its own match beyond the first 4
-constexpr uint32_t ZE_BUF_PAD = 160;
-constexpr uint32_t ZE_SLOT = ZB + 512;         // per-block output slot: 3-byte header + payload (< ZB once accepted; table descriptions are written before that is known)
-constexpr uint32_t ZE_SMEM_WARP = ZB + ZE_BUF_PAD + ZE_HSIZE * 2;   // buf, ht
-static_assert(ZB < 65535 && ZE_MAXSEQ <= 1024, "16-bit hash slots / 7-bit FSE tables assume small blocks");
-// per-tile FSE scratch (codes, state bits) lives in the tail of `buf`: the sequence bit stream staged there is at most
-// ZE_MAXSEQ * 58 bits, which ends below this offset
+constexpr uint32_t ZE_THREADS = ZR_SLICES * 32;
+static_assert(ZR <= 65536 && ZE_MAXSEQ <= 1024, "16-bit hash slots / sequence fields assume 64 KiB regions of 8 KiB blocks");
+
+// ---- shared-memory map of one CTA ----
+// parse phases:   [buf: region bytes + pad][ht_run: 8 x 2 KiB][ht_fin: 8 x 2 KiB][ctl]
+// entropy phases: [8 x per-warp staging (ZE_STAGE bytes) over buf][shared tables over ht_run][tree / table scratch over ht_fin][ctl]
+constexpr uint32_t ZE_STAGE = ZB + 32;                          // per-warp staging: literal streams, then the sequence bit stream
+constexpr uint32_t ZE_BUF_BYTES = ZR_SLICES * ZE_STAGE + 64;    // 65856: region bytes (65536) + zero pad for over-reads
+constexpr uint32_t ZE_HT_BYTES = ZR_SLICES * ZE_HSIZE * 2;
+constexpr uint32_t ZE_HTH_BYTES = (ZR_SLICES - 1) * ZE_HSIZE_H * 2 < 12288 ? 12288 : (ZR_SLICES - 1) * ZE_HSIZE_H * 2;   // also the entropy phases' scratch
+constexpr uint32_t ZE_OFF_RUN = ZE_BUF_BYTES;
+constexpr uint32_t ZE_OFF_FIN = ZE_OFF_RUN + ZE_HT_BYTES;
+constexpr uint32_t ZE_OFF_CTL = ZE_OFF_FIN + ZE_HTH_BYTES;
+constexpr uint32_t ZE_SMEM_BYTES = ZE_OFF_CTL + 512;
+// per-tile FSE scratch (codes, state bits) lives in the tail of a warp's staging area: the sequence bit stream staged there
+// is at most ZE_MAXSEQ * 58 bits, which ends below this offset
 constexpr uint32_t ZE_SEQ_AUX_OFF = ZB - 512;
 static_assert(ZE_MAXSEQ * 58 / 8 + 16 <= ZE_SEQ_AUX_OFF, "sequence bit stream would overlap the FSE tile scratch");
-static_assert(ZE_SEQ_AUX_OFF + 3 * 32 + 3 * 32 * 2 + 3 * 32 <= ZB + ZE_BUF_PAD, "FSE tile scratch must fit the block buffer");
-constexpr uint32_t ZE_SMEM_WARP_AL = (ZE_SMEM_WARP + 15) & ~15u;
+static_assert(ZE_SEQ_AUX_OFF + 3 * 32 + 3 * 32 * 2 + 3 * 32 <= ZE_STAGE, "FSE tile scratch must fit the staging area");
 
 __constant__ zf::SeqTables g_seq_tables = zf::make_seq_tables();
 __constant__ zf::PredefinedCTables g_pre_ctables = zf::make_predefined_ctables();
 
+// Per-block scratch in HBM (L2-resident in practice: written and read back by the same CTA within microseconds).
+constexpr uint32_t ZE_SLOT_A = ZB + 64;        // literal streams (or nothing for Raw / RLE literals)
+constexpr uint32_t ZE_SLOT_B = ZB;             // sequence bit stream
 struct ZstdEncScratch {
-    uint8_t* blk_out = nullptr;      // n_chunks * blocks_per_chunk * ZE_SLOT
-    uint32_t* blk_size = nullptr;    // n_chunks * blocks_per_chunk
-    uint2* seqs = nullptr;           // n_chunks * blocks_per_chunk * ZE_MAXSEQ
-    uint8_t* lits = nullptr;         // n_chunks * blocks_per_chunk * ZB   (literal staging for Huffman)
-    uint32_t* blk_meta = nullptr;    // n_chunks * blocks_per_chunk * 2    (nseq, nlit: only the two-launch variant uses it)
-    bool split = false;              // TSGPU_ENC_SPLIT=1: parse and entropy stage as two launches
-    uint32_t blocks_per_chunk = 0;
+    uint2* seqs = nullptr;           // blocks * ZE_MAXSEQ
+    uint8_t* lits = nullptr;         // blocks * ZB            literals in order
+    uint8_t* slot_a = nullptr;       // blocks * ZE_SLOT_A
+    uint8_t* slot_b = nullptr;       // blocks * ZE_SLOT_B
+    unsigned long long* reg_state = nullptr;   // chunks * regions_per_chunk: look-back words (ready bit 63 | inclusive frame bytes)
+    uint32_t blocks_per_chunk = 0, regions_per_chunk = 0;
     uint32_t max_batch = 0;
 };
 
 struct ZstdEncArgs {
     const uint8_t* in_base; const uint64_t* in_off; const uint32_t* in_len;
-    uint8_t* blk_out; uint32_t* blk_size; uint2* seqs; uint8_t* lits; uint32_t* blk_meta;
-    uint32_t blocks_per_chunk;
+    uint2* seqs; uint8_t* lits; uint8_t* slot_a; uint8_t* slot_b; unsigned long long* reg_state;
+    uint32_t blocks_per_chunk, regions_per_chunk;
     uint8_t* out_base; const uint64_t* out_off; uint32_t* out_len;
 };
 
 // ------------------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ uint32_t ze_hash(uint32_t v) { return (v * 2654435761u) >> (32 - ZE_HLOG); }
+__device__ __forceinline__ uint32_t ze_hash_h(uint32_t v) { return (v * 2654435761u) >> (32 - ZE_HLOG_H); }
+
 
 // number of equal leading bytes (0..4) of two words given their XOR
 __device__ __forceinline__ uint32_t ze_common_bytes(uint32_t x) { return x ? (uint32_t)(__ffs((int)x) - 1) >> 3 : 4u; }
@@ -93,6 +128,18 @@ __device__ __forceinline__ void ze_put_bits(uint32_t* words, uint32_t o, uint64_
     if (sh + nb > 64) atomicOr(&words[w + 2], (uint32_t)(val >> (64 - sh)));
 }
 
+// Hash-table insert where the HIGHEST position of the warp's step wins a shared slot — the hardware would keep an
+// arbitrary one, which made frames differ between runs; retried uploads must produce identical objects.
+__device__ __forceinline__ void ze_insert_max(uint16_t* ht, uint32_t h, uint32_t p, bool valid) {
+    if (valid) ht[h] = (uint16_t)p;
+    while (true) {
+        __syncwarp();
+        const bool lost = valid && ht[h] < p;            // a lower position of this step sits in the slot
+        if (!__any_sync(TS_FULL, lost)) break;
+        if (lost) ht[h] = (uint16_t)p;
+    }
+}
+
 #ifdef TSGPU_SIMT
 static inline unsigned __match_any_sync(unsigned, unsigned v) {
     simt::Warp& w = simt::g_blk->warps[simt::g_cur->warp];
@@ -109,27 +156,37 @@ static inline unsigned __match_any_sync(unsigned, unsigned v) {
 
 #include "zstd_fse_enc.cuh"
 #include "zstd_huf_enc.cuh"
-static_assert(sizeof(ts::ZeCTab) <= ts::ZE_HSIZE * 2 && 2048 <= ts::ZE_HSIZE * 2,
-              "phase B aliases the FSE encoding tables and the 2 KiB Huffman histogram/code table into the hash-table area");
 
 namespace ts {
 
-// ------------------------------------------------------------------------------------------ block compressor
-struct ZeFseShared {      // per-CTA copy of the predefined encoding tables
-    zf::PredefinedCTables t;
+// ------------------------------------------------------------------------------------------ region-wide state (shared memory)
+struct ZeFsePre { zf::PredefinedCTables t; };   // view of the predefined encoding tables in constant memory
+struct ZeRegion {                    // lives in the ctl area
+    uint32_t nseq[ZR_SLICES], nlit[ZR_SLICES];
+    ZeLitBlock lit[ZR_SLICES];
+    uint32_t seq_bytes[ZR_SLICES];   // bytes of the sequence bit stream of each block
+    uint32_t frame_base;             // where this region's first block goes in the frame
+    ZeKind kll, kof, kml;
+    uint32_t desc_bytes;             // FSE table descriptions (without the modes byte)
 };
+static_assert(sizeof(ZeRegion) <= 512, "ctl area");
 
+struct ZeShared {                    // over the ht_run area during the entropy phases
+    uint32_t hist[256];              // literal histogram of the region
+    uint32_t ctab[256];              // Huffman codes
+    uint32_t cnt[ZE_NSYM_LL + ZE_NSYM_ML + ZE_NSYM_OF + 7];   // sequence code histograms, then normalised counts
+    ZeCTab ct;
+    ZeHuf huf;
+    uint8_t desc[3][96];             // FSE table descriptions LL, OF, ML
+    uint32_t desc_len[3];
+};
+static_assert(sizeof(ZeShared) <= ZE_HT_BYTES, "shared tables must fit the running-hash-table area");
+constexpr uint32_t ZE_KIND_SCRATCH = 1024;     // per FSE kind in the ht_fin area (ze_build_kind needs >= 784 bytes)
+static_assert(8192 + 3 * ZE_KIND_SCRATCH <= ZE_HTH_BYTES, "tree scratch (7.5 KiB) + three table scratches must fit the history-table area");
 
-// Encodes the sequences section (everything after the Number_of_Sequences field): the modes byte and table
-// descriptions go straight to `hdr_out` (global), the bit stream is staged in the word buffer `bits` (shared).
-// Returns the bit-stream bytes; *desc_bytes = 1 (modes byte) + table descriptions.  Warp-uniform, N >= 1.
-__device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict__ seqs, uint32_t N, uint32_t* bits, ZeCTab* ct,
-                                                        uint8_t* codes /*[3][32]*/, uint16_t* stv /*[3][32]*/, uint8_t* stn /*[3][32]*/,
-                                                        const ZeFseShared* fs, uint8_t* hdr_out, uint32_t* desc_bytes, uint32_t lane) {
-    // ---- pass 1: code histograms (then normalised counts), in the word buffer beyond ze_build_kind's own scratch
-    uint32_t* cnt = bits + 256;
-    for (uint32_t i = lane; i < ZE_NSYM_LL + ZE_NSYM_ML + ZE_NSYM_OF; i += 32) cnt[i] = 0;
-    __syncwarp();
+// ------------------------------------------------------------------------------------------ sequences of one block
+// Code histograms of one block's sequences, added to the region's counters (shared-memory atomics).
+__device__ __forceinline__ void ze_seq_hist(const uint2* __restrict__ seqs, uint32_t N, uint32_t* cnt, uint32_t lane) {
     uint2 pre = lane < N ? seqs[lane] : make_uint2(0, 0);
     for (uint32_t t0 = 0; t0 < N; t0 += 32) {
         const uint32_t j = t0 + lane;
@@ -141,29 +198,21 @@ __device__ __forceinline__ uint32_t ze_encode_sequences(const uint2* __restrict_
             atomicAdd(&cnt[ZE_NSYM_LL + ZE_NSYM_ML + (uint32_t)zf::highbit32(s.y + 3)], 1u);
         }
     }
-    __syncwarp();
-    // ---- tables (descriptions in stream order LL, OF, ML); `bits` doubles as scratch until it is cleared
-    ZeKind kll, kof, kml;
-    uint8_t* desc = hdr_out + 1;
-    uint32_t dn = ze_build_kind(cnt, ZE_NSYM_LL, N, zf::LL_MAX_LOG, zf::LL_DEFAULT_LOG, fs->t.ll.state, fs->t.ll.sym,
-                                ct->st_ll, ct->sy_ll, (uint8_t*)bits, desc, &kll, true, lane);
-    dn += ze_build_kind(cnt + ZE_NSYM_LL + ZE_NSYM_ML, ZE_NSYM_OF, N, zf::OF_MAX_LOG, zf::OF_DEFAULT_LOG, fs->t.of.state, fs->t.of.sym,
-                        ct->st_of, ct->sy_of, (uint8_t*)bits, desc + dn, &kof, true, lane);
-    dn += ze_build_kind(cnt + ZE_NSYM_LL, ZE_NSYM_ML, N, zf::ML_MAX_LOG, zf::ML_DEFAULT_LOG, fs->t.ml.state, fs->t.ml.sym,
-                        ct->st_ml, ct->sy_ml, (uint8_t*)bits, desc + dn, &kml, true, lane);
-    if (lane == 0) hdr_out[0] = (uint8_t)((kll.mode << 6) | (kof.mode << 4) | (kml.mode << 2));
-    *desc_bytes = 1 + dn;
-    __syncwarp();
-    for (uint32_t i = lane; i < (ZB + ZE_BUF_PAD) / 4; i += 32) bits[i] = 0;
-    __syncwarp();
+}
 
-    // ---- pass 2: encode
+// Bit stream of one block's sequences with the region's tables, staged in the word buffer `bits` (shared, zeroed here).
+// Returns its size in bytes.  Warp-uniform, N >= 1.
+__device__ __forceinline__ uint32_t ze_encode_seq_bits(const uint2* __restrict__ seqs, uint32_t N, uint32_t* bits, const ZeCTab* ct,
+                                                       const ZeKind kll, const ZeKind kof, const ZeKind kml,
+                                                       uint8_t* codes /*[3][32]*/, uint16_t* stv /*[3][32]*/, uint8_t* stn /*[3][32]*/, uint32_t lane) {
+    for (uint32_t i = lane; i < ZE_STAGE / 4; i += 32) bits[i] = 0;
+    __syncwarp();
     uint32_t bitpos = 0;
     uint32_t state = 0;                              // lanes 0..2: OF, ML, LL chains
     const uint16_t* st_tab = lane == 0 ? ct->st_of : lane == 1 ? ct->st_ml : ct->st_ll;
     const zf::FseCSym* sy = lane == 0 ? ct->sy_of : lane == 1 ? ct->sy_ml : ct->sy_ll;
     const bool rle = (lane == 0 ? kof.mode : lane == 1 ? kml.mode : kll.mode) == 1;
-    pre = lane < N ? seqs[N - 1 - lane] : make_uint2(0, 0);
+    uint2 pre = lane < N ? seqs[N - 1 - lane] : make_uint2(0, 0);
     for (uint32_t t0 = 0; t0 < N; t0 += 32) {
         const uint32_t j = t0 + lane;                // stream order: j = 0 is the LAST sequence
         const bool have = j < N;
@@ -244,28 +293,7 @@ __device__ TS_NOINLINE void ze_warp_copy(uint8_t* __restrict__ dst, const uint8_
     if (lane < n - done) dst[done + lane] = src[done + lane];
 }
 
-__global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_blocks_kernel(const __grid_constant__ ZstdEncArgs A) {
-#include "zstd_enc_prologue.inc"
-#include "zstd_enc_parse.inc"
-#include "zstd_enc_emit.inc"
-}
-
-// The same block compressor as two launches (TSGPU_ENC_SPLIT=1; off by default): the parse kernel's hot loop is a few KB
-// of SASS that stays in the instruction caches, instead of competing with the entropy stage's code in one 90 KB kernel.
-// Sequences and literals already travel through global scratch, so the split adds 8 bytes of per-block state.
-__global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_parse_kernel(const __grid_constant__ ZstdEncArgs A) {
-#include "zstd_enc_prologue.inc"
-#include "zstd_enc_parse.inc"
-    (void)fs; (void)last_block; (void)out; (void)stn;              // the prologue is shared with the entropy stage
-    if (lane == 0) { A.blk_meta[2 * gblk] = nseq; A.blk_meta[2 * gblk + 1] = nlit; }
-}
-__global__ void __launch_bounds__(ZE_WPB * 32) zstd_enc_entropy_kernel(const __grid_constant__ ZstdEncArgs A) {
-#include "zstd_enc_prologue.inc"
-    const uint32_t nseq = A.blk_meta[2 * gblk], nlit = A.blk_meta[2 * gblk + 1];
-#include "zstd_enc_emit.inc"
-}
-
-// ------------------------------------------------------------------------------------------ frame assembly
+// ------------------------------------------------------------------------------------------ frame header
 __device__ __forceinline__ uint32_t ze_frame_header(uint8_t* h, uint32_t n) {     // see tshost::zstdFrameHeader
     uint32_t p = 0;
     h[p++] = 0x28; h[p++] = 0xB5; h[p++] = 0x2F; h[p++] = 0xFD;
@@ -279,56 +307,431 @@ __device__ __forceinline__ uint32_t ze_frame_header(uint8_t* h, uint32_t n) {   
     }
     return p;
 }
+__device__ __forceinline__ uint32_t ze_frame_header_size(uint32_t n) {
+    return n <= (1u << 21) ? (n < 256 ? 6u : n < 65536 + 256 ? 7u : 9u) : 10u;
+}
 
-__global__ void __launch_bounds__(256) zstd_enc_assemble_kernel(const __grid_constant__ ZstdEncArgs A) {
-    __shared__ uint32_t pos[1024 + 1];
-    __shared__ uint32_t hdr_len;
-    const uint32_t chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// ------------------------------------------------------------------------------------------ look-back words
+__device__ __forceinline__ void ze_publish(unsigned long long* w, uint64_t inclusive) {
+    __threadfence();
+#ifdef TSGPU_SIMT
+    *w = (1ull << 63) | inclusive;
+#else
+    atomicExch(w, (unsigned long long)((1ull << 63) | inclusive));
+#endif
+}
+__device__ __forceinline__ uint64_t ze_wait(unsigned long long* w) {
+    unsigned long long v;
+#ifdef TSGPU_SIMT
+    v = *w;                                              // the emulator runs CTAs in launch order: the word is already there
+#else
+    do { v = atomicAdd(w, 0ull); } while (!(v >> 63));
+#endif
+    __threadfence();
+    return (uint64_t)(v & ~(1ull << 63));
+}
+
+// ------------------------------------------------------------------------------------------ the region kernel
+__global__ void __launch_bounds__(ZE_THREADS, 2) zstd_enc_regions_kernel(const __grid_constant__ ZstdEncArgs A) {
+    TS_DYN_SMEM(smem);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t chunk = blockIdx.y, region = blockIdx.x;
     const uint32_t clen = A.in_len[chunk];
-    const uint32_t nblk = (clen + ZB - 1) / ZB;
     uint8_t* frame = A.out_base + A.out_off[chunk];
-    const uint32_t* bs = A.blk_size + (size_t)chunk * A.blocks_per_chunk;
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < nblk; base += 1024) {          // chunks of up to 1024 blocks at a time
-        const uint32_t cnt = min(1024u, nblk - base);
-        if (warp == 0) {
-            uint32_t run = carry;
-            for (uint32_t b0 = 0; b0 < cnt; b0 += 32) {
-                const uint32_t i = b0 + lane;
-                const uint32_t v = i < cnt ? bs[base + i] : 0;
-                const uint32_t inc = warp_inclusive_scan_u32(v, lane);
-                if (i < cnt) pos[i] = run + inc - v;
-                run += __shfl_sync(TS_FULL, inc, 31);
-            }
-            if (lane == 0) {
-                pos[cnt] = run;
-                if (base == 0) {
-                    uint8_t h[16];
-                    const uint32_t hl = ze_frame_header(h, clen);
-                    for (uint32_t k = 0; k < hl; k++) frame[k] = h[k];
-                    hdr_len = hl;
-                }
-            }
+    if (clen == 0) {                                     // empty chunk: header + empty last raw block
+        if (region == 0 && tid == 0) {
+            const uint32_t hl = ze_frame_header(frame, 0);
+            frame[hl] = 1; frame[hl + 1] = 0; frame[hl + 2] = 0;
+            A.out_len[chunk] = hl + 3;
         }
-        __syncthreads();
-        const uint32_t hl = hdr_len;
-        for (uint32_t b = warp; b < cnt; b += blockDim.x >> 5) {
-            const uint8_t* s = A.blk_out + ((size_t)chunk * A.blocks_per_chunk + base + b) * ZE_SLOT;
-            ze_warp_copy(frame + hl + pos[b], s, pos[b + 1] - pos[b], lane);
+        return;
+    }
+    if ((uint64_t)region * ZR >= clen) return;           // whole CTA
+    const uint32_t rn = min(ZR, clen - region * ZR);     // bytes of this region
+    const uint32_t nreg = (clen + ZR - 1) / ZR;
+    const uint32_t nslice = (rn + ZB - 1) / ZB;
+    const uint8_t* src = A.in_base + A.in_off[chunk] + (size_t)region * ZR;
+    const size_t gblk = (size_t)chunk * A.blocks_per_chunk + (size_t)region * ZR_SLICES + w;
+    uint2* seqs = A.seqs + gblk * ZE_MAXSEQ;
+    uint8_t* lits = A.lits + gblk * ZB;
+
+    uint8_t* buf = smem;
+    uint16_t* ht_run = (uint16_t*)(smem + ZE_OFF_RUN) + w * ZE_HSIZE;
+    uint16_t* ht_fin_all = (uint16_t*)(smem + ZE_OFF_FIN);
+    ZeRegion* R = (ZeRegion*)(smem + ZE_OFF_CTL);
+
+    // ---- phase 0: stage the region (128-bit loads when the source is aligned), zero the pad, reset the tables
+    if ((((uintptr_t)src) & 15) == 0) {
+        for (uint32_t i = tid * 16; i < rn; i += ZE_THREADS * 16) {
+            if (i + 16 <= rn) *(uint4*)(buf + i) = ldg128_stream((const uint4*)(src + i));
+            else for (uint32_t k = i; k < rn; k++) buf[k] = src[k];
         }
-        carry = pos[cnt];
+    } else {
+        for (uint32_t i = tid; i < rn; i += ZE_THREADS) buf[i] = src[i];
+    }
+    for (uint32_t i = rn + tid; i < ZE_BUF_BYTES; i += ZE_THREADS) buf[i] = 0;
+    for (uint32_t i = tid; i < (ZE_HT_BYTES + ZE_HTH_BYTES) / 4; i += ZE_THREADS) ((uint32_t*)(smem + ZE_OFF_RUN))[i] = 0xffffffffu;
+    __syncthreads();
+
+    const uint32_t s0 = w * ZB;                          // this warp's slice [s0, s1) of the region
+    const uint32_t s1 = min(s0 + ZB, rn);
+    const bool have_slice = s0 < rn;
+
+    // ---- phase 1: history tables.  Pre-pass: last occurrence of every hash inside each slice ...
+    if (have_slice && nslice > 1 && w + 1 < nslice) {    // the last slice's table would serve nobody
+        uint16_t* fin = ht_fin_all + w * ZE_HSIZE_H;
+        for (uint32_t cur = s0; cur < s1; cur += 32) {
+            const uint32_t p = cur + lane;
+            const bool valid = p < s1 && p + 4 <= rn;            // as a SOURCE a position may run over the slice end
+            const uint32_t v = ld_u32_unaligned(buf + p);
+            ze_insert_max(fin, ze_hash_h(v), p, valid);
+        }
+    }
+    __syncthreads();
+    // ... then an in-place cumulative merge: table j becomes "last occurrence in slices 0..j"; slice j+1 consults table j
+    for (uint32_t j = 1; j + 1 < nslice; j++) {
+        uint32_t* cur32 = (uint32_t*)(ht_fin_all + j * ZE_HSIZE_H);
+        const uint32_t* prev32 = (const uint32_t*)(ht_fin_all + (j - 1) * ZE_HSIZE_H);
+        for (uint32_t i = tid; i < ZE_HSIZE_H / 2; i += ZE_THREADS) {
+            const uint32_t c = cur32[i], p = prev32[i];
+            const uint32_t lo = (c & 0xffffu) != ZE_EMPTY ? (c & 0xffffu) : (p & 0xffffu);
+            const uint32_t hi = (c >> 16) != ZE_EMPTY ? (c >> 16) : (p >> 16);
+            cur32[i] = lo | (hi << 16);
+        }
         __syncthreads();
     }
-    if (tid == 0) {
-        uint32_t total = hdr_len + carry;
-        if (nblk == 0) {                                           // empty chunk: header + empty last raw block
-            uint8_t h[16];
-            const uint32_t hl = ze_frame_header(h, 0);
-            for (uint32_t k = 0; k < hl; k++) frame[k] = h[k];
-            frame[hl] = 1; frame[hl + 1] = 0; frame[hl + 2] = 0;
-            total = hl + 3;
+    const uint16_t* ht_hist = w > 0 ? ht_fin_all + (w - 1) * ZE_HSIZE_H : nullptr;
+
+    // ---- phase 2: greedy LZ parse of the slice, 32 positions per step
+    // Selection (which of the 32 candidate matches survive, left to right) is the only serial part and costs a
+    // handful of instructions per taken match; sequences are written by their own lanes in parallel and the step's
+    // literals (the positions no taken match covers) leave in the same step.
+    uint32_t nseq = 0, nlit = 0;
+    if (have_slice) {
+        uint32_t anchor = s0, cur = s0;
+        while (cur + 4 <= s1 && nseq + 8 <= ZE_MAXSEQ) {                // a step adds at most 8 sequences (min match 4)
+            const uint32_t p = cur + lane;
+            const bool valid = p + 4 <= s1;
+            // unaligned 4-byte reads as a rolling pair of aligned words per stream: one new LDS per stream and step
+            const uint32_t* wp = (const uint32_t*)(buf + (p & ~3u));
+            const uint32_t shp = (p & 3) * 8;
+            uint32_t a0 = wp[0], a1 = wp[1];
+            const uint32_t v = __funnelshift_r(a0, a1, shp);
+            const uint32_t h = ze_hash(v);
+            const uint32_t slot = valid ? ht_run[h] : ZE_EMPTY;
+            __syncwarp();
+            ze_insert_max(ht_run, h, p, valid);
+            uint32_t cand = slot != ZE_EMPTY ? slot : 0u;
+            const uint32_t* wc = (const uint32_t*)(buf + (cand & ~3u));
+            uint32_t shc = (cand & 3) * 8;
+            uint32_t c0 = wc[0], c1 = wc[1];
+            bool ok = slot != ZE_EMPTY && __funnelshift_r(c0, c1, shc) == v;
+#if !ZE_TUNE_BOTH
+            if (ht_hist) {                                            // nothing (or a collision) in this slice: the earlier slices
+                const uint32_t hs = (valid && !ok) ? ht_hist[ze_hash_h(v)] : ZE_EMPTY;
+                if (hs != ZE_EMPTY) {
+                    const uint32_t* wh = (const uint32_t*)(buf + (hs & ~3u));
+                    const uint32_t shh = (hs & 3) * 8;
+                    const uint32_t h0 = wh[0], h1 = wh[1];
+                    if (__funnelshift_r(h0, h1, shh) == v) { ok = true; cand = hs; wc = wh; shc = shh; c0 = h0; c1 = h1; }
+                }
+            }
+#endif
+            uint32_t len = 0;
+            if (ok) {
+                len = 4;
+                const uint32_t lim = min(s1 - p, 4 + ZE_LANE_EXT);
+                uint32_t b0 = a0, b1 = a1;
+                for (uint32_t k = 2; len < lim; k++) {
+                    b0 = b1; b1 = wp[k]; c0 = c1; c1 = wc[k];
+                    const uint32_t c = ze_common_bytes(__funnelshift_r(b0, b1, shp) ^ __funnelshift_r(c0, c1, shc));
+                    len += c;
+                    if (c < 4) break;
+                }
+                len = min(len, lim);
+            }
+#if ZE_TUNE_BOTH
+            if (ht_hist) {                                            // experiment: also try the earlier slices, keep the longer
+                const uint32_t hs = valid ? ht_hist[ze_hash_h(v)] : ZE_EMPTY;
+                if (hs != ZE_EMPTY) {
+                    const uint32_t* wh = (const uint32_t*)(buf + (hs & ~3u));
+                    const uint32_t shh = (hs & 3) * 8;
+                    uint32_t h0 = wh[0], h1 = wh[1];
+                    if (__funnelshift_r(h0, h1, shh) == v) {
+                        uint32_t l2 = 4;
+                        const uint32_t lim = min(s1 - p, 4 + ZE_LANE_EXT);
+                        uint32_t b0 = a0, b1 = a1;
+                        for (uint32_t k = 2; l2 < lim; k++) {
+                            b0 = b1; b1 = wp[k]; h0 = h1; h1 = wh[k];
+                            const uint32_t c = ze_common_bytes(__funnelshift_r(b0, b1, shp) ^ __funnelshift_r(h0, h1, shh));
+                            l2 += c;
+                            if (c < 4) break;
+                        }
+                        l2 = min(l2, lim);
+                        if (l2 > len + ZE_TUNE_BOTH - 1) { len = l2; ok = true; cand = hs; }
+                    }
+                }
+            }
+#endif
+            const uint32_t mask = __ballot_sync(TS_FULL, ok && len >= ZE_MIN_MATCH);
+            // Greedy selection, left to right.  Every lane precomputes where its match would end and which candidate would
+            // come next, so one shuffle per taken match walks the chain (the only serial part of the parse).
+            const uint32_t e = lane + len;
+            const uint32_t mnext = e < 32 ? mask & (0xffffffffu << e) : 0u;
+            const uint32_t nxt = mnext ? (uint32_t)__ffs((int)mnext) - 1 : 32u;
+            const bool capped = ok && len == 4 + ZE_LANE_EXT && p + len < s1;
+#if ZE_TUNE_LAZY
+            // lazy evaluation: a match is passed over when the next position starts a clearly longer one
+            const uint32_t len_next = __shfl_down_sync(TS_FULL, len, 1);
+            const bool defer = lane < 31 && ((mask >> (lane + 1)) & 1) && !capped && len_next >= len + ZE_TUNE_LAZY;
+            const uint32_t packed = e | (nxt << 8) | (capped ? 1u << 16 : 0u) | (defer ? 1u << 17 : 0u);
+#else
+            const uint32_t packed = e | (nxt << 8) | (capped ? 1u << 16 : 0u);
+#endif
+            uint32_t taken = 0, pos = 0;
+            uint32_t f = mask ? (uint32_t)__ffs((int)mask) - 1 : 32u;
+            while (f < 32) {
+                const uint32_t info = __shfl_sync(TS_FULL, packed, f);
+                uint32_t end = info & 0xffu, nf = (info >> 8) & 0xffu;
+#if ZE_TUNE_LAZY
+                if (info & (1u << 17)) { f = f + 1; continue; }
+#endif
+                if ((info >> 16) & 1) {                                // warp-wide extension of a long match
+                    uint32_t L = 4 + ZE_LANE_EXT;
+                    const uint32_t off = __shfl_sync(TS_FULL, p - cand, f);
+                    const uint32_t mpos = cur + f;
+                    while (true) {
+                        const uint32_t q = mpos + L + 4 * lane;
+                        uint32_t c = 0;
+                        if (q < s1) {
+                            c = ze_common_bytes(ld_u32_unaligned(buf + q) ^ ld_u32_unaligned(buf + q - off));
+                            c = min(c, s1 - q);
+                        }
+                        const uint32_t stop = __ballot_sync(TS_FULL, c < 4);
+                        if (stop) {
+                            const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
+                            L += 4 * fl + __shfl_sync(TS_FULL, c, fl);
+                            break;
+                        }
+                        L += 128;
+                    }
+                    if (lane == f) len = L;
+                    end = f + L;
+                    const uint32_t m2 = end < 32 ? mask & (0xffffffffu << end) : 0u;
+                    nf = m2 ? (uint32_t)__ffs((int)m2) - 1 : 32u;
+                }
+                taken |= 1u << f;
+                pos = end;
+                f = nf;
+            }
+            uint32_t cov = 0;                                          // positions of this step covered by a taken match
+            if (taken) {
+                const bool mine_taken = (taken >> lane) & 1;
+                const uint32_t my_end = p + len;                       // meaningful on taken lanes
+                const uint32_t lower = taken & ((1u << lane) - 1);
+                const uint32_t prev_lane = lower ? (uint32_t)(31 - __clz((int)lower)) : 0u;
+                uint32_t prev_end = __shfl_sync(TS_FULL, my_end, prev_lane);
+                if (!lower) prev_end = anchor;
+                uint32_t bk = 0;
+#if ZE_TUNE_BACK
+                if (mine_taken) {                                      // catch-up: grow the match backwards over this step's literals
+                    const uint32_t room = min(min(p - max(prev_end, cur), cand), (uint32_t)ZE_TUNE_BACK);
+                    while (bk < room && buf[p - 1 - bk] == buf[cand - 1 - bk]) bk++;
+                }
+#endif
+                if (mine_taken)
+                    seqs[nseq + (uint32_t)__popc(lower)] = make_uint2((p - bk - prev_end) | ((len + bk - 3) << 16), p - cand);
+                nseq += (uint32_t)__popc(taken);
+                anchor = cur + pos;
+                const uint32_t sl = lane - bk, tl = len + bk;          // covered span of the step starts bk lanes earlier
+                const uint32_t span = mine_taken ? (tl >= 32 - sl ? 0xffffffffu << sl : ((1u << tl) - 1) << sl) : 0u;
+                cov = __reduce_or_sync(TS_FULL, span);
+            }
+            // literals of the step, in order: one byte per uncovered position below the end of the slice
+            {
+                const uint32_t inside = s1 - cur >= 32 ? 0xffffffffu : (1u << (s1 - cur)) - 1;
+                const uint32_t lm = ~cov & inside;
+                if ((lm >> lane) & 1) lits[nlit + (uint32_t)__popc(lm & ((1u << lane) - 1))] = (uint8_t)v;
+                nlit += (uint32_t)__popc(lm);
+            }
+            cur = max(cur + 32, anchor);
         }
-        A.out_len[chunk] = total;
+        // the rest of the slice (after the last step, or after the sequence budget ran out) is literals
+        if (cur < s1) {
+            const uint32_t ll = s1 - cur;
+            for (uint32_t k = lane; k < ll; k += 32) lits[nlit + k] = buf[cur + k];
+            nlit += ll;
+        }
+        __syncwarp();
+        __threadfence_block();
+    }
+    if (lane == 0) { R->nseq[w] = nseq; R->nlit[w] = nlit; }
+    __syncthreads();                                                   // ---- the region's bytes and hash tables are dead from here on
+
+    // ---- phase 3: region statistics
+    ZeShared* S = (ZeShared*)(smem + ZE_OFF_RUN);
+    for (uint32_t i = tid; i < sizeof(ZeShared) / 4; i += ZE_THREADS) ((uint32_t*)S)[i] = 0;
+    __syncthreads();
+    if (have_slice) {
+        _Pragma("unroll 2")
+        for (uint32_t i = lane; i < nlit; i += 32) atomicAdd(&S->hist[lits[i]], 1u);
+        ze_seq_hist(seqs, nseq, S->cnt, lane);
+    }
+    __syncthreads();
+    uint32_t nseq_total = 0, nlit_total = 0;
+    for (uint32_t k = 0; k < ZR_SLICES; k++) { nseq_total += R->nseq[k]; nlit_total += R->nlit[k]; }
+
+    // ---- phase 4: one Huffman tree (warp 0) and the three FSE tables (warps 1-3), concurrently
+    {
+        uint8_t* fin_area = smem + ZE_OFF_FIN;
+        if (w == 0) {
+            ze_huf_build(S->hist, S->ctab, (uint32_t*)fin_area, nlit_total, &S->huf, lane);
+        } else if (w <= 3 && nseq_total) {
+            const ZeFsePre& pre = *(const ZeFsePre*)&g_pre_ctables;
+            uint8_t* scratch = fin_area + 8192 + (w - 1) * ZE_KIND_SCRATCH;
+            ZeKind k;
+            uint32_t dn;
+            if (w == 1) dn = ze_build_kind(S->cnt, ZE_NSYM_LL, nseq_total, zf::LL_MAX_LOG, zf::LL_DEFAULT_LOG, pre.t.ll.state, pre.t.ll.sym,
+                                           S->ct.st_ll, S->ct.sy_ll, scratch, S->desc[0], &k, true, lane);
+            else if (w == 2) dn = ze_build_kind(S->cnt + ZE_NSYM_LL + ZE_NSYM_ML, ZE_NSYM_OF, nseq_total, zf::OF_MAX_LOG, zf::OF_DEFAULT_LOG,
+                                                pre.t.of.state, pre.t.of.sym, S->ct.st_of, S->ct.sy_of, scratch, S->desc[1], &k, true, lane);
+            else dn = ze_build_kind(S->cnt + ZE_NSYM_LL, ZE_NSYM_ML, nseq_total, zf::ML_MAX_LOG, zf::ML_DEFAULT_LOG, pre.t.ml.state, pre.t.ml.sym,
+                                    S->ct.st_ml, S->ct.sy_ml, scratch, S->desc[2], &k, true, lane);
+            if (lane == 0) {
+                S->desc_len[w - 1] = dn;
+                if (w == 1) R->kll = k; else if (w == 2) R->kof = k; else R->kml = k;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 5: every warp encodes its block's literal streams and sequence bits (sizes first, nothing placed yet)
+    uint8_t* stage = smem + w * ZE_STAGE;
+    uint8_t* slot_a = A.slot_a + gblk * ZE_SLOT_A;
+    uint8_t* slot_b = A.slot_b + gblk * ZE_SLOT_B;
+    if (have_slice) {
+        ze_huf_plan_block(lits, nlit, S->ctab, &S->huf, &R->lit[w], lane);
+        const ZeLitBlock lb = R->lit[w];
+        if (lb.kind == 2) {
+            ze_huf_encode_block(lits, nlit, S->ctab, lb.stream_bytes, (uint32_t*)stage, lane);
+            ze_warp_copy(slot_a, stage, lb.stream_bytes, lane);
+        }
+        __syncwarp();
+        uint32_t sbytes = 0;
+        if (nseq) {
+            uint8_t* codes = stage + ZE_SEQ_AUX_OFF;
+            uint16_t* stv = (uint16_t*)(codes + 96);
+            uint8_t* stn = (uint8_t*)(stv + 96);
+            sbytes = ze_encode_seq_bits(seqs, nseq, (uint32_t*)stage, &S->ct, R->kll, R->kof, R->kml, codes, stv, stn, lane);
+            ze_warp_copy(slot_b, stage, sbytes, lane);
+        }
+        if (lane == 0) R->seq_bytes[w] = sbytes;
+    }
+    __syncthreads();
+
+    // ---- phase 6: who carries the descriptions, what each block weighs, where the region goes
+    // (every thread computes the same small table from shared memory: 8 entries)
+    uint32_t my_off = 0, my_size = 0, my_lit_type = 0, total = 0;
+    bool my_raw = false, my_seq_owner = false;
+    const uint32_t desc_total = nseq_total ? ((R->kll.mode == 0 ? 0 : S->desc_len[0]) + (R->kof.mode == 0 ? 0 : S->desc_len[1]) +
+                                              (R->kml.mode == 0 ? 0 : S->desc_len[2])) : 0;
+    {
+        bool tree_given = false, desc_given = false;
+        for (uint32_t k = 0; k < nslice; k++) {
+            const uint32_t bn = min(ZB, rn - k * ZB);
+            const ZeLitBlock lb = R->lit[k];
+            const uint32_t nsq = R->nseq[k];
+            const bool tree_here = lb.kind == 2 && !tree_given;
+            const bool desc_here = nsq != 0 && !desc_given;
+            uint32_t lit_sz;
+            if (lb.kind == 0) lit_sz = 3 + lb.n;
+            else if (lb.kind == 1) lit_sz = 3 + 1;
+            else {
+                const uint32_t comp = (tree_here ? S->huf.tree_bytes : 0) + 6 + lb.stream_bytes;
+                lit_sz = ze_lit_header_huf_size(lb.n, comp) + comp;
+            }
+            const uint32_t shdr = nsq == 0 ? 1u : (nsq < 128 ? 1u : 2u) + 1u;      // Number_of_Sequences (+ modes byte)
+            const uint32_t payload = lit_sz + shdr + (desc_here ? desc_total : 0) + R->seq_bytes[k];
+            const bool raw = payload >= bn;                                  // would not shrink (with its duties): Raw_Block, state untouched
+            const uint32_t bsize = 3 + (raw ? bn : payload);
+            if (!raw) { tree_given |= lb.kind == 2; desc_given |= nsq != 0; }
+            if (k == w) { my_off = total; my_size = bsize; my_raw = raw; my_lit_type = lb.kind == 2 ? (tree_here ? 2u : 3u) : lb.kind; my_seq_owner = desc_here; }
+            total += bsize;
+        }
+    }
+    if (tid == 0) {
+        unsigned long long* rs = A.reg_state + (size_t)chunk * A.regions_per_chunk;
+        const uint64_t base = region == 0 ? ze_frame_header(frame, clen) : ze_wait(&rs[region - 1]);
+        R->frame_base = (uint32_t)base;
+        if (region + 1 < nreg) ze_publish(&rs[region], base + total);
+        else A.out_len[chunk] = (uint32_t)(base + total);
+    }
+    __syncthreads();
+
+    // ---- phase 7: every warp writes its block into the frame
+    if (have_slice) {
+        const uint32_t bn = s1 - s0;
+        uint8_t* out = frame + R->frame_base + my_off;
+        const bool last_block = region + 1 == nreg && w + 1 == nslice;
+        if (lane == 0) {
+            const uint32_t hdr = (last_block ? 1u : 0u) | ((my_raw ? 0u : 2u) << 1) | ((my_size - 3) << 3);
+            out[0] = (uint8_t)hdr; out[1] = (uint8_t)(hdr >> 8); out[2] = (uint8_t)(hdr >> 16);
+        }
+        if (my_raw) {
+            ze_warp_copy(out + 3, src + s0, bn, lane);
+        } else {
+            const ZeLitBlock lb = R->lit[w];
+            uint8_t* body = out + 3;
+            uint32_t at = 0;
+            if (lb.kind == 0) {
+                if (lane == 0) ze_lit_header_raw(body, 0, lb.n);
+                ze_warp_copy(body + 3, lits, lb.n, lane);
+                at = 3 + lb.n;
+            } else if (lb.kind == 1) {
+                if (lane == 0) { ze_lit_header_raw(body, 1, lb.n); body[3] = (uint8_t)lb.rle_byte; }
+                at = 4;
+            } else {
+                const uint32_t tb = my_lit_type == 2 ? S->huf.tree_bytes : 0;
+                const uint32_t comp = tb + 6 + lb.stream_bytes;
+                const uint32_t hsz = ze_lit_header_huf_size(lb.n, comp);
+                if (lane == 0) {
+                    ze_lit_header_huf(body, my_lit_type, lb.n, comp);
+                    uint8_t* j = body + hsz + tb;
+                    j[0] = (uint8_t)lb.ssz[0]; j[1] = (uint8_t)(lb.ssz[0] >> 8); j[2] = (uint8_t)lb.ssz[1]; j[3] = (uint8_t)(lb.ssz[1] >> 8);
+                    j[4] = (uint8_t)lb.ssz[2]; j[5] = (uint8_t)(lb.ssz[2] >> 8);
+                }
+                for (uint32_t i = lane; i < tb; i += 32) body[hsz + i] = S->huf.desc[i];
+                ze_warp_copy(body + hsz + tb + 6, slot_a, lb.stream_bytes, lane);
+                at = hsz + comp;
+            }
+            uint8_t* sp = body + at;
+            if (nseq == 0) {
+                if (lane == 0) sp[0] = 0;                              // Number_of_Sequences = 0: the sequences section ends here
+            } else {
+                const uint32_t shdr = nseq < 128 ? 1u : 2u;
+                uint32_t dn = 0;
+                if (lane == 0) {
+                    if (shdr == 1) sp[0] = (uint8_t)nseq;
+                    else { sp[0] = (uint8_t)((nseq >> 8) + 0x80); sp[1] = (uint8_t)nseq; }
+                    // owner: the real modes + descriptions; the others repeat them (Predefined_Mode costs nothing to restate)
+                    const uint32_t mll = R->kll.mode, mof = R->kof.mode, mml = R->kml.mode;
+                    const uint32_t rll = mll == 0 ? 0u : 3u, rof = mof == 0 ? 0u : 3u, rml = mml == 0 ? 0u : 3u;
+                    sp[shdr] = my_seq_owner ? (uint8_t)((mll << 6) | (mof << 4) | (mml << 2)) : (uint8_t)((rll << 6) | (rof << 4) | (rml << 2));
+                }
+                if (my_seq_owner) {
+                    uint8_t* d = sp + shdr + 1;
+                    const uint32_t order[3] = {0, 1, 2};               // stream order LL, OF, ML = desc[0], desc[1], desc[2]
+                    for (uint32_t q = 0; q < 3; q++) {
+                        const uint32_t kmode = q == 0 ? R->kll.mode : q == 1 ? R->kof.mode : R->kml.mode;
+                        if (kmode == 0) continue;
+                        const uint32_t len = S->desc_len[order[q]];
+                        for (uint32_t i = lane; i < len; i += 32) d[dn + i] = S->desc[order[q]][i];
+                        dn += len;
+                    }
+                }
+                ze_warp_copy(sp + shdr + 1 + dn, slot_b, R->seq_bytes[w], lane);
+            }
+        }
     }
 }
 
@@ -337,49 +740,40 @@ static thread_local const char* g_zstd_err = "";
 inline const char* zstd_last_error() { return g_zstd_err; }
 
 inline const char* zstd_enc_scratch_alloc(ZstdEncScratch& s, uint32_t chunk_cap, uint32_t max_batch) {
-    s.blocks_per_chunk = (chunk_cap + ZB - 1) / ZB;
+    s.regions_per_chunk = (chunk_cap + ZR - 1) / ZR;
+    if (s.regions_per_chunk == 0) s.regions_per_chunk = 1;
+    s.blocks_per_chunk = s.regions_per_chunk * ZR_SLICES;
     s.max_batch = max_batch;
     const size_t nblk = (size_t)s.blocks_per_chunk * max_batch;
     const char* e;
-    if ((e = rt::malloc_device((void**)&s.blk_out, nblk * ZE_SLOT + 256))) return e;
-    if ((e = rt::malloc_device((void**)&s.blk_size, nblk * 4 + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.seqs, nblk * ZE_MAXSEQ * sizeof(uint2) + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.lits, nblk * ZB + 256))) return e;
-    if ((e = rt::malloc_device((void**)&s.blk_meta, nblk * 8 + 256))) return e;
-    { const char* v = getenv("TSGPU_ENC_SPLIT"); s.split = v && atoi(v) != 0; }
+    if ((e = rt::malloc_device((void**)&s.slot_a, nblk * ZE_SLOT_A + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.slot_b, nblk * ZE_SLOT_B + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.reg_state, (size_t)s.regions_per_chunk * max_batch * 8 + 256))) return e;
     return nullptr;
 }
 inline void zstd_enc_scratch_free(ZstdEncScratch& s) {
-    rt::free_device(s.blk_out); rt::free_device(s.blk_size); rt::free_device(s.seqs); rt::free_device(s.lits); rt::free_device(s.blk_meta);
+    rt::free_device(s.seqs); rt::free_device(s.lits); rt::free_device(s.slot_a); rt::free_device(s.slot_b); rt::free_device(s.reg_state);
     s = ZstdEncScratch{};
 }
-
-constexpr uint32_t ZE_SMEM_BYTES = ZE_WPB * ZE_SMEM_WARP_AL;
 
 inline int zstd_compress_batch(ZstdEncScratch& s, rt::stream_t st, const uint8_t* in_base, const uint64_t* d_in_off,
                                const uint32_t* d_in_len, uint32_t n_chunks, uint32_t chunk_size,
                                uint8_t* out_base, const uint64_t* d_out_off, uint32_t* d_out_len, LaunchProf& prof) {
     if (n_chunks > s.max_batch) { g_zstd_err = "batch larger than the context"; return -1; }
-    const uint32_t bpc = (chunk_size + ZB - 1) / ZB;
-    if (bpc > s.blocks_per_chunk) { g_zstd_err = "chunk larger than the context"; return -1; }
+    uint32_t rpc = (chunk_size + ZR - 1) / ZR;
+    if (rpc > s.regions_per_chunk) { g_zstd_err = "chunk larger than the context"; return -1; }
+    if (rpc == 0) rpc = 1;                                   // empty chunks still get their frame
     ZstdEncArgs A;
     A.in_base = in_base; A.in_off = d_in_off; A.in_len = d_in_len;
-    A.blk_out = s.blk_out; A.blk_size = s.blk_size; A.seqs = s.seqs; A.lits = s.lits; A.blk_meta = s.blk_meta;
-    A.blocks_per_chunk = s.blocks_per_chunk;
+    A.seqs = s.seqs; A.lits = s.lits; A.slot_a = s.slot_a; A.slot_b = s.slot_b; A.reg_state = s.reg_state;
+    A.blocks_per_chunk = s.blocks_per_chunk; A.regions_per_chunk = s.regions_per_chunk;
     A.out_base = out_base; A.out_off = d_out_off; A.out_len = d_out_len;
-    if (bpc) {
-        const dim3 grid((bpc + ZE_WPB - 1) / ZE_WPB, n_chunks), block(ZE_WPB * 32);
-        if (!s.split) {
-            TS_LAUNCH_P(prof, "zstd_enc_blocks", zstd_enc_blocks_kernel, grid, block, ZE_SMEM_BYTES, st, A);
-        } else {
-            TS_LAUNCH_P(prof, "zstd_enc_parse", zstd_enc_parse_kernel, grid, block, ZE_SMEM_BYTES, st, A);
-            TS_LAUNCH_P(prof, "zstd_enc_entropy", zstd_enc_entropy_kernel, grid, block, ZE_SMEM_BYTES, st, A);
-        }
-        const char* e = rt::last_error();
-        if (e) { g_zstd_err = e; return -7; }
-    }
-    TS_LAUNCH_P(prof, "zstd_enc_assemble", zstd_enc_assemble_kernel, dim3(n_chunks), dim3(256), 0, st, A);
-    const char* e = rt::last_error();
+    const char* e = rt::memset_async(s.reg_state, 0, (size_t)s.regions_per_chunk * n_chunks * 8, st);
+    if (e) { g_zstd_err = e; return -7; }
+    TS_LAUNCH_P(prof, "zstd_enc_regions", zstd_enc_regions_kernel, dim3(rpc, n_chunks), dim3(ZE_THREADS), ZE_SMEM_BYTES, st, A);
+    e = rt::last_error();
     if (e) { g_zstd_err = e; return -7; }
     return 0;
 }

@@ -19,14 +19,14 @@ namespace ts {
 constexpr uint32_t ZE_NSYM_LL = 36, ZE_NSYM_ML = 53, ZE_NSYM_OF = 32;
 constexpr uint32_t ZE_PREDEF_BELOW = 64;          // fewer sequences than this: Predefined_Mode
 
-// Table logs never exceed ZE_MAX_TLOG: FSE_optimalTableLog caps them at highbit(N - 1) - 2 = 7 for N <= 1024 sequences
-// (and at least highbit(max code) + 2 <= 7); the predefined tables are 6 / 6 / 5 bits.
-constexpr uint32_t ZE_MAX_TLOG = 7;
-struct ZeCTab {                                   // per-warp, aliases the (free) hash-table area in phase B
-    uint16_t st_ll[1 << ZE_MAX_TLOG], st_ml[1 << ZE_MAX_TLOG], st_of[1 << ZE_MAX_TLOG];
+// One set of tables per 64 KiB region (up to 8192 sequences): table logs as FSE_optimalTableLog picks them, i.e. up to the
+// format's maxima 9 / 9 / 8 (LL / ML / OF); the predefined tables are 6 / 6 / 5 bits.
+constexpr uint32_t ZE_MAX_TLOG = 9;
+struct ZeCTab {                                   // per region, in the (free) hash-table area during the entropy phases
+    uint16_t st_ll[1 << zf::LL_MAX_LOG], st_ml[1 << zf::ML_MAX_LOG], st_of[1 << zf::OF_MAX_LOG];
     zf::FseCSym sy_ll[ZE_NSYM_LL], sy_ml[ZE_NSYM_ML], sy_of[ZE_NSYM_OF];
 };
-static_assert(sizeof(ZeCTab) <= 2048, "ZeCTab must fit the hash-table area");
+static_assert(sizeof(ZeCTab) <= 4096, "ZeCTab must fit its slot of the hash-table area");
 
 struct ZeKind {                                   // uniform per-kind parameters after table selection
     uint32_t mode;                                // 0 predefined, 1 RLE, 2 FSE compressed
@@ -102,7 +102,7 @@ __device__ TS_NOINLINE uint32_t ze_build_kind(uint32_t* cnt, uint32_t alphabet, 
     if (min_bits > log) log = min_bits;
     if (log < 5) log = 5;
     if (log > max_log) log = max_log;
-    if (log > ZE_MAX_TLOG) log = ZE_MAX_TLOG;                // cannot bind for N <= 1024 (see ZeCTab); keeps the tables in bounds regardless
+    if (log > ZE_MAX_TLOG) log = ZE_MAX_TLOG;                // cannot bind (max_log <= 9); keeps the tables in bounds regardless
     const uint32_t size = 1u << log;
     // normalise: floor share, at least one cell per present code, remainder to (or excess from) the largest codes
     uint32_t p0 = c0 ? max(1u, (uint32_t)(((uint64_t)c0 << log) / N)) : 0u;

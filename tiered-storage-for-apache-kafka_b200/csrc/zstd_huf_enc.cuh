@@ -1,11 +1,13 @@
-// zstd_huf_enc.cuh — literals section of a compressed block (RFC 8878 §3.1.1.3.1, §4.2): Raw, RLE or
-// Huffman-compressed (4 streams, direct 4-bit weight table).  One warp per block, everything in shared memory:
-//   histogram (shared-memory atomics) -> rank sort of the used symbols -> two-queue Huffman merge on lane 0
-//   (depth limited to 11 by halving counts and rebuilding) -> canonical codes in the order the decoder's table
-//   is filled (weight ascending, symbol ascending) -> the four streams packed by all lanes with a shuffle
-//   suffix-scan of code lengths and atomicOr into a zeroed staging buffer.
-// Blocks whose highest used byte value needs more than 128 listed weights (FSE-compressed weight tables) and
-// blocks that Huffman would not shrink fall back to Raw literals.
+// zstd_huf_enc.cuh — literals section of a compressed block (RFC 8878 §3.1.1.3.1, §4.2): Raw, RLE, or Huffman-compressed with
+// ONE tree per 64 KiB region: the first block of the region that uses it carries the tree description
+// (Compressed_Literals_Block), the later ones are Treeless_Literals_Blocks.
+//   ze_huf_build          one warp, once per region: region histogram -> rank sort of the used symbols -> two-queue Huffman
+//                         merge on lane 0 (depth limited to 11 by halving counts and rebuilding) -> canonical codes in the
+//                         order the decoder's table is filled (weight ascending, symbol ascending) -> tree description
+//                         (direct 4-bit weights, or FSE-compressed weights when byte values above 128 occur)
+//   ze_huf_encode_block   one warp per block: exact size first (sum of code lengths per stream), then the four streams
+//                         packed by all lanes with a shuffle suffix-scan of code lengths and atomicOr into a zeroed staging
+//                         buffer in shared memory
 #pragma once
 #include "ts_common.cuh"
 #include "zstd_format.h"
@@ -14,52 +16,34 @@
 
 namespace ts {
 
-// Raw_Literals_Block with the 3-byte header (Size_Format 11: 20-bit Regenerated_Size).
-__device__ TS_NOINLINE uint32_t ze_raw_literals(const uint8_t* __restrict__ lits, uint32_t n, uint8_t* body, uint32_t lane) {
-    if (lane == 0) {
-        body[0] = (uint8_t)((3u << 2) | ((n & 0xf) << 4));
-        body[1] = (uint8_t)(n >> 4);
-        body[2] = (uint8_t)(n >> 12);
-    }
-    for (uint32_t i = lane; i < n; i += 32) body[3 + i] = lits[i];
-    return 3 + n;
-}
-__device__ __forceinline__ uint32_t ze_rle_literals(uint8_t v, uint32_t n, uint8_t* body, uint32_t lane) {
-    if (lane == 0) {
-        body[0] = (uint8_t)(1u | (3u << 2) | ((n & 0xf) << 4));
-        body[1] = (uint8_t)(n >> 4);
-        body[2] = (uint8_t)(n >> 12);
-        body[3] = v;
-    }
-    return 4;
-}
-
-constexpr uint32_t ZE_HUF_MIN = 64;            // below this many literals a table cannot pay for itself
-// FSE-compressed weights also shave ~1.5 % off text-like blocks (tree description 62 -> ~25 bytes per 8 KiB block) but cost
-// ~5 % of the block's time; by default they are used only where direct weights cannot describe the tree (symbols > 128).
+constexpr uint32_t ZE_HUF_MIN = 64;            // below this many literals in a block Huffman streams cannot pay for their 6-byte jump table
+constexpr uint32_t ZE_HUF_REGION_MIN = 256;    // below this many literals in a region a tree cannot pay for itself
+// FSE-compressed weights shave ~1.5 % off text-like data at 8 KiB granularity; with one tree per 64 KiB region the tree is
+// < 0.5 % of the output, so they are used only where direct weights cannot describe the tree (symbols > 128).
 constexpr bool ZE_FSE_WEIGHTS_ALWAYS = false;
 
-// Returns the bytes written at `body`.  `work`: >= ZB + 160 bytes of shared memory (tree scratch, then the
-// stream staging area); `aux16`: 2 KiB of shared memory (histogram + code table).
-__device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict__ lits, uint32_t n, uint8_t* body,
-                                                       uint32_t* work, uint16_t* aux16, uint32_t lane) {
-    if (n < ZE_HUF_MIN) return ze_raw_literals(lits, n, body, lane);
-    uint32_t* hist = (uint32_t*)aux16;         // [256]
-    uint32_t* ctab = hist + 256;               // [256] code | len << 16
+struct ZeHuf {                                 // region-wide result of ze_huf_build (shared memory)
+    uint32_t ok;                               // 0: no usable tree (blocks write Raw / RLE literals)
+    uint32_t tree_bytes;                       // size of the description in `desc`
+    uint32_t max_len;
+    uint8_t desc[132];                         // header byte + weights (direct: <= 1 + 64; FSE-compressed: <= 1 + 127)
+};
+
+// Region-wide tree.  hist[256] (counts, destroyed), ctab[256] out (code | len << 16, 0 = unused symbol), work: >= 7.5 KiB of
+// shared-memory scratch, n = literals in the region.  One warp.
+__device__ TS_NOINLINE void ze_huf_build(uint32_t* hist, uint32_t* ctab, uint32_t* work, uint32_t n, ZeHuf* hf, uint32_t lane) {
     uint32_t* keys = work + 1280;              // [256] used symbols: count << 8 | symbol
     uint32_t* sorted = work;                   // [256]
     uint32_t* nodew = work + 256;              // [512]
     uint16_t* parent = (uint16_t*)(work + 768);   // [512]
     uint8_t* depth = (uint8_t*)(work + 1024);  // [512]
     uint32_t* meta = work + 1200;              // small scalars shared by the warp
-
-    for (uint32_t i = lane; i < 256; i += 32) { hist[i] = 0; ctab[i] = 0; }
+    if (lane == 0) { hf->ok = 0; hf->tree_bytes = 0; hf->max_len = 0; }
+    for (uint32_t i = lane; i < 256; i += 32) ctab[i] = 0;
     __syncwarp();
-    _Pragma("unroll 2")
-    for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[lits[i]], 1u);
-    __syncwarp();
+    if (n < ZE_HUF_REGION_MIN) return;
 
-    // compact the used symbols (8 per lane, ascending symbol order)
+    // compact the used symbols (8 per lane, ascending symbol order); counts are capped so that count << 8 cannot overflow
     uint32_t mine = 0;
     for (uint32_t k = 0; k < 8; k++) mine += hist[lane * 8 + k] ? 1u : 0u;
     const uint32_t inc = warp_inclusive_scan_u32(mine, lane);
@@ -69,25 +53,27 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
         for (uint32_t k = 0; k < 8; k++) { const uint32_t s = lane * 8 + k; if (hist[s]) keys[at++] = (hist[s] << 8) | s; }
     }
     __syncwarp();
-    if (m == 1) return ze_rle_literals((uint8_t)(keys[0] & 0xff), n, body, lane);
+    if (m < 2) return;                         // a single symbol: every block of the region is an RLE literals block
     {   // Shannon estimate in 1/16 bit units: sum c * (log2(n) - log2(c)), log2 by leading zeros + a linear fraction
         uint32_t cost = 0;
+        const uint32_t hn = (uint32_t)zf::highbit32(n);
+        const uint32_t lgn = (hn << 4) + (((n << (31 - hn)) >> 27) & 15) + 1;
         for (uint32_t k = 0; k < 8; k++) {
             const uint32_t c = hist[lane * 8 + k];
             if (c) {
                 const uint32_t hb = (uint32_t)zf::highbit32(c);
                 const uint32_t lg16 = (hb << 4) + (((c << (31 - hb)) >> 27) & 15);       // ~ 16 * log2(c)
-                cost += c * (((uint32_t)zf::highbit32(n) << 4) + (((n << (31 - zf::highbit32(n))) >> 27) & 15) + 1 - lg16);
+                cost += c * (lgn - lg16);
             }
         }
         const uint32_t bits16 = __reduce_add_sync(TS_FULL, cost);
-        if ((bits16 >> 7) + m / 2 + 16 >= n) return ze_raw_literals(lits, n, body, lane);   // >= n bytes even before rounding losses
+        if ((bits16 >> 7) + m / 2 + 16 >= n) return;                      // >= n bytes even before rounding losses
     }
     const uint32_t last_sym = keys[m - 1] & 0xff;
 
     // ---- code lengths: rebuild with halved counts until the tree is at most 11 deep
     uint32_t max_len = 0;
-    for (uint32_t round = 0; round < 16; round++) {
+    for (uint32_t round = 0; round < 20; round++) {
         for (uint32_t e = lane; e < m; e += 32) {                         // rank sort (keys are distinct)
             const uint32_t key = keys[e];
             uint32_t r = 0;
@@ -128,7 +114,7 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
         }
         __syncwarp();
     }
-    if (max_len > (uint32_t)zf::HUF_MAX_LOG) return ze_raw_literals(lits, n, body, lane);
+    if (max_len > (uint32_t)zf::HUF_MAX_LOG) return;
 
     // ---- canonical codes: weight w = max_len + 1 - len; cells are dealt weight-ascending, symbol-ascending
     if (lane == 0) {
@@ -141,7 +127,6 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
         // sorted[] is ordered by count; symbol order inside a weight class comes from walking symbols ascending
         _Pragma("unroll 1")
         for (uint32_t i = 0; i < m; i++) ctab[sorted[i] & 0xff] = (uint32_t)depth[i] << 16;      // park the length
-        uint64_t total_bits = 0;
         _Pragma("unroll 1")
         for (uint32_t s = 0; s <= last_sym; s++) {
             const uint32_t len = ctab[s] >> 16;
@@ -149,22 +134,21 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
             const uint32_t w = max_len + 1 - len;
             ctab[s] = (start[w] >> (w - 1)) | (len << 16);
             start[w] += 1u << (w - 1);
-            total_bits += (uint64_t)len * hist[s];
         }
-        meta[1] = (uint32_t)total_bits;
     }
     __syncwarp();
     const uint32_t nweights = last_sym;                                   // symbols 0 .. last_sym-1 are listed
     // Tree description: direct 4-bit weights (at most 128 of them) or FSE-compressed weights (RFC 8878 §4.2.1.1);
     // the shorter wins.  The FSE form is what lets alphabets above byte value 128 (binary payloads) be Huffman-coded.
     uint32_t tree_bytes = nweights <= 128 ? 1 + (nweights + 1) / 2 : 0xffffffffu;
-    uint8_t* wdesc = (uint8_t*)hist;                                      // the histogram is dead: header byte + FSE description
+    uint8_t* wdesc = hf->desc;
+    bool fse_weights = false;
     {
         uint8_t* wts = (uint8_t*)(work + 1536);                           // weights, then FSE tables, in dead tree scratch
         uint32_t* wcnt = (uint32_t*)(wts + 256);                          // [16]
         uint16_t* wst = (uint16_t*)(wcnt + 16);                           // [64]
         zf::FseCSym* wsy = (zf::FseCSym*)(wst + 64);                      // [16]
-        uint8_t* wscratch = (uint8_t*)(wsy + 16);                         // >= 772 bytes
+        uint8_t* wscratch = (uint8_t*)(wsy + 16);                         // >= 784 bytes
         if (lane < 16) wcnt[lane] = 0;
         __syncwarp();
         for (uint32_t s2 = lane; s2 < nweights; s2 += 32) {
@@ -196,36 +180,84 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
                         const uint32_t nbo = (sv + (uint32_t)c.delta_nb_bits) >> 16;
                         acc |= (uint64_t)(sv & ((1u << nbo) - 1)) << nb; nb += nbo;
                         st[i & 1] = wst[(int32_t)(sv >> nbo) + c.delta_find_state];
-                        while (nb >= 8) { o[ob++] = (uint8_t)acc; acc >>= 8; nb -= 8; }
+                        while (nb >= 8 && ob < 120) { o[ob++] = (uint8_t)acc; acc >>= 8; nb -= 8; }
                     }
                     acc |= (uint64_t)(st[1] & ((1u << wk.log) - 1)) << nb; nb += wk.log;      // flush odd chain, then even chain
                     acc |= (uint64_t)(st[0] & ((1u << wk.log) - 1)) << nb; nb += wk.log;
                     acc |= 1ull << nb; nb += 1;                                                // end mark
-                    while (nb > 0) { o[ob++] = (uint8_t)acc; acc >>= 8; nb = nb >= 8 ? nb - 8 : 0; }
-                    meta[2] = dsz + ob;
+                    while (nb > 0 && ob < 126) { o[ob++] = (uint8_t)acc; acc >>= 8; nb = nb >= 8 ? nb - 8 : 0; }
+                    meta[2] = nb ? 0xffffu : dsz + ob;                    // did not fit 127 bytes: unusable
                 }
                 __syncwarp();
                 const uint32_t fsz = meta[2];
                 if (fsz < 128 && 1 + fsz < tree_bytes) {
                     if (lane == 0) wdesc[0] = (uint8_t)fsz;
                     tree_bytes = 1 + fsz;
-                } else if (lane == 0) wdesc[0] = 0xff;
-            } else if (lane == 0) wdesc[0] = 0xff;
-        } else if (lane == 0) wdesc[0] = 0xff;
+                    fse_weights = true;
+                }
+            }
+        }
         __syncwarp();
     }
-    if (tree_bytes == 0xffffffffu) return ze_raw_literals(lits, n, body, lane);   // neither form can describe this tree
-    const bool fse_weights = wdesc[0] != 0xff;
-    const uint32_t est = tree_bytes + 6 + (meta[1] >> 3) + 8;
-    if (est + 5 >= n) return ze_raw_literals(lits, n, body, lane);        // Huffman would not pay
+    if (tree_bytes == 0xffffffffu) return;                                // neither form can describe this tree
+    if (!fse_weights && lane == 0) {
+        wdesc[0] = (uint8_t)(127 + nweights);
+        for (uint32_t i = 0; i < nweights; i += 2) {
+            const uint32_t l0 = ctab[i] >> 16, l1 = i + 1 < nweights ? ctab[i + 1] >> 16 : 0;
+            const uint32_t w0 = l0 ? max_len + 1 - l0 : 0, w1 = l1 ? max_len + 1 - l1 : 0;
+            wdesc[1 + i / 2] = (uint8_t)((w0 << 4) | w1);
+        }
+    }
+    if (lane == 0) { hf->ok = 1; hf->tree_bytes = tree_bytes; hf->max_len = max_len; }
+    __syncwarp();
+}
 
-    // ---- the four streams, staged in `work` (cleared first; tree scratch is dead from here on)
+struct ZeLitBlock {                  // what a block's literals section will consist of (decided before anything is written)
+    uint32_t kind;                   // 0 Raw, 1 RLE, 2 Huffman (tree or treeless decided later)
+    uint32_t n;                      // regenerated size
+    uint32_t stream_bytes;           // Huffman: bytes of the four streams
+    uint32_t ssz[3];                 // Huffman: sizes of streams 1-3 (jump table)
+    uint32_t rle_byte;
+};
+
+// Exact sizes of the four Huffman streams of this block (no output).  Returns false when a literal has no code.
+__device__ __forceinline__ void ze_huf_plan_block(const uint8_t* __restrict__ lits, uint32_t n, const uint32_t* ctab, const ZeHuf* hf,
+                                                  ZeLitBlock* lb, uint32_t lane) {
+    uint32_t kind = 0, stream_bytes = 0, s1 = 0, s2 = 0, s3 = 0, rle = 0;
+    if (n >= 1) {                                                         // RLE: all literals equal
+        const uint8_t first = lits[0];
+        bool same = true;
+        for (uint32_t i = lane; i < n; i += 32) same = same && lits[i] == first;
+        if (__all_sync(TS_FULL, same)) { kind = 1; rle = first; }
+    }
+    if (kind == 0 && hf->ok && n >= ZE_HUF_MIN) {
+        const uint32_t seg = (n + 3) / 4;
+        uint32_t tot[4];
+        bool coded = true;
+        for (uint32_t st = 0; st < 4; st++) {
+            const uint32_t a = st * seg, b = st < 3 ? min(n, a + seg) : n;
+            uint32_t bits = 0;
+            for (uint32_t i = a + lane; i < b; i += 32) { const uint32_t l = ctab[lits[i]] >> 16; coded = coded && l != 0; bits += l; }
+            tot[st] = __reduce_add_sync(TS_FULL, bits);
+        }
+        if (__all_sync(TS_FULL, coded)) {
+            s1 = (tot[0] + 8) >> 3; s2 = (tot[1] + 8) >> 3; s3 = (tot[2] + 8) >> 3;         // + end mark, rounded up
+            const uint32_t s4 = (tot[3] + 8) >> 3;
+            stream_bytes = s1 + s2 + s3 + s4;
+            if (stream_bytes + 6 + 2 < n && s1 < 65536 && s2 < 65536 && s3 < 65536) kind = 2;   // must beat Raw (3-byte header vs up to 5)
+        }
+    }
+    if (lane == 0) { lb->kind = kind; lb->n = n; lb->stream_bytes = stream_bytes; lb->ssz[0] = s1; lb->ssz[1] = s2; lb->ssz[2] = s3; lb->rle_byte = rle; }
+    __syncwarp();
+}
+
+// The four streams of this block into `work` (shared-memory words, >= stream_bytes + 8 bytes).  Layout: streams back to back.
+__device__ __forceinline__ void ze_huf_encode_block(const uint8_t* __restrict__ lits, uint32_t n, const uint32_t* ctab, uint32_t stream_bytes,
+                                                    uint32_t* work, uint32_t lane) {
+    for (uint32_t i = lane; i < (stream_bytes + 11) / 4; i += 32) work[i] = 0;
+    __syncwarp();
     const uint32_t seg = (n + 3) / 4;
-    __syncwarp();
-    for (uint32_t i = lane; i < (ZB + 128) / 4; i += 32) work[i] = 0;
-    __syncwarp();
     uint32_t byte_pos = 0;
-    uint64_t ssz_all = 0;                                                 // four 16-bit stream sizes
     _Pragma("unroll 1")
     for (uint32_t st = 0; st < 4; st++) {
         const uint32_t s0 = st * seg, s1 = st < 3 ? min(n, s0 + seg) : n;
@@ -251,41 +283,31 @@ __device__ __forceinline__ uint32_t ze_encode_literals(const uint8_t* __restrict
             const uint32_t o = byte_pos * 8 + total;
             atomicOr(&work[o >> 5], 1u << (o & 31));
         }
-        const uint32_t sz = (total + 1 + 7) >> 3;
-        ssz_all |= (uint64_t)sz << (16 * st);
-        byte_pos += sz;
+        byte_pos += (total + 1 + 7) >> 3;
         __syncwarp();
     }
-    const uint32_t comp = tree_bytes + 6 + byte_pos;
+}
+
+// Literals_Section_Header for a Raw / RLE literals block (always the 3-byte form) — one lane.
+__device__ __forceinline__ uint32_t ze_lit_header_raw(uint8_t* body, uint32_t type, uint32_t n) {
+    body[0] = (uint8_t)(type | (3u << 2) | ((n & 0xf) << 4));
+    body[1] = (uint8_t)(n >> 4);
+    body[2] = (uint8_t)(n >> 12);
+    return 3;
+}
+// ... and for a Compressed (type 2) / Treeless (type 3) block with four streams; comp = tree + jump table + streams.
+__device__ __forceinline__ uint32_t ze_lit_header_huf(uint8_t* body, uint32_t type, uint32_t n, uint32_t comp) {
     const uint32_t hsz = (n < 1024 && comp < 1024) ? 3u : (n < 16384 && comp < 16384) ? 4u : 5u;
-    if (hsz + comp >= 3 + n) return ze_raw_literals(lits, n, body, lane);
-    if (lane == 0) {
-        const uint32_t sf = hsz - 2;                                      // 1, 2, 3: all with four streams
-        uint64_t h;
-        if (hsz == 3) h = 2u | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 14);
-        else if (hsz == 4) h = 2u | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 18);
-        else h = 2u | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 22);
-        for (uint32_t k = 0; k < hsz; k++) body[k] = (uint8_t)(h >> (8 * k));
-        uint8_t* t = body + hsz;
-        if (fse_weights) {
-            for (uint32_t i = 0; i < tree_bytes; i++) t[i] = wdesc[i];
-        } else {
-            t[0] = (uint8_t)(127 + nweights);
-            for (uint32_t i = 0; i < nweights; i += 2) {
-                const uint32_t l0 = ctab[i] >> 16, l1 = i + 1 < nweights ? ctab[i + 1] >> 16 : 0;
-                const uint32_t w0 = l0 ? max_len + 1 - l0 : 0, w1 = l1 ? max_len + 1 - l1 : 0;
-                t[1 + i / 2] = (uint8_t)((w0 << 4) | w1);
-            }
-        }
-        uint8_t* j = t + tree_bytes;
-        for (uint32_t k = 0; k < 6; k++) j[k] = (uint8_t)(ssz_all >> (8 * k));            // jump table: sizes of streams 1-3
-    }
-    uint8_t* sp = body + hsz + tree_bytes + 6;
-    const uint8_t* wb = (const uint8_t*)work;
-    _Pragma("unroll 2")
-    for (uint32_t i = lane; i < byte_pos; i += 32) sp[i] = wb[i];
-    __syncwarp();
-    return hsz + comp;
+    const uint32_t sf = hsz - 2;                                          // 1, 2, 3: all with four streams
+    uint64_t h;
+    if (hsz == 3) h = type | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 14);
+    else if (hsz == 4) h = type | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 18);
+    else h = type | (sf << 2) | ((uint64_t)n << 4) | ((uint64_t)comp << 22);
+    for (uint32_t k = 0; k < hsz; k++) body[k] = (uint8_t)(h >> (8 * k));
+    return hsz;
+}
+__device__ __forceinline__ uint32_t ze_lit_header_huf_size(uint32_t n, uint32_t comp) {
+    return (n < 1024 && comp < 1024) ? 3u : (n < 16384 && comp < 16384) ? 4u : 5u;
 }
 
 }  // namespace ts
