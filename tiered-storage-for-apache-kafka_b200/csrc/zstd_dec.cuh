@@ -559,22 +559,21 @@ __device__ __forceinline__ uint32_t zd_block_entropy(const uint8_t* blk, uint32_
 }
 
 // ------------------------------------------------------------------------------------------ execution stage, one CTA
-// Executes the sequences the entropy stage left in the arenas, blocks [b_first, b_last) in order, into out[0..) (generic
-// pointer: HBM for whole frames, shared memory for self-contained regions).  ZX_T sequences are taken per step:
+// Executes the sequences the entropy stage left in the arenas, blocks [b_first, b_last) in order.  Output is assembled in a
+// shared-memory WINDOW (`win`, holding frame positions [win_pos0, win_pos0 + win_cap)) and flushed to HBM by the caller
+// (regions: once, 64 KiB) or here after every block (whole frames: the window is the current block, <= 128 KiB; matches that
+// reach before it read the flushed bytes from `far`).  ZX_T sequences are taken per step:
 //   * positions by a CTA-wide prefix sum of literal and match lengths,
 //   * every literal run copied at once (they depend on nothing),
-//   * matches by EXACT dependency tracking: a match waits only for the earlier matches of the same step whose
-//     destination overlaps its source (found by binary search in the step's positions); everything before the step is
-//     complete.  Rounds of "copy what is ready, barrier" run until the step is done — the depth of the real dependency
-//     chains, not the number of sequences, bounds the number of rounds.
+//   * matches by EXACT dependency tracking without barriers: the sequences whose output covers a match's source are found
+//     by binary search in the step's positions; a match spins on their done bits (one 32-bit word per warp, written only by
+//     that warp) and copies as soon as they are set.  Text compressed against its nearest earlier occurrence makes chains
+//     of dozens of dependent matches inside one step: a hop along such a chain costs a shared-memory poll, not a barrier.
 constexpr int ZX_T = 512;
-constexpr uint32_t ZX_DEP_SPAN = 6;          // producers checked individually; wider sources wait to be first in line
 struct ZxShared {
     uint32_t ostart[ZX_T + 1];               // output position of each sequence of the step (+ end)
-    uint32_t mlen[ZX_T];
-    uint8_t done[ZX_T];
+    uint32_t dbits[ZX_T / 32];               // done bit per sequence of the step; word w is written by warp w only
     uint64_t wsum[ZX_T / 32];
-    uint32_t wpend[ZX_T / 32];
     uint64_t tot;
     uint32_t rep[3];
     int32_t err;
@@ -597,39 +596,61 @@ __device__ __forceinline__ uint64_t zx_block_scan(uint64_t v, uint32_t tid, ZxSh
     return inc;
 }
 
-// Cooperative copy by the calling WARP: n bytes from src to dst (no overlap), any alignment.
-__device__ __forceinline__ void zx_warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) {
-    for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
+__device__ __forceinline__ uint32_t zx_ld_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+
+// are all sequences [ja, jb] of the step done?  (bits of words ja/32 .. jb/32)
+__device__ __forceinline__ bool zx_all_done(const uint32_t* dbits, uint32_t ja, uint32_t jb) {
+    const uint32_t wa = ja >> 5, wb = jb >> 5;
+    for (uint32_t w = wa; w <= wb; w++) {
+        uint32_t need = 0xffffffffu;
+        if (w == wa) need &= 0xffffffffu << (ja & 31);
+        if (w == wb) need &= 0xffffffffu >> (31 - (jb & 31));
+        if ((zx_ld_volatile(&dbits[w]) & need) != need) return false;
+    }
+    return true;
 }
 
-// Returns bytes produced (the new output position) or sets sh->err (<0 corrupt / contract violated).
-// base_hist: bytes of history before out[0] that may be referenced (0 for regions and frames).
+// Flush win[0..n) to dst (HBM), 128-bit stores when the destination allows.  All threads; no barrier inside.
+__device__ __forceinline__ void zx_flush(uint8_t* dst, const uint8_t* win, uint32_t n, uint32_t tid) {
+    if ((((uintptr_t)dst) & 15) == 0) {
+        for (uint32_t k = tid * 16; k + 16 <= n; k += ZX_T * 16) stg128_stream((uint4*)(dst + k), *(const uint4*)(win + k));
+        for (uint32_t k = (n & ~15u) + tid; k < n; k += ZX_T) dst[k] = win[k];
+    } else {
+        for (uint32_t k = tid; k < n; k += ZX_T) dst[k] = win[k];
+    }
+}
+
+// Returns the new output position (bytes produced since position 0 of the caller's numbering) or sets sh->err
+// (<0 corrupt / contract violated, 3 = a block needs the serial path).
+//   win / win_cap   shared-memory window
+//   far             HBM image of the output, position 0 at far[0] (nullptr: nothing before the window may be referenced)
+//   per_block       true: the window restarts at every block and is flushed to `far` after it (whole frames)
+//                   false: one window for all blocks, the caller flushes (regions)
 __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, const uint32_t* bo, const ZdBlkMeta* meta,
-                                                      uint32_t b_first, uint32_t b_last, uint8_t* out, uint32_t out_cap,
+                                                      uint32_t b_first, uint32_t b_last, uint8_t* win, uint32_t win_cap,
+                                                      uint8_t* far, bool per_block, uint32_t out_cap,
                                                       const uint8_t* lit_arena, const uint64_t* seq_arena, uint32_t frame_len,
                                                       ZxShared* sh, uint32_t tid, bool no_carried_reps) {
     const uint32_t lane = tid & 31, w = tid >> 5;
     uint32_t op = 0;
+    uint32_t win_pos0 = 0;                               // frame position of win[0]
     if (tid == 0) { sh->rep[0] = 1; sh->rep[1] = 4; sh->rep[2] = 8; sh->err = 0; }
     __syncthreads();
     for (uint32_t b = b_first; b < b_last; b++) {
         const uint32_t pos = bo[b];
         const uint32_t h = frame[pos] | (frame[pos + 1] << 8) | ((uint32_t)frame[pos + 2] << 16);
         const uint32_t type = (h >> 1) & 3, bsz = h >> 3;
-        const uint32_t room = min((uint32_t)zf::BLOCK_MAX, out_cap - op);
-        if (type == 0) {
-            if (bsz > room || pos + 3 + bsz > frame_len) { if (tid == 0) sh->err = -1; __syncthreads(); return op; }
-            for (uint32_t k = tid; k < bsz; k += ZX_T) out[op + k] = frame[pos + 3 + k];
-            op += bsz;
-            __syncthreads();
-            continue;
-        }
-        if (type == 1) {
-            if (bsz > room || pos + 4 > frame_len) { if (tid == 0) sh->err = -1; __syncthreads(); return op; }
+        if (per_block) win_pos0 = op;
+        const uint32_t room = min(min((uint32_t)zf::BLOCK_MAX, out_cap - op), win_cap - (op - win_pos0));
+        uint8_t* wout = win - win_pos0;                  // wout[position] for positions inside the window
+        if (type == 0 || type == 1) {                    // Raw_Block / RLE_Block
+            if (bsz > room || pos + 3 + (type == 0 ? bsz : 1) > frame_len) { if (tid == 0) sh->err = -1; __syncthreads(); return op; }
             const uint8_t v = frame[pos + 3];
-            for (uint32_t k = tid; k < bsz; k += ZX_T) out[op + k] = v;
-            op += bsz;
+            if (type == 0) { for (uint32_t k = tid; k < bsz; k += ZX_T) wout[op + k] = frame[pos + 3 + k]; }
+            else { for (uint32_t k = tid; k < bsz; k += ZX_T) wout[op + k] = v; }
             __syncthreads();
+            if (per_block) { zx_flush(far + op, win, bsz, tid); __syncthreads(); }
+            op += bsz;
             continue;
         }
         const ZdBlkMeta m = meta[b];
@@ -665,13 +686,13 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
             const uint64_t inc = zx_block_scan(((uint64_t)(ll + ml) << 32) | ll, tid, sh, &tot);
             const uint32_t tot_o = (uint32_t)(tot >> 32), tot_l = (uint32_t)tot;
             const uint32_t o_start = op + (uint32_t)(inc >> 32) - ll - ml, l_start = lp + (uint32_t)inc - ll, m_start = o_start + ll;
-            if (mine && off > m_start) bad = true;
+            if (mine && (off > m_start || (!far && off > m_start - win_pos0))) bad = true;
             sh->ostart[tid] = mine ? o_start : op + tot_o;
-            sh->mlen[tid] = mine ? ml : 0;
-            sh->done[tid] = (!mine || ml == 0) ? 1 : 0;
+            const uint32_t preset = __ballot_sync(TS_FULL, !mine || ml == 0);         // nothing to wait for on these
+            if (lane == 0) sh->dbits[w] = preset;
             if (tid == 0) sh->ostart[ZX_T] = op + tot_o;
             const bool any_bad = __syncthreads_or(bad) != 0;
-            if (any_bad || lp + tot_l > regen || (uint64_t)(op - blk_op0) + tot_o > zf::BLOCK_MAX || (uint64_t)op + tot_o > out_cap) {
+            if (any_bad || lp + tot_l > regen || (uint64_t)(op - blk_op0) + tot_o > room) {
                 if (tid == 0) sh->err = -1;
                 __syncthreads();
                 return op;
@@ -679,7 +700,7 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
             // ---- literal runs: short ones by their own thread, long ones by the warp
             {
                 const uint32_t quick = min(ll, 32u);
-                uint8_t* ld = out + o_start;
+                uint8_t* ld = wout + o_start;
                 if (rle_lit < 0x100) { for (uint32_t k = 0; k < quick; k++) ld[k] = (uint8_t)rle_lit; }
                 else {
                     const uint8_t* ls = lit + l_start;
@@ -695,11 +716,11 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
                     const uint32_t f = (uint32_t)__ffs((int)longs) - 1;
                     longs &= longs - 1;
                     const uint32_t fo = __shfl_sync(TS_FULL, o_start, f), fl = __shfl_sync(TS_FULL, l_start, f), fn = __shfl_sync(TS_FULL, ll, f);
-                    if (rle_lit < 0x100) { for (uint32_t k = 32 + lane; k < fn; k += 32) out[fo + k] = (uint8_t)rle_lit; }
-                    else { for (uint32_t k = 32 + lane; k < fn; k += 32) out[fo + k] = lit[fl + k]; }
+                    if (rle_lit < 0x100) { for (uint32_t k = 32 + lane; k < fn; k += 32) wout[fo + k] = (uint8_t)rle_lit; }
+                    else { for (uint32_t k = 32 + lane; k < fn; k += 32) wout[fo + k] = lit[fl + k]; }
                 }
             }
-            // ---- producers of this match inside the step: sequences [ja, jb] cover its source bytes
+            // ---- producers of this match inside the step: sequences [ja, jb] cover the part of its source other sequences write
             const uint32_t s_lo = m_start - off;                          // first source byte
             const uint32_t s_hi = min(s_lo + ml, m_start);                // one past the last source byte written by someone else
             uint32_t ja = 0, jb = 0;
@@ -710,83 +731,82 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
                 const uint32_t x = max(s_lo, op);
                 while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] <= x) lo = mid; else hi = mid - 1; }
                 ja = lo;
-                lo = ja; hi = tid;
+                hi = tid;
                 while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] < s_hi) lo = mid; else hi = mid - 1; }
                 jb = lo;
-                if (jb == tid) jb = tid ? tid - 1 : 0;                    // own literals precede the match: never a producer
-                if (ja > jb) inside = false;
+                if (jb == tid) { if (tid == 0 || ja == tid) inside = false; else jb = tid - 1; }   // own literals precede the match: never a producer
             }
-            __syncthreads();                                              // literals, ostart/mlen/done visible
-            bool done = !mine || ml == 0;
-            uint8_t* d = out + m_start;
-            const uint8_t* msrc = d - off;
-            while (true) {
-                // first pending sequence of the step (for sources too wide to check producer by producer)
-                const uint32_t pend = __ballot_sync(TS_FULL, !done);
-                if (lane == 0) sh->wpend[w] = pend;
-                __syncthreads();
-                bool ready = false;
-                if (!done) {
-                    if (!inside) ready = true;
-                    else if (jb - ja < ZX_DEP_SPAN) {
-                        ready = true;
-                        for (uint32_t j = ja; j <= jb; j++) {
-                            if (sh->done[j]) continue;
-                            const uint32_t pm = sh->ostart[j + 1] - sh->mlen[j];      // producer's match bytes [pm, ostart[j+1])
-                            if (sh->ostart[j + 1] > s_lo && pm < s_hi) { ready = false; break; }
-                        }
-                    } else {
-                        uint32_t first = ZX_T;
-                        for (uint32_t q = 0; q < ZX_T / 32; q++) { const uint32_t pm = sh->wpend[q]; if (pm) { first = q * 32 + (uint32_t)__ffs((int)pm) - 1; break; } }
-                        ready = first == tid;
-                    }
-                }
-                if (ready && ml <= 64) {
-                    uint32_t k = 0;
-                    if (off >= 4) {
-                        for (; k + 4 <= ml; k += 4) {
-                            const uint8_t b0 = msrc[k], b1 = msrc[k + 1], b2 = msrc[k + 2], b3 = msrc[k + 3];
-                            d[k] = b0; d[k + 1] = b1; d[k + 2] = b2; d[k + 3] = b3;
+            __syncthreads();                                              // literals, ostart, dbits visible to everyone
+            // ---- matches: every warp runs its own loop; a lane copies once the done bits of its producers are set
+            {
+                bool done = !mine || ml == 0;
+                const bool from_far = s_hi <= win_pos0 && ml != 0;        // whole source before the window: flushed long ago
+                const bool straddle = !from_far && s_lo < win_pos0;       // (only with off >= ml, else s_hi would be m_start)
+                uint8_t* d = wout + m_start;
+                uint32_t pend = __ballot_sync(TS_FULL, !done);
+                while (pend) {
+                    bool ready = false;
+                    if (!done) ready = !inside || zx_all_done(sh->dbits, ja, jb);
+                    if (ready) __threadfence_block();                      // acquire: the producers' bytes are visible
+                    if (ready && ml <= 64) {
+                        if (from_far) { const uint8_t* ms = far + s_lo; for (uint32_t k = 0; k < ml; k++) d[k] = ms[k]; }
+                        else if (straddle) { for (uint32_t k = 0; k < ml; k++) { const uint32_t q = s_lo + k; d[k] = q < win_pos0 ? far[q] : wout[q]; } }
+                        else {
+                            const uint8_t* ms = d - off;
+                            uint32_t k = 0;
+                            if (off >= 4) {
+                                for (; k + 4 <= ml; k += 4) {
+                                    const uint8_t b0 = ms[k], b1 = ms[k + 1], b2 = ms[k + 2], b3 = ms[k + 3];
+                                    d[k] = b0; d[k + 1] = b1; d[k + 2] = b2; d[k + 3] = b3;
+                                }
+                            }
+                            for (; k < ml; k++) d[k] = ms[k];             // byte-serial: overlap (off < ml) is fine
                         }
                     }
-                    for (; k < ml; k++) d[k] = msrc[k];
-                }
-                uint32_t big = __ballot_sync(TS_FULL, ready && ml > 64);
-                while (big) {                                             // long matches: 32 lanes per match
-                    const uint32_t f = (uint32_t)__ffs((int)big) - 1;
-                    big &= big - 1;
-                    const uint32_t fm = __shfl_sync(TS_FULL, m_start, f), fl = __shfl_sync(TS_FULL, ml, f), fo = __shfl_sync(TS_FULL, off, f);
-                    uint8_t* dd = out + fm;
-                    const uint8_t* mm = dd - fo;
-                    if (fo >= 32) {
-                        for (uint32_t k0 = 0; k0 < fl; k0 += 32) {
-                            const uint32_t k = k0 + lane;
-                            if (k < fl) dd[k] = mm[k];
-                            if (fo < fl) __syncwarp();
+                    uint32_t big = __ballot_sync(TS_FULL, ready && ml > 64);
+                    while (big) {                                         // long matches: 32 lanes per match
+                        const uint32_t f = (uint32_t)__ffs((int)big) - 1;
+                        big &= big - 1;
+                        const uint32_t fm = __shfl_sync(TS_FULL, m_start, f), fl = __shfl_sync(TS_FULL, ml, f), fo = __shfl_sync(TS_FULL, off, f);
+                        uint8_t* dd = wout + fm;
+                        const uint32_t fs = fm - fo;                      // source position
+                        if (fo >= 32) {
+                            for (uint32_t k0 = 0; k0 < fl; k0 += 32) {
+                                const uint32_t k = k0 + lane;
+                                if (k < fl) { const uint32_t q = fs + k; dd[k] = q < win_pos0 ? far[q] : wout[q]; }
+                                if (fo < fl) __syncwarp();               // later strides may read what this one wrote
+                            }
+                        } else {
+                            // periodic source: the fo bytes before the destination, all of them already written
+                            for (uint32_t k = lane; k < fl; k += 32) { const uint32_t q = fs + k % fo; dd[k] = q < win_pos0 ? far[q] : wout[q]; }
                         }
-                    } else {
-                        for (uint32_t k = lane; k < fl; k += 32) dd[k] = mm[k % fo];
+                    }
+                    __syncwarp();                                         // the warp's copies of this round are ordered before ...
+                    if (ready) done = true;
+                    const uint32_t now = __ballot_sync(TS_FULL, !done);
+                    if (now != pend) {                                    // ... the release of their done bits
+                        if (lane == 0) { __threadfence_block(); *(volatile uint32_t*)&sh->dbits[w] = ~now; }
+                        pend = now;
                     }
                 }
-                __syncthreads();                                          // copies of this round complete before anyone is told so
-                if (ready) { sh->done[tid] = 1; done = true; }
-                if (!__syncthreads_or(!done)) break;
             }
+            __syncthreads();                                              // the step is complete
             op += tot_o; lp += tot_l;
         }
         // trailing literals of the block
         {
-            if (lp > regen || (uint64_t)(op - blk_op0) + (regen - lp) > zf::BLOCK_MAX || (uint64_t)op + (regen - lp) > out_cap) {
+            if (lp > regen || (uint64_t)(op - blk_op0) + (regen - lp) > room) {
                 if (tid == 0) sh->err = -1;
                 __syncthreads();
                 return op;
             }
             const uint32_t ll = regen - lp;
-            if (rle_lit < 0x100) { for (uint32_t k = tid; k < ll; k += ZX_T) out[op + k] = (uint8_t)rle_lit; }
-            else { for (uint32_t k = tid; k < ll; k += ZX_T) out[op + k] = lit[lp + k]; }
+            if (rle_lit < 0x100) { for (uint32_t k = tid; k < ll; k += ZX_T) wout[op + k] = (uint8_t)rle_lit; }
+            else { for (uint32_t k = tid; k < ll; k += ZX_T) wout[op + k] = lit[lp + k]; }
             op += ll;
         }
         __syncthreads();
+        if (per_block) { zx_flush(far + blk_op0, win, op - blk_op0, tid); }
         if (tid == 0) {                                                   // repeat offsets after the block
             uint32_t nr[3];
             for (int k = 0; k < 3; k++) {                                 // an offset that underflowed is only an error if it is used
@@ -799,7 +819,7 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
             }
             sh->rep[0] = nr[0]; sh->rep[1] = nr[1]; sh->rep[2] = nr[2];
         }
-        __syncthreads();
+        __syncthreads();                                                  // (also: the flushed bytes are visible before the next block reads `far`)
         if (sh->err) return op;
     }
     return op;
@@ -1023,7 +1043,7 @@ __global__ void __launch_bounds__(ZX_T, 2) zstd_dec_regions_kernel(const __grid_
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
     const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
-    const uint32_t made = zx_execute_blocks(p, bo, meta, b0, b1, obuf, want,
+    const uint32_t made = zx_execute_blocks(p, bo, meta, b0, b1, obuf, ZR, nullptr, false, want,
                                             A.par_lits + (size_t)chunk * A.par_lit_cap, A.par_seqs + (size_t)chunk * A.par_seq_cap,
                                             A.in_len[chunk], &sh, tid, region != 0);
     if (sh.err || made != want) {
@@ -1034,18 +1054,14 @@ __global__ void __launch_bounds__(ZX_T, 2) zstd_dec_regions_kernel(const __grid_
         return;
     }
     if (tid == 0) atomicAdd(&A.stats[0], 1ull);
-    uint8_t* dst = A.out_base + A.out_off[chunk] + (size_t)region * ZR;
-    if ((((uintptr_t)dst) & 15) == 0) {
-        for (uint32_t k = tid * 16; k + 16 <= made; k += ZX_T * 16) stg128_stream((uint4*)(dst + k), *(const uint4*)(obuf + k));
-        for (uint32_t k = (made & ~15u) + tid; k < made; k += ZX_T) dst[k] = obuf[k];
-    } else {
-        for (uint32_t k = tid; k < made; k += ZX_T) dst[k] = obuf[k];
-    }
+    zx_flush(A.out_base + A.out_off[chunk] + (size_t)region * ZR, obuf, made, tid);
 }
 
 // 3c: one CTA per frame — execution stage straight into the frame's output in HBM (what libzstd-written frames need: their
 // matches reach back up to the whole window).
-__global__ void __launch_bounds__(ZX_T, 2) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
+constexpr uint32_t ZX_FRAME_SMEM = zf::BLOCK_MAX;      // the window is the current block
+__global__ void __launch_bounds__(ZX_T, 1) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
+    TS_DYN_SMEM(wbuf);
     __shared__ ZxShared sh;
     const uint32_t tid = threadIdx.x;
     const uint32_t chunk = blockIdx.x;
@@ -1057,7 +1073,7 @@ __global__ void __launch_bounds__(ZX_T, 2) zstd_dec_par_execute_kernel(const __g
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
     const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
-    const uint32_t made = zx_execute_blocks(p, bo, meta, 0, nblk, A.out_base + A.out_off[chunk], fcs,
+    const uint32_t made = zx_execute_blocks(p, bo, meta, 0, nblk, wbuf, ZX_FRAME_SMEM, A.out_base + A.out_off[chunk], true, fcs,
                                             A.par_lits + (size_t)chunk * A.par_lit_cap, A.par_seqs + (size_t)chunk * A.par_seq_cap,
                                             A.in_len[chunk], &sh, tid, false);
     if (tid == 0) {
@@ -1101,6 +1117,7 @@ inline const char* zstd_kernels_configure() {
     if ((e = rt::allow_smem(zstd_dec_frames_kernel, ZD_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_par_entropy_kernel, ZD_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_regions_kernel, ZX_REGION_SMEM))) return e;
+    if ((e = rt::allow_smem(zstd_dec_par_execute_kernel, ZX_FRAME_SMEM))) return e;
     return nullptr;
 }
 
@@ -1134,7 +1151,7 @@ inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     TS_LAUNCH_P(prof, "zstd_dec_regions", zstd_dec_regions_kernel, dim3(rpc, n_chunks), dim3(ZX_T), ZX_REGION_SMEM, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
-    TS_LAUNCH_P(prof, "zstd_dec_frame_exec", zstd_dec_par_execute_kernel, dim3(n_chunks), dim3(ZX_T), 0, st, A);
+    TS_LAUNCH_P(prof, "zstd_dec_frame_exec", zstd_dec_par_execute_kernel, dim3(n_chunks), dim3(ZX_T), ZX_FRAME_SMEM, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     TS_LAUNCH_P(prof, "zstd_dec_serial", zstd_dec_frames_kernel, dim3((n_chunks + ZD_WPB - 1) / ZD_WPB), dim3(ZD_WPB * 32),
                 ZD_SMEM_BYTES, st, A);

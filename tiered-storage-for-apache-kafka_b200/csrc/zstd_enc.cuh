@@ -38,48 +38,33 @@ constexpr uint32_t ZR = ZB * ZR_SLICES;        // 64 KiB region
 #ifndef ZE_TUNE_HLOG_H
 #define ZE_TUNE_HLOG_H 11
 #endif
-#ifndef ZE_TUNE_MIN_MATCH
-#define ZE_TUNE_MIN_MATCH 5
-#endif
-#ifndef ZE_TUNE_LANE_EXT
-#define ZE_TUNE_LANE_EXT 12
-#endif
-#ifndef ZE_TUNE_BOTH     // n > 0: the earlier slices are consulted even when this slice has a match, and win if n bytes longer
-#define ZE_TUNE_BOTH 2
-#endif
-#ifndef ZE_TUNE_LAZY     // n > 0: a match is passed over when the next position starts one at least n bytes longer
-#define ZE_TUNE_LAZY 1
-#endif
-#ifndef ZE_TUNE_BACK     // bytes a taken match may grow backwards over the literals of its step (libzstd's "catch up")
-#define ZE_TUNE_BACK 31
-#endif
 constexpr int ZE_HLOG = ZE_TUNE_HLOG;          // per-slice hash tables: 2^10 x u16 (region-relative position)
 constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
 constexpr int ZE_HLOG_H = ZE_TUNE_HLOG_H;      // history tables (last occurrence in all earlier slices): 7 of them
 constexpr uint32_t ZE_HSIZE_H = 1u << ZE_HLOG_H;
 constexpr uint32_t ZE_EMPTY = 0xffffu;         // no position: 65535 cannot start a 4-byte match in a 64 KiB region
 constexpr uint32_t ZE_MAXSEQ = ZB / 8;         // sequences kept per block; beyond that the rest goes out as literals
-constexpr uint32_t ZE_MIN_MATCH = ZE_TUNE_MIN_MATCH;   // 5: a 4-byte match costs more bits than four Huffman-coded literals (libzstd level 3 also uses 5)
-constexpr uint32_t ZE_LANE_EXT = ZE_TUNE_LANE_EXT;     // 12: bytes a lane extends its own match beyond the first 4
+constexpr uint32_t ZE_MIN_MATCH = 5;           // a 4-byte match costs more bits than four Huffman-coded literals (libzstd level 3 also uses 5); candidates are verified on 5 bytes
 constexpr uint32_t ZE_THREADS = ZR_SLICES * 32;
 static_assert(ZR <= 65536 && ZE_MAXSEQ <= 1024, "16-bit hash slots / sequence fields assume 64 KiB regions of 8 KiB blocks");
 
 // ---- shared-memory map of one CTA ----
 // parse phases:   [buf: region bytes + pad][ht_run: 8 x 2 KiB][ht_fin: 8 x 2 KiB][ctl]
 // entropy phases: [8 x per-warp staging (ZE_STAGE bytes) over buf][shared tables over ht_run][tree / table scratch over ht_fin][ctl]
-constexpr uint32_t ZE_STAGE = ZB + 32;                          // per-warp staging: literal streams, then the sequence bit stream
-constexpr uint32_t ZE_BUF_BYTES = ZR_SLICES * ZE_STAGE + 64;    // 65856: region bytes (65536) + zero pad for over-reads
+constexpr uint32_t ZE_STAGE = ZB + 448;                         // per-warp staging: literal streams, then the sequence bit stream + tile scratch
+constexpr uint32_t ZE_BUF_BYTES = ZR_SLICES * ZE_STAGE + 64;    // region bytes (65536) + zero pad for over-reads
 constexpr uint32_t ZE_HT_BYTES = ZR_SLICES * ZE_HSIZE * 2;
 constexpr uint32_t ZE_HTH_BYTES = (ZR_SLICES - 1) * ZE_HSIZE_H * 2 < 12288 ? 12288 : (ZR_SLICES - 1) * ZE_HSIZE_H * 2;   // also the entropy phases' scratch
 constexpr uint32_t ZE_OFF_RUN = ZE_BUF_BYTES;
 constexpr uint32_t ZE_OFF_FIN = ZE_OFF_RUN + ZE_HT_BYTES;
 constexpr uint32_t ZE_OFF_CTL = ZE_OFF_FIN + ZE_HTH_BYTES;
 constexpr uint32_t ZE_SMEM_BYTES = ZE_OFF_CTL + 512;
-// per-tile FSE scratch (codes, state bits) lives in the tail of a warp's staging area: the sequence bit stream staged there
-// is at most ZE_MAXSEQ * 58 bits, which ends below this offset
-constexpr uint32_t ZE_SEQ_AUX_OFF = ZB - 512;
-static_assert(ZE_MAXSEQ * 58 / 8 + 16 <= ZE_SEQ_AUX_OFF, "sequence bit stream would overlap the FSE tile scratch");
-static_assert(ZE_SEQ_AUX_OFF + 3 * 32 + 3 * 32 * 2 + 3 * 32 <= ZE_STAGE, "FSE tile scratch must fit the staging area");
+// per-tile FSE scratch lives in the tail of a warp's staging area: the sequence bit stream staged there is at most
+// ZE_MAXSEQ * 58 bits, which ends below this offset.  Per tile of 32 sequences and per kind (OF, ML, LL): the symbols'
+// transforms (8 bytes each) going in, the state bits (value | count << 16) coming out of the chains.
+constexpr uint32_t ZE_SEQ_AUX_OFF = 7456;
+static_assert(ZE_MAXSEQ * 58 / 8 + 16 <= ZE_SEQ_AUX_OFF && ZE_SEQ_AUX_OFF % 8 == 0, "sequence bit stream would overlap the FSE tile scratch");
+static_assert(ZE_SEQ_AUX_OFF + 3 * 32 * 8 + 3 * 32 * 4 <= ZE_STAGE, "FSE tile scratch must fit the staging area");
 
 __constant__ zf::SeqTables g_seq_tables = zf::make_seq_tables();
 __constant__ zf::PredefinedCTables g_pre_ctables = zf::make_predefined_ctables();
@@ -110,14 +95,7 @@ __device__ __forceinline__ uint32_t ze_hash_h(uint32_t v) { return (v * 26544357
 
 
 // number of equal leading bytes (0..4) of two words given their XOR
-__device__ __forceinline__ uint32_t ze_common_bytes(uint32_t x) { return x ? (uint32_t)(__ffs((int)x) - 1) >> 3 : 4u; }
-
-__device__ __forceinline__ uint32_t ze_ll_code(uint32_t ll) {
-    return ll < 64 ? g_seq_tables.ll_code[ll] : (uint32_t)zf::highbit32(ll) + 19;
-}
-__device__ __forceinline__ uint32_t ze_ml_code(uint32_t mlbase) {
-    return mlbase < 128 ? g_seq_tables.ml_code[mlbase] : (uint32_t)zf::highbit32(mlbase) + 36;
-}
+__device__ __forceinline__ uint32_t ze_common_bytes(uint32_t x) { return (uint32_t)__clz((int)__brev(x)) >> 3; }
 
 // OR a bit field (val, nb <= 58 bits) into a zeroed little-endian word buffer at bit offset `o` (shared memory)
 __device__ __forceinline__ void ze_put_bits(uint32_t* words, uint32_t o, uint64_t val, uint32_t nb) {
@@ -129,17 +107,8 @@ __device__ __forceinline__ void ze_put_bits(uint32_t* words, uint32_t o, uint64_
 }
 
 // Hash-table insert where the HIGHEST position of the warp's step wins a shared slot — the hardware would keep an
-// arbitrary one, which made frames differ between runs; retried uploads must produce identical objects.
-__device__ __forceinline__ void ze_insert_max(uint16_t* ht, uint32_t h, uint32_t p, bool valid) {
-    if (valid) ht[h] = (uint16_t)p;
-    while (true) {
-        __syncwarp();
-        const bool lost = valid && ht[h] < p;            // a lower position of this step sits in the slot
-        if (!__any_sync(TS_FULL, lost)) break;
-        if (lost) ht[h] = (uint16_t)p;
-    }
-}
-
+// arbitrary one, which made frames differ between runs; retried uploads must produce identical objects.  Lanes with the
+// same slot find each other with match.any; only the highest of them stores.
 #ifdef TSGPU_SIMT
 static inline unsigned __match_any_sync(unsigned, unsigned v) {
     simt::Warp& w = simt::g_blk->warps[simt::g_cur->warp];
@@ -151,6 +120,12 @@ static inline unsigned __match_any_sync(unsigned, unsigned v) {
     return r;
 }
 #endif
+
+__device__ __forceinline__ void ze_insert_max(uint16_t* ht, uint32_t h, uint32_t p, bool valid) {
+    const uint32_t peers = __match_any_sync(TS_FULL, valid ? h : 0xffff0000u | (threadIdx.x & 31));
+    if (valid && (peers >> (threadIdx.x & 31)) == 1u) ht[h] = (uint16_t)p;     // no peer in a higher lane
+    __syncwarp();
+}
 
 }  // namespace ts
 
@@ -171,6 +146,11 @@ struct ZeRegion {                    // lives in the ctl area
 };
 static_assert(sizeof(ZeRegion) <= 512, "ctl area");
 
+// Code tables of the sequence fields in shared memory (the constant-memory originals serialise on divergent indices).
+struct ZeCodeTabs { uint8_t ll_code[64], ml_code[128], ll_bits[36], ml_bits[53], pad[3]; };
+__device__ __forceinline__ uint32_t ze_ll_code_s(const ZeCodeTabs* t, uint32_t ll) { return ll < 64 ? t->ll_code[ll] : (uint32_t)zf::highbit32(ll) + 19; }
+__device__ __forceinline__ uint32_t ze_ml_code_s(const ZeCodeTabs* t, uint32_t mlbase) { return mlbase < 128 ? t->ml_code[mlbase] : (uint32_t)zf::highbit32(mlbase) + 36; }
+
 struct ZeShared {                    // over the ht_run area during the entropy phases
     uint32_t hist[256];              // literal histogram of the region
     uint32_t ctab[256];              // Huffman codes
@@ -179,6 +159,7 @@ struct ZeShared {                    // over the ht_run area during the entropy 
     ZeHuf huf;
     uint8_t desc[3][96];             // FSE table descriptions LL, OF, ML
     uint32_t desc_len[3];
+    ZeCodeTabs tabs;
 };
 static_assert(sizeof(ZeShared) <= ZE_HT_BYTES, "shared tables must fit the running-hash-table area");
 constexpr uint32_t ZE_KIND_SCRATCH = 1024;     // per FSE kind in the ht_fin area (ze_build_kind needs >= 784 bytes)
@@ -186,32 +167,36 @@ static_assert(8192 + 3 * ZE_KIND_SCRATCH <= ZE_HTH_BYTES, "tree scratch (7.5 KiB
 
 // ------------------------------------------------------------------------------------------ sequences of one block
 // Code histograms of one block's sequences, added to the region's counters (shared-memory atomics).
-__device__ __forceinline__ void ze_seq_hist(const uint2* __restrict__ seqs, uint32_t N, uint32_t* cnt, uint32_t lane) {
+__device__ __forceinline__ void ze_seq_hist(const uint2* __restrict__ seqs, uint32_t N, uint32_t* cnt, const uint8_t* ll_code, const uint8_t* ml_code, uint32_t lane) {
     uint2 pre = lane < N ? seqs[lane] : make_uint2(0, 0);
     for (uint32_t t0 = 0; t0 < N; t0 += 32) {
         const uint32_t j = t0 + lane;
         const uint2 s = pre;
         if (j + 32 < N) pre = seqs[j + 32];                  // next tile in flight while this one is counted
         if (j < N) {
-            atomicAdd(&cnt[ze_ll_code(s.x & 0xffff)], 1u);
-            atomicAdd(&cnt[ZE_NSYM_LL + ze_ml_code(s.x >> 16)], 1u);
+            const uint32_t ll = s.x & 0xffff, mlb = s.x >> 16;
+            atomicAdd(&cnt[ll < 64 ? ll_code[ll] : (uint32_t)zf::highbit32(ll) + 19], 1u);
+            atomicAdd(&cnt[ZE_NSYM_LL + (mlb < 128 ? ml_code[mlb] : (uint32_t)zf::highbit32(mlb) + 36)], 1u);
             atomicAdd(&cnt[ZE_NSYM_LL + ZE_NSYM_ML + (uint32_t)zf::highbit32(s.y + 3)], 1u);
         }
     }
 }
 
 // Bit stream of one block's sequences with the region's tables, staged in the word buffer `bits` (shared, zeroed here).
-// Returns its size in bytes.  Warp-uniform, N >= 1.
+// Returns its size in bytes.  Warp-uniform, N >= 1.  Per tile of 32 sequences every lane looks up the transforms of its
+// sequence's three codes; lanes 0-2 then walk the three state chains (the only serial part: one 8-byte load, the bit
+// count, one store, one table load per symbol) and every lane packs its own field.
 __device__ __forceinline__ uint32_t ze_encode_seq_bits(const uint2* __restrict__ seqs, uint32_t N, uint32_t* bits, const ZeCTab* ct,
-                                                       const ZeKind kll, const ZeKind kof, const ZeKind kml,
-                                                       uint8_t* codes /*[3][32]*/, uint16_t* stv /*[3][32]*/, uint8_t* stn /*[3][32]*/, uint32_t lane) {
+                                                       const ZeCodeTabs* tabs, const ZeKind kll, const ZeKind kof, const ZeKind kml,
+                                                       uint2* pk /*[3][32]*/, uint32_t* sb /*[3][32]*/, uint32_t lane) {
     for (uint32_t i = lane; i < ZE_STAGE / 4; i += 32) bits[i] = 0;
     __syncwarp();
     uint32_t bitpos = 0;
     uint32_t state = 0;                              // lanes 0..2: OF, ML, LL chains
     const uint16_t* st_tab = lane == 0 ? ct->st_of : lane == 1 ? ct->st_ml : ct->st_ll;
-    const zf::FseCSym* sy = lane == 0 ? ct->sy_of : lane == 1 ? ct->sy_ml : ct->sy_ll;
     const bool rle = (lane == 0 ? kof.mode : lane == 1 ? kml.mode : kll.mode) == 1;
+    const uint2* mypk = pk + (lane < 3 ? lane : 0) * 32;
+    uint32_t* mysb = sb + (lane < 3 ? lane : 0) * 32;
     uint2 pre = lane < N ? seqs[N - 1 - lane] : make_uint2(0, 0);
     for (uint32_t t0 = 0; t0 < N; t0 += 32) {
         const uint32_t j = t0 + lane;                // stream order: j = 0 is the LAST sequence
@@ -221,41 +206,45 @@ __device__ __forceinline__ uint32_t ze_encode_seq_bits(const uint2* __restrict__
         if (j + 32 < N) pre = seqs[N - 1 - (j + 32)];
         if (have) {
             ll = s.x & 0xffff; mlb = s.x >> 16; offb = s.y + 3;       // mlb = matchLength - 3, offb = offset + 3 (no repcodes)
-            llc = ze_ll_code(ll); mlc = ze_ml_code(mlb); ofc = (uint32_t)zf::highbit32(offb);
-            codes[lane] = (uint8_t)ofc; codes[32 + lane] = (uint8_t)mlc; codes[64 + lane] = (uint8_t)llc;
+            llc = ze_ll_code_s(tabs, ll); mlc = ze_ml_code_s(tabs, mlb); ofc = (uint32_t)zf::highbit32(offb);
+            const zf::FseCSym a = ct->sy_of[ofc], b = ct->sy_ml[mlc], c = ct->sy_ll[llc];
+            pk[lane] = make_uint2((uint32_t)a.delta_nb_bits, (uint32_t)a.delta_find_state);
+            pk[32 + lane] = make_uint2((uint32_t)b.delta_nb_bits, (uint32_t)b.delta_find_state);
+            pk[64 + lane] = make_uint2((uint32_t)c.delta_nb_bits, (uint32_t)c.delta_find_state);
         }
         __syncwarp();
         if (lane < 3) {
             const uint32_t cnt = min(32u, N - t0);
             if (rle) {
-                for (uint32_t i = 0; i < cnt; i++) { stv[lane * 32 + i] = 0; stn[lane * 32 + i] = 0; }
+                for (uint32_t i = 0; i < cnt; i++) mysb[i] = 0;
             } else {
-                zf::FseCSym c = sy[codes[lane * 32]];
-                for (uint32_t i = 0; i < cnt; i++) {
-                    const zf::FseCSym cn = sy[codes[lane * 32 + min(i + 1, cnt - 1)]];    // prefetch: independent of the state chain
-                    if (t0 + i == 0) {               // FSE_initCState2
-                        const uint32_t nb = (uint32_t)(c.delta_nb_bits + (1 << 15)) >> 16;
-                        const uint32_t v = (nb << 16) - (uint32_t)c.delta_nb_bits;
-                        state = st_tab[(int32_t)(v >> nb) + c.delta_find_state];
-                        stv[lane * 32 + i] = 0; stn[lane * 32 + i] = 0;
-                    } else {                         // FSE_encodeSymbol
-                        const uint32_t nb = (state + (uint32_t)c.delta_nb_bits) >> 16;
-                        stv[lane * 32 + i] = (uint16_t)(state & ((1u << nb) - 1));
-                        stn[lane * 32 + i] = (uint8_t)nb;
-                        state = st_tab[(int32_t)(state >> nb) + c.delta_find_state];
-                    }
-                    c = cn;
+                uint32_t i = 0;
+                if (t0 == 0) {                       // FSE_initCState2 with the last sequence's symbol
+                    const uint2 c = mypk[0];
+                    const uint32_t nb = (uint32_t)((int32_t)c.x + (1 << 15)) >> 16;
+                    const uint32_t v = (nb << 16) - c.x;
+                    state = st_tab[(int32_t)(v >> nb) + (int32_t)c.y];
+                    mysb[0] = 0;
+                    i = 1;
+                }
+                _Pragma("unroll 4")
+                for (; i < cnt; i++) {               // FSE_encodeSymbol
+                    const uint2 c = mypk[i];
+                    const uint32_t nb = (state + c.x) >> 16;
+                    mysb[i] = (state & ((1u << nb) - 1)) | (nb << 16);
+                    state = st_tab[(int32_t)(state >> nb) + (int32_t)c.y];
                 }
             }
         }
         __syncwarp();
         uint64_t field = 0; uint32_t nb = 0;
         if (have) {
-            const uint32_t llb = g_seq_tables.ll_bits[llc], mlbits = g_seq_tables.ml_bits[mlc];
+            const uint32_t llb = tabs->ll_bits[llc], mlbits = tabs->ml_bits[mlc];
             // order inside a field (first written = lowest bits): OF state, ML state, LL state, LL extra, ML extra, OF extra
-            field = stv[lane]; nb = stn[lane];
-            field |= (uint64_t)stv[32 + lane] << nb; nb += stn[32 + lane];
-            field |= (uint64_t)stv[64 + lane] << nb; nb += stn[64 + lane];
+            const uint32_t b0 = sb[lane], b1 = sb[32 + lane], b2 = sb[64 + lane];
+            field = b0 & 0xffff; nb = b0 >> 16;
+            field |= (uint64_t)(b1 & 0xffff) << nb; nb += b1 >> 16;
+            field |= (uint64_t)(b2 & 0xffff) << nb; nb += b2 >> 16;
             field |= (uint64_t)(ll & ((1u << llb) - 1)) << nb; nb += llb;
             field |= (uint64_t)(mlb & ((1u << mlbits) - 1)) << nb; nb += mlbits;
             field |= (uint64_t)(offb & ((1u << ofc) - 1)) << nb; nb += ofc;
@@ -403,149 +392,91 @@ __global__ void __launch_bounds__(ZE_THREADS, 2) zstd_enc_regions_kernel(const _
     const uint16_t* ht_hist = w > 0 ? ht_fin_all + (w - 1) * ZE_HSIZE_H : nullptr;
 
     // ---- phase 2: greedy LZ parse of the slice, 32 positions per step
-    // Selection (which of the 32 candidate matches survive, left to right) is the only serial part and costs a
-    // handful of instructions per taken match; sequences are written by their own lanes in parallel and the step's
-    // literals (the positions no taken match covers) leave in the same step.
+    // All 32 lanes hash, look up and VERIFY their position (the first ZE_MIN_MATCH bytes); the verified candidates are then
+    // walked left to right — the only serial part — and each taken match is measured by the whole warp: forwards 128 bytes
+    // per probe, backwards over the literals before it (libzstd's "catch up").  Nothing is spent on extending the ~90 % of
+    // the candidates that lie inside an earlier match.  Sequences are written by their own lanes afterwards, and the
+    // step's literals (the positions no taken match covers) leave in the same step.
     uint32_t nseq = 0, nlit = 0;
     if (have_slice) {
         uint32_t anchor = s0, cur = s0;
         while (cur + 4 <= s1 && nseq + 8 <= ZE_MAXSEQ) {                // a step adds at most 8 sequences (min match 4)
             const uint32_t p = cur + lane;
-            const bool valid = p + 4 <= s1;
-            // unaligned 4-byte reads as a rolling pair of aligned words per stream: one new LDS per stream and step
+            const bool valid = p + ZE_MIN_MATCH <= s1;
+            // unaligned reads as a pair of aligned words
             const uint32_t* wp = (const uint32_t*)(buf + (p & ~3u));
             const uint32_t shp = (p & 3) * 8;
-            uint32_t a0 = wp[0], a1 = wp[1];
+            const uint32_t a0 = wp[0], a1 = wp[1];
             const uint32_t v = __funnelshift_r(a0, a1, shp);
+            const uint32_t v4 = (a1 >> shp) & 0xffu;                   // fifth byte
             const uint32_t h = ze_hash(v);
             const uint32_t slot = valid ? ht_run[h] : ZE_EMPTY;
             __syncwarp();
             ze_insert_max(ht_run, h, p, valid);
             uint32_t cand = slot != ZE_EMPTY ? slot : 0u;
-            const uint32_t* wc = (const uint32_t*)(buf + (cand & ~3u));
-            uint32_t shc = (cand & 3) * 8;
-            uint32_t c0 = wc[0], c1 = wc[1];
-            bool ok = slot != ZE_EMPTY && __funnelshift_r(c0, c1, shc) == v;
-#if !ZE_TUNE_BOTH
+            bool ok;
+            {
+                const uint32_t* wc = (const uint32_t*)(buf + (cand & ~3u));
+                const uint32_t shc = (cand & 3) * 8;
+                const uint32_t c0 = wc[0], c1 = wc[1];
+                ok = slot != ZE_EMPTY && __funnelshift_r(c0, c1, shc) == v && ((c1 >> shc) & 0xffu) == v4;
+            }
             if (ht_hist) {                                            // nothing (or a collision) in this slice: the earlier slices
                 const uint32_t hs = (valid && !ok) ? ht_hist[ze_hash_h(v)] : ZE_EMPTY;
                 if (hs != ZE_EMPTY) {
                     const uint32_t* wh = (const uint32_t*)(buf + (hs & ~3u));
                     const uint32_t shh = (hs & 3) * 8;
                     const uint32_t h0 = wh[0], h1 = wh[1];
-                    if (__funnelshift_r(h0, h1, shh) == v) { ok = true; cand = hs; wc = wh; shc = shh; c0 = h0; c1 = h1; }
+                    if (__funnelshift_r(h0, h1, shh) == v && ((h1 >> shh) & 0xffu) == v4) { ok = true; cand = hs; }
                 }
             }
-#endif
-            uint32_t len = 0;
-            if (ok) {
-                len = 4;
-                const uint32_t lim = min(s1 - p, 4 + ZE_LANE_EXT);
-                uint32_t b0 = a0, b1 = a1;
-                for (uint32_t k = 2; len < lim; k++) {
-                    b0 = b1; b1 = wp[k]; c0 = c1; c1 = wc[k];
-                    const uint32_t c = ze_common_bytes(__funnelshift_r(b0, b1, shp) ^ __funnelshift_r(c0, c1, shc));
-                    len += c;
-                    if (c < 4) break;
-                }
-                len = min(len, lim);
-            }
-#if ZE_TUNE_BOTH
-            if (ht_hist) {                                            // experiment: also try the earlier slices, keep the longer
-                const uint32_t hs = valid ? ht_hist[ze_hash_h(v)] : ZE_EMPTY;
-                if (hs != ZE_EMPTY) {
-                    const uint32_t* wh = (const uint32_t*)(buf + (hs & ~3u));
-                    const uint32_t shh = (hs & 3) * 8;
-                    uint32_t h0 = wh[0], h1 = wh[1];
-                    if (__funnelshift_r(h0, h1, shh) == v) {
-                        uint32_t l2 = 4;
-                        const uint32_t lim = min(s1 - p, 4 + ZE_LANE_EXT);
-                        uint32_t b0 = a0, b1 = a1;
-                        for (uint32_t k = 2; l2 < lim; k++) {
-                            b0 = b1; b1 = wp[k]; h0 = h1; h1 = wh[k];
-                            const uint32_t c = ze_common_bytes(__funnelshift_r(b0, b1, shp) ^ __funnelshift_r(h0, h1, shh));
-                            l2 += c;
-                            if (c < 4) break;
-                        }
-                        l2 = min(l2, lim);
-                        if (l2 > len + ZE_TUNE_BOTH - 1) { len = l2; ok = true; cand = hs; }
-                    }
-                }
-            }
-#endif
-            const uint32_t mask = __ballot_sync(TS_FULL, ok && len >= ZE_MIN_MATCH);
-            // Greedy selection, left to right.  Every lane precomputes where its match would end and which candidate would
-            // come next, so one shuffle per taken match walks the chain (the only serial part of the parse).
-            const uint32_t e = lane + len;
-            const uint32_t mnext = e < 32 ? mask & (0xffffffffu << e) : 0u;
-            const uint32_t nxt = mnext ? (uint32_t)__ffs((int)mnext) - 1 : 32u;
-            const bool capped = ok && len == 4 + ZE_LANE_EXT && p + len < s1;
-#if ZE_TUNE_LAZY
-            // lazy evaluation: a match is passed over when the next position starts a clearly longer one
-            const uint32_t len_next = __shfl_down_sync(TS_FULL, len, 1);
-            const bool defer = lane < 31 && ((mask >> (lane + 1)) & 1) && !capped && len_next >= len + ZE_TUNE_LAZY;
-            const uint32_t packed = e | (nxt << 8) | (capped ? 1u << 16 : 0u) | (defer ? 1u << 17 : 0u);
-#else
-            const uint32_t packed = e | (nxt << 8) | (capped ? 1u << 16 : 0u);
-#endif
-            uint32_t taken = 0, pos = 0;
+            const uint32_t mask = __ballot_sync(TS_FULL, ok);
+            // walk the candidates
+            uint32_t taken = 0, cov = 0;
+            uint32_t my_ll = 0, my_ml = 0;                             // sequence of this lane, if it is taken
+            uint32_t prev_end = anchor;
             uint32_t f = mask ? (uint32_t)__ffs((int)mask) - 1 : 32u;
             while (f < 32) {
-                const uint32_t info = __shfl_sync(TS_FULL, packed, f);
-                uint32_t end = info & 0xffu, nf = (info >> 8) & 0xffu;
-#if ZE_TUNE_LAZY
-                if (info & (1u << 17)) { f = f + 1; continue; }
-#endif
-                if ((info >> 16) & 1) {                                // warp-wide extension of a long match
-                    uint32_t L = 4 + ZE_LANE_EXT;
-                    const uint32_t off = __shfl_sync(TS_FULL, p - cand, f);
-                    const uint32_t mpos = cur + f;
-                    while (true) {
-                        const uint32_t q = mpos + L + 4 * lane;
-                        uint32_t c = 0;
-                        if (q < s1) {
-                            c = ze_common_bytes(ld_u32_unaligned(buf + q) ^ ld_u32_unaligned(buf + q - off));
-                            c = min(c, s1 - q);
-                        }
-                        const uint32_t stop = __ballot_sync(TS_FULL, c < 4);
-                        if (stop) {
-                            const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
-                            L += 4 * fl + __shfl_sync(TS_FULL, c, fl);
-                            break;
-                        }
-                        L += 128;
+                const uint32_t pf = cur + f;
+                const uint32_t cf = __shfl_sync(TS_FULL, cand, f);
+                // forwards: lane l compares the 4 bytes at +4 + 4l (the first 4 are known to match)
+                uint32_t L = 4;
+                while (true) {
+                    const uint32_t q = pf + L + 4 * lane;
+                    uint32_t c = 0;
+                    if (q < s1) {
+                        c = ze_common_bytes(ld_u32_unaligned(buf + q) ^ ld_u32_unaligned(buf + (q - pf + cf)));
+                        c = min(c, s1 - q);
                     }
-                    if (lane == f) len = L;
-                    end = f + L;
-                    const uint32_t m2 = end < 32 ? mask & (0xffffffffu << end) : 0u;
-                    nf = m2 ? (uint32_t)__ffs((int)m2) - 1 : 32u;
+                    const uint32_t stop = __ballot_sync(TS_FULL, c < 4);
+                    if (stop) {
+                        const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
+                        L += 4 * fl + __shfl_sync(TS_FULL, c, fl);
+                        break;
+                    }
+                    L += 128;
                 }
-                taken |= 1u << f;
-                pos = end;
-                f = nf;
-            }
-            uint32_t cov = 0;                                          // positions of this step covered by a taken match
-            if (taken) {
-                const bool mine_taken = (taken >> lane) & 1;
-                const uint32_t my_end = p + len;                       // meaningful on taken lanes
-                const uint32_t lower = taken & ((1u << lane) - 1);
-                const uint32_t prev_lane = lower ? (uint32_t)(31 - __clz((int)lower)) : 0u;
-                uint32_t prev_end = __shfl_sync(TS_FULL, my_end, prev_lane);
-                if (!lower) prev_end = anchor;
+                // backwards over this step's literals: lane l compares the byte 1 + l before the match
                 uint32_t bk = 0;
-#if ZE_TUNE_BACK
-                if (mine_taken) {                                      // catch-up: grow the match backwards over this step's literals
-                    const uint32_t room = min(min(p - max(prev_end, cur), cand), (uint32_t)ZE_TUNE_BACK);
-                    while (bk < room && buf[p - 1 - bk] == buf[cand - 1 - bk]) bk++;
+                {
+                    const uint32_t room = min(pf - max(prev_end, cur), cf);
+                    const bool diff = lane >= room || buf[pf - 1 - lane] != buf[cf - 1 - lane];
+                    bk = (uint32_t)__ffs((int)__ballot_sync(TS_FULL, diff)) - 1;        // lane 31 always differs or is >= room (room <= 31)
                 }
-#endif
-                if (mine_taken)
-                    seqs[nseq + (uint32_t)__popc(lower)] = make_uint2((p - bk - prev_end) | ((len + bk - 3) << 16), p - cand);
+                const uint32_t start = f - bk, tl = L + bk;            // in lanes of this step
+                if (lane == f) { my_ll = pf - bk - prev_end; my_ml = tl; }
+                taken |= 1u << f;
+                cov |= (tl >= 32 - start ? 0xffffffffu : (1u << tl) - 1) << start;
+                prev_end = pf + L;
+                const uint32_t end = f + L;
+                const uint32_t rest = end < 32 ? mask & (0xffffffffu << end) : 0u;
+                f = rest ? (uint32_t)__ffs((int)rest) - 1 : 32u;
+            }
+            if (taken) {
+                if ((taken >> lane) & 1)
+                    seqs[nseq + (uint32_t)__popc(taken & ((1u << lane) - 1))] = make_uint2(my_ll | ((my_ml - 3) << 16), p - cand);
                 nseq += (uint32_t)__popc(taken);
-                anchor = cur + pos;
-                const uint32_t sl = lane - bk, tl = len + bk;          // covered span of the step starts bk lanes earlier
-                const uint32_t span = mine_taken ? (tl >= 32 - sl ? 0xffffffffu << sl : ((1u << tl) - 1) << sl) : 0u;
-                cov = __reduce_or_sync(TS_FULL, span);
+                anchor = prev_end;
             }
             // literals of the step, in order: one byte per uncovered position below the end of the slice
             {
@@ -572,10 +503,15 @@ __global__ void __launch_bounds__(ZE_THREADS, 2) zstd_enc_regions_kernel(const _
     ZeShared* S = (ZeShared*)(smem + ZE_OFF_RUN);
     for (uint32_t i = tid; i < sizeof(ZeShared) / 4; i += ZE_THREADS) ((uint32_t*)S)[i] = 0;
     __syncthreads();
+    if (tid < 64) S->tabs.ll_code[tid] = g_seq_tables.ll_code[tid];
+    if (tid < 128) S->tabs.ml_code[tid] = g_seq_tables.ml_code[tid];
+    if (tid < 36) S->tabs.ll_bits[tid] = g_seq_tables.ll_bits[tid];
+    if (tid >= 64 && tid < 64 + 53) S->tabs.ml_bits[tid - 64] = g_seq_tables.ml_bits[tid - 64];
+    __syncthreads();
     if (have_slice) {
         _Pragma("unroll 2")
         for (uint32_t i = lane; i < nlit; i += 32) atomicAdd(&S->hist[lits[i]], 1u);
-        ze_seq_hist(seqs, nseq, S->cnt, lane);
+        ze_seq_hist(seqs, nseq, S->cnt, S->tabs.ll_code, S->tabs.ml_code, lane);
     }
     __syncthreads();
     uint32_t nseq_total = 0, nlit_total = 0;
@@ -619,10 +555,9 @@ __global__ void __launch_bounds__(ZE_THREADS, 2) zstd_enc_regions_kernel(const _
         __syncwarp();
         uint32_t sbytes = 0;
         if (nseq) {
-            uint8_t* codes = stage + ZE_SEQ_AUX_OFF;
-            uint16_t* stv = (uint16_t*)(codes + 96);
-            uint8_t* stn = (uint8_t*)(stv + 96);
-            sbytes = ze_encode_seq_bits(seqs, nseq, (uint32_t*)stage, &S->ct, R->kll, R->kof, R->kml, codes, stv, stn, lane);
+            uint2* pk = (uint2*)(stage + ZE_SEQ_AUX_OFF);
+            uint32_t* sb = (uint32_t*)(pk + 96);
+            sbytes = ze_encode_seq_bits(seqs, nseq, (uint32_t*)stage, &S->ct, &S->tabs, R->kll, R->kof, R->kml, pk, sb, lane);
             ze_warp_copy(slot_b, stage, sbytes, lane);
         }
         if (lane == 0) R->seq_bytes[w] = sbytes;
