@@ -18,6 +18,7 @@
 #include "ts_common.cuh"
 #include "aesgcm.cuh"
 #include "index_scan.cuh"
+#include "pack.cuh"
 #include "rt.h"
 #include "launch_prof.h"
 #include "zstd_enc.cuh"
@@ -65,6 +66,7 @@ struct Work {
     uint8_t* d_orig = nullptr;     // max_batch * chunk_cap
     uint8_t* d_frames = nullptr;   // max_batch * frame_stride        (zstd frames, 16-byte aligned slots)
     uint8_t* d_xf = nullptr;       // max_batch * slot_stride         (transformed slots)
+    uint8_t* d_pack = nullptr;     // max_batch * slot_stride         (transformed chunks back to back: what one D2H takes home)
     uint8_t* d_desc = nullptr;  uint8_t* h_desc = nullptr;  size_t desc_bytes = 0;
     Desc dd{}, hd{};               // device / pinned-host views of the descriptor block
     uint4* d_partials = nullptr;  uint32_t max_ranges = 0;
@@ -123,6 +125,7 @@ static int work_init_impl(tsgpu_ctx* c, Work& w, int device) {
     RT(rt::malloc_device((void**)&w.d_orig, nb * align_up(c->chunk_cap, 16) + 256));
     RT(rt::malloc_device((void**)&w.d_frames, nb * c->frame_stride + 256));
     RT(rt::malloc_device((void**)&w.d_xf, nb * c->slot_stride + 256));
+    RT(rt::malloc_device((void**)&w.d_pack, nb * c->slot_stride + 256));
     carve_desc(nullptr, c->max_batch, w.dd, &w.desc_bytes);
     RT(rt::malloc_device((void**)&w.d_desc, w.desc_bytes));
     RT(rt::malloc_host((void**)&w.h_desc, w.desc_bytes));
@@ -144,7 +147,7 @@ static void work_free(Work& w) {
     rt::set_device(w.device);
     if (w.stream) rt::stream_sync(w.stream);
     if (w.out_stream) rt::stream_sync(w.out_stream);
-    rt::free_device(w.d_orig); rt::free_device(w.d_frames); rt::free_device(w.d_xf);
+    rt::free_device(w.d_orig); rt::free_device(w.d_frames); rt::free_device(w.d_xf); rt::free_device(w.d_pack);
     rt::free_device(w.d_desc); rt::free_host(w.h_desc);
     rt::free_device(w.d_partials); rt::free_device(w.d_keyctx); rt::free_host(w.h_sizes);
     zstd_enc_scratch_free(w.zenc); zstd_dec_scratch_free(w.zdec);
@@ -296,7 +299,6 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
     uint32_t cur_max = cs;
     xb.final_base = w.d_orig; xb.final_stride = cs; xb.final_head = 0;
     if (flags & TSGPU_FLAG_ZSTD) {
-        if (!(flags & TSGPU_FLAG_AES)) { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }   // d_frames is the final buffer
         int rc = zstd_compress_batch(w.zenc, st, cur_base, cur_off, cur_len, nb, cs, w.d_frames, w.dd.b_off, w.dd.b_len, c->prof);
         if (rc) return fail(rc, "zstd compress: %s", zstd_last_error());
         cur_base = w.d_frames; cur_off = w.dd.b_off; cur_len = w.dd.b_len; cur_max = (uint32_t)frame_bound(cs);
@@ -305,13 +307,22 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
     if (flags & TSGPU_FLAG_AES) {
         const bool key_ready = w.key_valid && memcmp(&w.key_rk, &rk, sizeof rk) == 0;
         w.key_rk = rk; w.key_valid = false;                  // valid again once the stage has been enqueued
-        { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }                                  // d_xf is the final buffer
         int rc = gcm_stage<true>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, w.d_xf, w.dd.c_off, w.dd.c_len,
                                  w.dd.ivs, w.dd.aad, aad_len, w.dd.status, nb, cur_max, w.d_partials, w.max_ranges);
         if (rc) return rc;
         w.key_valid = true;
         cur_len = w.dd.c_len;
         xb.final_base = w.d_xf; xb.final_stride = c->slot_stride; xb.final_head = TSGPU_SLOT_HEAD;
+    }
+    // the transformed chunks, back to back, so the batch leaves in one copy (the previous batch's copy-out may still be
+    // reading d_pack: this is the first kernel of the batch that has to wait for it)
+    { int rcw = wait_copies_out(w, st); if (rcw) return rcw; }
+    {
+        PackArgs P;
+        P.base = xb.final_base; P.stride = xb.final_stride; P.head = xb.final_head; P.len = cur_len; P.n = nb; P.out = w.d_pack;
+        const uint64_t longest = (flags & TSGPU_FLAG_ZSTD) ? frame_bound(cs) + 28 : (uint64_t)cs + 28;
+        TS_LAUNCH_P(c->prof, "pack_chunks", pack_chunks_kernel, dim3((uint32_t)((longest + PACK_PIECE - 1) / PACK_PIECE), nb), dim3(PACK_T), 0, st, P);
+        CHECK_LAUNCH("pack_chunks_kernel");
     }
     RT(rt::d2h(w.h_sizes, cur_len, 4ull * nb, st));
     RT(rt::event_record(w.ev_sizes, st));
@@ -405,13 +416,11 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
         RT(rt::set_device(w.device));
         RT(rt::event_sync(w.ev_sizes));
         rt::stream_t os = c->split_out ? w.out_stream : w.stream;    // the sizes event has completed: nothing to order on out_stream
-        for (uint32_t i = 0; i < xb.nb; i++) {
-            uint32_t sz = w.h_sizes[i];
-            if (dst_off + sz > dst_cap) return fail(TSGPU_E_SHORT, "dst too small");
-            RT(rt::d2h(dst + dst_off, xb.final_base + (uint64_t)i * xb.final_stride + xb.final_head, sz, os));
-            transformed_sizes[xb.c0 + i] = sz;
-            dst_off += sz;
-        }
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < xb.nb; i++) { transformed_sizes[xb.c0 + i] = w.h_sizes[i]; total += w.h_sizes[i]; }
+        if (dst_off + total > dst_cap) return fail(TSGPU_E_SHORT, "dst too small");
+        if (total) RT(rt::d2h(dst + dst_off, w.d_pack, total, os));  // one copy per batch: the chunks were packed on the device
+        dst_off += total;
         RT(rt::event_record(w.ev_done, os));
         w.out_pending = c->split_out;
         return TSGPU_OK;

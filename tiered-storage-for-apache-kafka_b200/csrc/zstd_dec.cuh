@@ -572,6 +572,7 @@ __device__ __forceinline__ uint32_t zd_block_entropy(const uint8_t* blk, uint32_
 constexpr int ZX_T = 512;
 struct ZxShared {
     uint32_t ostart[ZX_T + 1];               // output position of each sequence of the step (+ end)
+    uint32_t mlen[ZX_T], moff[ZX_T];         // match length / offset of each sequence of the step (source forwarding)
     uint32_t dbits[ZX_T / 32];               // done bit per sequence of the step; word w is written by warp w only
     uint64_t wsum[ZX_T / 32];
     uint64_t tot;
@@ -688,6 +689,7 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
             const uint32_t o_start = op + (uint32_t)(inc >> 32) - ll - ml, l_start = lp + (uint32_t)inc - ll, m_start = o_start + ll;
             if (mine && (off > m_start || (!far && off > m_start - win_pos0))) bad = true;
             sh->ostart[tid] = mine ? o_start : op + tot_o;
+            sh->mlen[tid] = mine ? ml : 0; sh->moff[tid] = off;
             const uint32_t preset = __ballot_sync(TS_FULL, !mine || ml == 0);         // nothing to wait for on these
             if (lane == 0) sh->dbits[w] = preset;
             if (tid == 0) sh->ostart[ZX_T] = op + tot_o;
@@ -720,23 +722,40 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
                     else { for (uint32_t k = 32 + lane; k < fn; k += 32) wout[fo + k] = lit[fl + k]; }
                 }
             }
-            // ---- producers of this match inside the step: sequences [ja, jb] cover the part of its source other sequences write
-            const uint32_t s_lo = m_start - off;                          // first source byte
-            const uint32_t s_hi = min(s_lo + ml, m_start);                // one past the last source byte written by someone else
+            __syncthreads();                                              // literals, ostart, mlen, moff, dbits visible to everyone
+            // ---- producers of this match inside the step: sequences [ja, jb] cover the part of its source other sequences write.
+            // Source forwarding first: text matched against its nearest earlier occurrence makes chains of dozens of matches
+            // inside one step, each copying what the previous one wrote.  When a source lies entirely inside ONE earlier match
+            // of the step, the bytes are, by the definition of an LZ copy, the bytes that match itself copies — so this match
+            // can read THEM instead (offset += that match's offset) and no longer depends on it.  A few hops shorten the
+            // chains to what really is a partial overlap.
+            uint32_t s_lo = m_start - off;                                // first source byte
+            uint32_t s_hi = min(s_lo + ml, m_start);                      // one past the last source byte written by someone else
             uint32_t ja = 0, jb = 0;
             bool inside = false;                                          // does the source reach into this step's output?
-            if (mine && ml && s_hi > op) {
-                inside = true;
-                uint32_t lo = 0, hi = tid;                                // last j <= tid with ostart[j] <= x
-                const uint32_t x = max(s_lo, op);
-                while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] <= x) lo = mid; else hi = mid - 1; }
-                ja = lo;
-                hi = tid;
-                while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] < s_hi) lo = mid; else hi = mid - 1; }
-                jb = lo;
-                if (jb == tid) { if (tid == 0 || ja == tid) inside = false; else jb = tid - 1; }   // own literals precede the match: never a producer
+            if (mine && ml) {
+                for (uint32_t hop = 0; ; hop++) {
+                    inside = false;
+                    if (s_hi <= op) break;
+                    inside = true;
+                    uint32_t lo = 0, hi = tid;                            // last j <= tid with ostart[j] <= x
+                    const uint32_t x = max(s_lo, op);
+                    while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] <= x) lo = mid; else hi = mid - 1; }
+                    ja = lo;
+                    hi = tid;
+                    while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] < s_hi) lo = mid; else hi = mid - 1; }
+                    jb = lo;
+                    if (jb == tid) { if (tid == 0 || ja == tid) { inside = false; break; } jb = tid - 1; }   // own literals precede the match: never a producer
+                    if (hop >= 12 || off < ml || ja != jb || s_lo < op) break;
+                    const uint32_t pend_ = sh->ostart[ja + 1], pst = pend_ - sh->mlen[ja];   // producer's match bytes [pst, pend_)
+                    if (s_lo < pst || s_hi > pend_) {
+                        if (s_hi <= pst) inside = false;                  // only the producer's literals: written already
+                        break;
+                    }
+                    const uint32_t po = sh->moff[ja];
+                    off += po; s_lo -= po; s_hi -= po;                    // read what the producer reads
+                }
             }
-            __syncthreads();                                              // literals, ostart, dbits visible to everyone
             // ---- matches: every warp runs its own loop; a lane copies once the done bits of its producers are set
             {
                 bool done = !mine || ml == 0;

@@ -38,7 +38,7 @@ constexpr uint32_t ZR = ZB * ZR_SLICES;        // 64 KiB region
 #ifndef ZE_TUNE_HLOG_H
 #define ZE_TUNE_HLOG_H 11
 #endif
-constexpr int ZE_HLOG = ZE_TUNE_HLOG;          // per-slice hash tables: 2^10 x u16 (region-relative position)
+constexpr int ZE_HLOG = ZE_TUNE_HLOG;          // per-slice running tables: 2^10 x u16 (region-relative position)
 constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
 constexpr int ZE_HLOG_H = ZE_TUNE_HLOG_H;      // history tables (last occurrence in all earlier slices): 7 of them
 constexpr uint32_t ZE_HSIZE_H = 1u << ZE_HLOG_H;
@@ -107,8 +107,10 @@ __device__ __forceinline__ void ze_put_bits(uint32_t* words, uint32_t o, uint64_
 }
 
 // Hash-table insert where the HIGHEST position of the warp's step wins a shared slot — the hardware would keep an
-// arbitrary one, which made frames differ between runs; retried uploads must produce identical objects.  Lanes with the
-// same slot find each other with match.any; only the highest of them stores.
+// arbitrary one, which made frames differ between runs; retried uploads must produce identical objects.  Lanes re-store
+// until no lower position is left in a slot: one round when the step has no slot collision, one more per extra peer.
+// (match.any would find the peers in one instruction but serialises on the number of distinct values: measured 20 ms per
+// GiB on random data; 32-bit slots would allow atomicMax but halve the table at equal shared memory: -1.7 % ratio.)
 #ifdef TSGPU_SIMT
 static inline unsigned __match_any_sync(unsigned, unsigned v) {
     simt::Warp& w = simt::g_blk->warps[simt::g_cur->warp];
@@ -122,9 +124,13 @@ static inline unsigned __match_any_sync(unsigned, unsigned v) {
 #endif
 
 __device__ __forceinline__ void ze_insert_max(uint16_t* ht, uint32_t h, uint32_t p, bool valid) {
-    const uint32_t peers = __match_any_sync(TS_FULL, valid ? h : 0xffff0000u | (threadIdx.x & 31));
-    if (valid && (peers >> (threadIdx.x & 31)) == 1u) ht[h] = (uint16_t)p;     // no peer in a higher lane
-    __syncwarp();
+    if (valid) ht[h] = (uint16_t)p;
+    while (true) {
+        __syncwarp();
+        const bool lost = valid && ht[h] < p;            // a lower position of this step sits in the slot
+        if (!__any_sync(TS_FULL, lost)) break;
+        if (lost) ht[h] = (uint16_t)p;
+    }
 }
 
 }  // namespace ts
@@ -392,44 +398,47 @@ __global__ void __launch_bounds__(ZE_THREADS, 2) zstd_enc_regions_kernel(const _
     const uint16_t* ht_hist = w > 0 ? ht_fin_all + (w - 1) * ZE_HSIZE_H : nullptr;
 
     // ---- phase 2: greedy LZ parse of the slice, 32 positions per step
-    // All 32 lanes hash, look up and VERIFY their position (the first ZE_MIN_MATCH bytes); the verified candidates are then
-    // walked left to right — the only serial part — and each taken match is measured by the whole warp: forwards 128 bytes
-    // per probe, backwards over the literals before it (libzstd's "catch up").  Nothing is spent on extending the ~90 % of
-    // the candidates that lie inside an earlier match.  Sequences are written by their own lanes afterwards, and the
-    // step's literals (the positions no taken match covers) leave in the same step.
+    // Straight-line work per lane (no loops, no divergence worth the name): hash, look up, verify the candidate on 4 bytes,
+    // measure the next 4 forwards and the 4 before it backwards.  The verified candidates are then walked left to right —
+    // the only serial part: a match that ran through all 8 measured bytes is extended by the whole warp (128 bytes per
+    // probe), every taken match grows backwards over the literals before it (libzstd's "catch up", up to 4 bytes).
+    // Sequences are written by their own lanes afterwards; the step's literals leave in the same step.
     uint32_t nseq = 0, nlit = 0;
     if (have_slice) {
         uint32_t anchor = s0, cur = s0;
         while (cur + 4 <= s1 && nseq + 8 <= ZE_MAXSEQ) {                // a step adds at most 8 sequences (min match 4)
             const uint32_t p = cur + lane;
             const bool valid = p + ZE_MIN_MATCH <= s1;
-            // unaligned reads as a pair of aligned words
+            // 12 bytes around the position as aligned words: [p-4, p+8)
             const uint32_t* wp = (const uint32_t*)(buf + (p & ~3u));
             const uint32_t shp = (p & 3) * 8;
-            const uint32_t a0 = wp[0], a1 = wp[1];
+            const uint32_t am = p >= 4 ? wp[-1] : 0u, a0 = wp[0], a1 = wp[1], a2 = wp[2];
             const uint32_t v = __funnelshift_r(a0, a1, shp);
-            const uint32_t v4 = (a1 >> shp) & 0xffu;                   // fifth byte
             const uint32_t h = ze_hash(v);
             const uint32_t slot = valid ? ht_run[h] : ZE_EMPTY;
             __syncwarp();
-            ze_insert_max(ht_run, h, p, valid);
+            ze_insert_max(ht_run, h, p, valid);                        // the highest position of the step wins a shared slot
             uint32_t cand = slot != ZE_EMPTY ? slot : 0u;
-            bool ok;
-            {
-                const uint32_t* wc = (const uint32_t*)(buf + (cand & ~3u));
-                const uint32_t shc = (cand & 3) * 8;
-                const uint32_t c0 = wc[0], c1 = wc[1];
-                ok = slot != ZE_EMPTY && __funnelshift_r(c0, c1, shc) == v && ((c1 >> shc) & 0xffu) == v4;
-            }
+            const uint32_t* wc = (const uint32_t*)(buf + (cand & ~3u));
+            uint32_t shc = (cand & 3) * 8;
+            uint32_t cm = cand >= 4 ? wc[-1] : 0u, c0 = wc[0], c1 = wc[1], c2 = wc[2];
+            bool ok = slot != ZE_EMPTY && __funnelshift_r(c0, c1, shc) == v;
             if (ht_hist) {                                            // nothing (or a collision) in this slice: the earlier slices
                 const uint32_t hs = (valid && !ok) ? ht_hist[ze_hash_h(v)] : ZE_EMPTY;
                 if (hs != ZE_EMPTY) {
                     const uint32_t* wh = (const uint32_t*)(buf + (hs & ~3u));
                     const uint32_t shh = (hs & 3) * 8;
                     const uint32_t h0 = wh[0], h1 = wh[1];
-                    if (__funnelshift_r(h0, h1, shh) == v && ((h1 >> shh) & 0xffu) == v4) { ok = true; cand = hs; }
+                    if (__funnelshift_r(h0, h1, shh) == v) { ok = true; cand = hs; shc = shh; cm = hs >= 4 ? wh[-1] : 0u; c0 = h0; c1 = h1; c2 = wh[2]; }
                 }
             }
+            // forwards: bytes 4..7; backwards: how many of the 4 bytes before the position match (never past the candidate's start)
+            uint32_t len = 4 + ze_common_bytes(__funnelshift_r(a1, a2, shp) ^ __funnelshift_r(c1, c2, shc));
+            len = min(len, s1 - p);
+            ok = ok && valid && len >= ZE_MIN_MATCH;
+            const uint32_t xb = __funnelshift_r(am, a0, shp) ^ __funnelshift_r(cm, c0, shc);
+            const uint32_t bkr = min((uint32_t)__clz((int)xb) >> 3, min(cand, 4u));
+            const uint32_t packed = len | (bkr << 8);
             const uint32_t mask = __ballot_sync(TS_FULL, ok);
             // walk the candidates
             uint32_t taken = 0, cov = 0;
@@ -438,31 +447,27 @@ __global__ void __launch_bounds__(ZE_THREADS, 2) zstd_enc_regions_kernel(const _
             uint32_t f = mask ? (uint32_t)__ffs((int)mask) - 1 : 32u;
             while (f < 32) {
                 const uint32_t pf = cur + f;
-                const uint32_t cf = __shfl_sync(TS_FULL, cand, f);
-                // forwards: lane l compares the 4 bytes at +4 + 4l (the first 4 are known to match)
-                uint32_t L = 4;
-                while (true) {
-                    const uint32_t q = pf + L + 4 * lane;
-                    uint32_t c = 0;
-                    if (q < s1) {
-                        c = ze_common_bytes(ld_u32_unaligned(buf + q) ^ ld_u32_unaligned(buf + (q - pf + cf)));
-                        c = min(c, s1 - q);
+                const uint32_t info = __shfl_sync(TS_FULL, packed, f);
+                uint32_t L = info & 0xffu;
+                if (L == 8 && pf + 8 < s1) {                           // ran through the measured bytes: lane l compares the 4 bytes at +8 + 4l
+                    const uint32_t cf = __shfl_sync(TS_FULL, cand, f);
+                    while (true) {
+                        const uint32_t q = pf + L + 4 * lane;
+                        uint32_t c = 0;
+                        if (q < s1) {
+                            c = ze_common_bytes(ld_u32_unaligned(buf + q) ^ ld_u32_unaligned(buf + (q - pf + cf)));
+                            c = min(c, s1 - q);
+                        }
+                        const uint32_t stop = __ballot_sync(TS_FULL, c < 4);
+                        if (stop) {
+                            const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
+                            L += 4 * fl + __shfl_sync(TS_FULL, c, fl);
+                            break;
+                        }
+                        L += 128;
                     }
-                    const uint32_t stop = __ballot_sync(TS_FULL, c < 4);
-                    if (stop) {
-                        const uint32_t fl = (uint32_t)__ffs((int)stop) - 1;
-                        L += 4 * fl + __shfl_sync(TS_FULL, c, fl);
-                        break;
-                    }
-                    L += 128;
                 }
-                // backwards over this step's literals: lane l compares the byte 1 + l before the match
-                uint32_t bk = 0;
-                {
-                    const uint32_t room = min(pf - max(prev_end, cur), cf);
-                    const bool diff = lane >= room || buf[pf - 1 - lane] != buf[cf - 1 - lane];
-                    bk = (uint32_t)__ffs((int)__ballot_sync(TS_FULL, diff)) - 1;        // lane 31 always differs or is >= room (room <= 31)
-                }
+                const uint32_t bk = min(info >> 8, pf - max(prev_end, cur));     // backwards only over this step's literals
                 const uint32_t start = f - bk, tl = L + bk;            // in lanes of this step
                 if (lane == f) { my_ll = pf - bk - prev_end; my_ml = tl; }
                 taken |= 1u << f;
