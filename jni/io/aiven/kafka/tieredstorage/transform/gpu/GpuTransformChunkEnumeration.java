@@ -3,6 +3,8 @@ package io.aiven.kafka.tieredstorage.transform.gpu;
 import java.io.IOException;
 import java.io.InputStream;
 import java.nio.ByteBuffer;
+import java.nio.channels.Channels;
+import java.nio.channels.ReadableByteChannel;
 import java.security.SecureRandom;
 import java.util.ArrayDeque;
 import java.util.NoSuchElementException;
@@ -15,30 +17,44 @@ import io.aiven.kafka.tieredstorage.transform.TransformChunkEnumeration;
  * (RemoteStorageManager.java:434-453): reads a batch of original chunks from the segment stream, transforms the
  * whole batch on the GPU with one native call and serves one byte[] per nextElement(), so TransformFinisher,
  * the ChunkIndex builders and the storage backends are unchanged.
+ *
+ * <p>The segment stream is read straight into a pinned direct buffer (no byte[] bounce in front of the H2D copy).
+ * The two pinned staging buffers come from a per-context {@link PinnedPool} and go back to it when the stream is
+ * exhausted, on {@link #close()}, or — as a last resort — when the enumeration is garbage collected.
  */
-public class GpuTransformChunkEnumeration implements TransformChunkEnumeration {
+public class GpuTransformChunkEnumeration implements TransformChunkEnumeration, AutoCloseable {
     private final long ctx;
-    private final InputStream inputStream;
+    private final ReadableByteChannel channel;
     private final int originalChunkSize;
     private final int flags;
     private final DataKeyAndAAD keyAndAad;   // null when encryption is off
     private final int batchChunks;
     private final SecureRandom random = new SecureRandom();
     private final ArrayDeque<byte[]> ready = new ArrayDeque<>();
-    private final ByteBuffer src;
-    private final ByteBuffer dst;
+    private final PinnedPool pool;
+    private PinnedPool.Lease src;
+    private PinnedPool.Lease dst;
     private boolean eof = false;
 
-    public GpuTransformChunkEnumeration(final long ctx, final InputStream inputStream, final int originalChunkSize,
-                                        final boolean compression, final DataKeyAndAAD keyAndAad, final int batchChunks) {
+    public GpuTransformChunkEnumeration(final long ctx, final PinnedPool pool, final InputStream inputStream,
+                                        final int originalChunkSize, final boolean compression,
+                                        final DataKeyAndAAD keyAndAad, final int batchChunks) {
+        if (inputStream == null) {
+            throw new NullPointerException("inputStream cannot be null");
+        }
+        if (originalChunkSize < 0) {
+            throw new IllegalArgumentException("Original chunk size must be non-negative, " + originalChunkSize + " given");
+        }
         this.ctx = ctx;
-        this.inputStream = inputStream;
+        this.pool = pool;
+        this.channel = Channels.newChannel(inputStream);
         this.originalChunkSize = originalChunkSize;
         this.flags = (compression ? TsGpu.FLAG_ZSTD : 0) | (keyAndAad != null ? TsGpu.FLAG_AES : 0);
         this.keyAndAad = keyAndAad;
         this.batchChunks = batchChunks;
-        this.src = TsGpu.allocPinned((long) batchChunks * originalChunkSize);
-        this.dst = TsGpu.allocPinned(TsGpu.transformBound(flags, (long) batchChunks * originalChunkSize, originalChunkSize));
+        final long batchBytes = (long) batchChunks * originalChunkSize;
+        this.src = pool.lease(batchBytes);
+        this.dst = pool.lease(TsGpu.transformBound(flags, batchBytes, originalChunkSize));
     }
 
     @Override
@@ -75,41 +91,65 @@ public class GpuTransformChunkEnumeration implements TransformChunkEnumeration {
             return;
         }
         try {
-            src.clear();
-            final byte[] buf = new byte[originalChunkSize];
-            int chunks = 0;
-            long total = 0;
-            while (chunks < batchChunks) {
-                final int n = inputStream.readNBytes(buf, 0, originalChunkSize);
-                if (n == 0) {
-                    eof = true;
-                    break;
-                }
-                src.put(buf, 0, n);
-                total += n;
-                chunks++;
-                if (n < originalChunkSize) {
+            final ByteBuffer in = src.buffer();
+            in.clear();
+            in.limit((int) Math.min(in.capacity(), (long) batchChunks * originalChunkSize));
+            while (in.hasRemaining()) {                 // the stream lands directly in pinned memory
+                if (channel.read(in) < 0) {
                     eof = true;
                     break;
                 }
             }
-            if (chunks == 0) {
+            final long total = in.position();
+            if (total == 0) {
+                release();
                 return;
+            }
+            final int chunks = (int) ((total + originalChunkSize - 1) / originalChunkSize);
+            if (total < (long) batchChunks * originalChunkSize) {
+                eof = true;                              // a short batch ends the segment (BaseTransformChunkEnumeration:61-93)
             }
             final byte[] ivs = new byte[chunks * TsGpu.IV_SIZE];
             random.nextBytes(ivs);
             final int[] sizes = new int[chunks];
-            final int n = TsGpu.transform(ctx, flags, src, total, originalChunkSize,
+            final ByteBuffer out = dst.buffer();
+            final int n = TsGpu.transform(ctx, flags, in, total, originalChunkSize,
                 keyAndAad == null ? null : keyAndAad.dataKey.getEncoded(), keyAndAad == null ? null : keyAndAad.aad,
-                ivs, dst, sizes);
-            dst.clear();
+                ivs, out, sizes);
+            out.clear();
             for (int i = 0; i < n; i++) {
                 final byte[] chunk = new byte[sizes[i]];
-                dst.get(chunk);
+                out.get(chunk);
                 ready.add(chunk);
             }
+            if (eof) {
+                release();
+            }
         } catch (final IOException e) {
+            release();
             throw new RuntimeException(e);
+        } catch (final RuntimeException e) {
+            release();
+            throw e;
         }
+    }
+
+    private void release() {
+        if (src != null) {
+            src.close();
+            src = null;
+        }
+        if (dst != null) {
+            dst.close();
+            dst = null;
+        }
+    }
+
+    /** Returns the pinned staging buffers to the pool.  Idempotent; also called when the stream is exhausted. */
+    @Override
+    public void close() {
+        eof = true;
+        ready.clear();
+        release();
     }
 }

@@ -85,6 +85,51 @@ int main(void) {
     /* too small an int[] for the sizes: error, nothing thrown away silently */
     jarray small = mk_array(1, NULL, 2, 4);
     CHECK(NS(transform)(env, NULL, h, 3, src, n, cs, jkey, jaad, jivs, dst, small) == -1 && thrown_msg[0] != 0);
+    thrown_msg[0] = 0;
+    /* a heap (non-direct) buffer has no address; a length beyond the capacity; null arrays -> IllegalArgumentException, no crash */
+    struct _jobject heap = { 3, NULL, -1 };
+    CHECK(NS(transform)(env, NULL, h, 3, &heap, n, cs, jkey, jaad, jivs, dst, sizes) == -1);
+    CHECK(strcmp(thrown_class, "java/lang/IllegalArgumentException") == 0 && strstr(thrown_msg, "direct ByteBuffer") != NULL); thrown_msg[0] = 0;
+    CHECK(NS(transform)(env, NULL, h, 3, src, (jlong)n + 1, cs, jkey, jaad, jivs, dst, sizes) == -1 && strstr(thrown_msg, "capacity") != NULL); thrown_msg[0] = 0;
+    CHECK(NS(transform)(env, NULL, h, 3, src, n, cs, jkey, jaad, jivs, dst, NULL) == -1 && strstr(thrown_msg, "transformedSizes") != NULL); thrown_msg[0] = 0;
+    jarray shortiv = mk_array(2, ivs, 24, 1);
+    CHECK(NS(transform)(env, NULL, h, 3, src, n, cs, jkey, jaad, shortiv, dst, sizes) == -1 && strstr(thrown_msg, "12 bytes per chunk") != NULL); thrown_msg[0] = 0;
+    jarray badkey = mk_array(2, key, 16, 1);
+    CHECK(NS(transform)(env, NULL, h, 3, src, n, cs, badkey, jaad, jivs, dst, sizes) == -1 && strstr(thrown_msg, "32 bytes") != NULL); thrown_msg[0] = 0;
+    NS(detransform)(env, NULL, h, 3, dst, (jlong)total, sizes, jkey, jaad, back, NULL);
+    CHECK(strstr(thrown_msg, "chunks cannot be null") != NULL); thrown_msg[0] = 0;
+    NS(detransform)(env, NULL, h, 3, dst, (jlong)total, sizes, jkey, jaad, &heap, osz);
+    CHECK(strstr(thrown_msg, "direct ByteBuffer") != NULL); thrown_msg[0] = 0;
+    NS(freePinned)(env, NULL, NULL);                                               /* tolerated */
+
+    /* the flow of GpuDetransformChunkEnumeration / GpuChunkManager.getChunks: a window of consecutive chunks of the object
+     * (ranged GET = bytes [pos(first), end(last)) read into a pinned buffer), one detransform call, chunks served one by one */
+    ((uint8_t*)dst->data)[40] ^= 1;                                                /* undo the flipped bit */
+    {
+        const jint first = 1, cnt = 2;
+        jlong off = 0, win = 0, orig = 0;
+        for (int i = 0; i < first; i++) off += ((jint*)sizes->data)[i];
+        for (int i = first; i < first + cnt; i++) { win += ((jint*)sizes->data)[i]; orig += (i == nch - 1) ? n - 3 * cs : cs; }
+        jobject wsrc = NS(allocPinned)(env, NULL, win), wdst = NS(allocPinned)(env, NULL, orig);
+        memcpy(wsrc->data, (uint8_t*)dst->data + off, (size_t)win);
+        jarray wts = mk_array(1, (jint*)sizes->data + first, cnt, 4), wos = mk_array(1, NULL, cnt, 4);
+        NS(detransform)(env, NULL, h, 3, wsrc, win, wts, jkey, jaad, wdst, wos);
+        CHECK(thrown_msg[0] == 0 && memcmp(wdst->data, s + (size_t)first * cs, (size_t)orig) == 0);
+        CHECK(((jint*)wos->data)[0] == cs && ((jint*)wos->data)[1] == cs);
+        /* a ranged GET that came back short: "Stream has fewer bytes than expected" (BaseDetransformChunkEnumeration.java:106-108) */
+        NS(detransform)(env, NULL, h, 3, wsrc, win - 1, wts, jkey, jaad, wdst, wos);
+        CHECK(strstr(thrown_msg, "fewer bytes than expected") != NULL); thrown_msg[0] = 0;
+        NS(freePinned)(env, NULL, wsrc); NS(freePinned)(env, NULL, wdst);
+    }
+    /* the flow of PinnedPool: buffers are reused across enumerations, and a second segment through the same buffers works */
+    {
+        for (int i = 0; i < n; i++) s[i] = (uint8_t)(i * 31 >> 3);
+        jint got2 = NS(transform)(env, NULL, h, 2, src, n, cs, jkey, jaad, jivs, dst, sizes);
+        CHECK(got2 == nch && thrown_msg[0] == 0 && ((jint*)sizes->data)[0] == cs + 28);
+        uint64_t t2 = 0; for (int i = 0; i < nch; i++) t2 += ((jint*)sizes->data)[i];
+        NS(detransform)(env, NULL, h, 2, dst, (jlong)t2, sizes, jkey, jaad, back, osz);
+        CHECK(thrown_msg[0] == 0 && memcmp(back->data, s, n) == 0);
+    }
     CHECK(live_copies == 0);                                                       /* every Get*Elements was released */
     NS(freePinned)(env, NULL, src); NS(freePinned)(env, NULL, dst); NS(freePinned)(env, NULL, back);
     NS(destroy)(env, NULL, h);

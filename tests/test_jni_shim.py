@@ -26,8 +26,34 @@ def test_java_native_declarations_match_the_exports():
         n_java = len([p for p in params.split(",") if p.strip()])
         n_c = len([p for p in m.group(1).split(",") if p.strip()])
         assert n_c == n_java + 2, (name, n_java, n_c)         # JNIEnv*, jclass + the Java parameters
-    # the enumeration the plugin would instantiate implements the reference's interface by name
+    # the enumerations the plugin would instantiate implement the reference's interfaces by name
     enum = open(os.path.join(ROOT, "jni", PKG, "GpuTransformChunkEnumeration.java")).read()
-    assert "implements TransformChunkEnumeration" in enum
-    for method in ("originalChunkSize", "transformedChunkSize", "hasMoreElements", "nextElement"):
+    assert "implements TransformChunkEnumeration, AutoCloseable" in enum
+    for method in ("originalChunkSize", "transformedChunkSize", "hasMoreElements", "nextElement", "close"):
         assert re.search(r"\b" + method + r"\s*\(", enum), method
+    assert "readNBytes" not in enum and "channel.read(in)" in enum            # the stream lands in pinned memory, no byte[] bounce
+    de = open(os.path.join(ROOT, "jni", PKG, "GpuDetransformChunkEnumeration.java")).read()
+    assert "implements DetransformChunkEnumeration, AutoCloseable" in de and "Stream has fewer bytes than expected" in de
+    for method in ("hasMoreElements", "nextElement", "close"):
+        assert re.search(r"\b" + method + r"\s*\(", de), method
+    cm = open(os.path.join(ROOT, "jni", "io/aiven/kafka/tieredstorage/fetch/gpu/GpuChunkManager.java")).read()
+    assert "implements ChunkManager" in cm and "getChunks" in cm and "BytesRange.of(" in cm
+    pool = open(os.path.join(ROOT, "jni", PKG, "PinnedPool.java")).read()
+    assert "TsGpu.freePinned" in pool and "Cleaner" in pool                   # pinned memory is returned, also for leaked leases
+
+
+def test_java_sources_reference_only_existing_reference_members():
+    """No JDK here, so the Java cannot be compiled: at least every reference type / member the sources name must exist in
+    /root/reference when it is present (skipped on the GPU box)."""
+    ref = "/root/reference/core/src/main/java/io/aiven/kafka/tieredstorage"
+    if not os.path.isdir(ref):
+        import pytest
+        pytest.skip("reference tree not present")
+    chunk = open(os.path.join(ref, "Chunk.java")).read()
+    for field in ("transformedPosition", "transformedSize", "originalSize"):
+        assert re.search(r"public final int " + field, chunk)
+    assert "SecretKey dataKey();" in open(os.path.join(ref, "manifest/SegmentEncryptionMetadata.java")).read()
+    assert "InputStream getChunk(" in open(os.path.join(ref, "fetch/ChunkManager.java")).read()
+    assert "interface DetransformChunkEnumeration extends Enumeration<byte[]>" in open(os.path.join(ref, "transform/DetransformChunkEnumeration.java")).read()
+    br = open("/root/reference/storage/core/src/main/java/io/aiven/kafka/tieredstorage/storage/BytesRange.java").read()
+    assert "public static BytesRange of(final int from, final int to)" in br

@@ -45,8 +45,11 @@ inline float tevent_ms(tevent_t, tevent_t) { return 0.f; }
 inline const char* device_sync() { return nullptr; }
 template <class K> inline const char* allow_smem(K, size_t) { return nullptr; }
 }  // namespace rt
+// the emulator is single-threaded by construction: concurrent host threads take turns launching
+#include <mutex>
+namespace rt { inline std::mutex& simt_launch_mutex() { static std::mutex m; return m; } }
 #define TS_LAUNCH(kern, grid, block, smem, stream, ...) \
-    do { simt::launch(grid, block, smem, [&] { kern(__VA_ARGS__); }); } while (0)
+    do { std::lock_guard<std::mutex> simt_lock_(rt::simt_launch_mutex()); simt::launch(grid, block, smem, [&] { kern(__VA_ARGS__); }); } while (0)
 #else
 #include <cuda_runtime.h>
 namespace rt {

@@ -7,6 +7,7 @@
 //   [AES-GCM kernels], D2H of the chunk sizes, then per-chunk D2H of exactly transformed_size bytes to the
 //   running offset in dst (the packed .log object layout).  Batches complete in order;
 //   up to (devices x slots) batches are in flight so copies overlap kernels.
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <stdarg.h>
@@ -61,6 +62,7 @@ struct Work {
     bool dev_pending = false;
     bool out_pending = false;              // a copy-out on out_stream still reads this slot's final buffer
     bool busy = false, ready = false;
+    bool claimed = false;                  // owned by a call in progress (guarded by tsgpu_ctx::mu)
     Aes256RoundKeys key_rk{};      // the key this slot's GcmKeyCtx (H powers, Shoup table) was built for
     bool key_valid = false;        //   ... consecutive calls with one segment's data key skip the set-up kernel
     uint8_t* d_orig = nullptr;     // max_batch * chunk_cap
@@ -83,12 +85,14 @@ struct Lane { int device = 0; Work w[NSLOT_MAX]; };
 }  // namespace
 
 struct tsgpu_ctx {
-    std::mutex mu;
+    std::mutex mu;                 // guards slot ownership (Work::claimed, active_calls) and lazy slot allocation — NOT held while a call runs
+    std::condition_variable cv;
+    uint32_t active_calls = 0;
     std::vector<Lane> lanes;
     uint32_t chunk_cap = 0, max_batch = 0;
     uint64_t frame_stride = 0, slot_stride = 0;
     LaunchProf prof;
-    uint32_t nslot = 8;            // work slots per device in flight (TSGPU_SLOTS overrides; measured best with batches of 4 x 4 MiB)
+    uint32_t nslot = 16;           // work slots per device (TSGPU_SLOTS overrides); one call takes at most 8 of them
     bool split_out = true;         // copies-out ride their own stream (the slot's next batch starts behind an event, not behind them)
 };
 
@@ -225,7 +229,7 @@ extern "C" void* tsgpu_host_alloc(size_t bytes) {
     return p;
 }
 extern "C" void tsgpu_host_free(void* p) { rt::free_host(p); }
-extern "C" uint64_t tsgpu_launch_count(const tsgpu_ctx* c) { return c ? c->prof.launches : 0; }
+extern "C" uint64_t tsgpu_launch_count(const tsgpu_ctx* c) { return c ? c->prof.launches.load() : 0; }
 
 // ------------------------------------------------------------------------------------------ AES-GCM stage
 // Runs key set-up (once per call and work slot), the main kernel over (ranges x chunks) and the finalize kernel.
@@ -261,6 +265,75 @@ static int gcm_stage(tsgpu_ctx* c, Work& w, rt::stream_t st, const Aes256RoundKe
 // out_stream; the first kernel that overwrites the buffer they are read from waits for them here.
 static int wait_copies_out(Work& w, rt::stream_t st) {
     if (w.out_pending) { RT(rt::stream_wait_event(st, w.ev_done)); w.out_pending = false; }
+    return TSGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------ slot ownership
+// Kafka drives this library from up to 10 copier threads plus the fetch pool (README.md:221 of the reference; SURVEY.md §8b
+// "Threading").  A call does not hold a context-wide lock: it claims a set of work slots (streams + arenas + pinned
+// descriptor block), runs on them, and gives them back.  The first caller gets up to 8 slots per device (what one segment
+// needs to keep copies and kernels overlapped); later callers share what is free, so concurrent calls overlap on the GPU
+// instead of queueing behind each other.
+namespace {
+struct SlotClaim {
+    tsgpu_ctx* c = nullptr;
+    std::vector<Work*> slots;
+    ~SlotClaim() { release(); }
+    void release() {
+        if (!c || slots.empty()) { c = nullptr; return; }
+        {
+            std::lock_guard<std::mutex> lock(c->mu);
+            for (Work* w : slots) w->claimed = false;
+            c->active_calls--;
+        }
+        c->cv.notify_all();
+        slots.clear(); c = nullptr;
+    }
+};
+}
+// Claims at least one slot (waiting if every slot is taken), at most `want` and at most the caller's fair share; slots are
+// allocated on first use.  Returns TSGPU_OK with claim.slots interleaved across devices (round-robin dealing of batches).
+static int claim_slots(tsgpu_ctx* c, uint32_t want, SlotClaim& claim, int only_device_index = -1, int only_slot = -1, bool wait_dev = true) {
+    std::unique_lock<std::mutex> lock(c->mu);
+    const uint32_t per_call_max = 8;
+    while (true) {
+        std::vector<Work*> got;
+        const uint32_t share = std::max<uint32_t>(2, c->nslot / (c->active_calls + 1));
+        const uint32_t per_dev = std::min(std::min(want, per_call_max), share);
+        for (uint32_t k = 0; k < c->nslot && got.size() < (size_t)want; k++) {      // slot-major: interleaves the devices
+            for (size_t l = 0; l < c->lanes.size(); l++) {
+                if (only_device_index >= 0 && (int)l != only_device_index) continue;
+                if (only_slot >= 0 && (int)k != only_slot) continue;
+                Work& w = c->lanes[l].w[k];
+                if (w.claimed) continue;
+                uint32_t mine_on_dev = 0;
+                for (Work* g : got) mine_on_dev += g->device == c->lanes[l].device ? 1u : 0u;
+                if (only_slot < 0 && mine_on_dev >= per_dev) continue;
+                got.push_back(&w);
+            }
+        }
+        if (!got.empty()) {
+            for (Work* w : got) w->claimed = true;
+            c->active_calls++;
+            claim.c = c; claim.slots = got;
+            break;
+        }
+        c->cv.wait(lock);
+    }
+    // lazy allocation under the lock (rare: first use of a slot)
+    for (Work* w : claim.slots) {
+        if (!w->ready) {
+            int rc = work_init(c, *w, w->device);
+            if (rc) { lock.unlock(); claim.release(); return rc; }
+        }
+    }
+    lock.unlock();
+    if (wait_dev) for (Work* w : claim.slots) if (w->dev_pending) {        // device-API work enqueued on this slot's arenas: let it finish first
+        const char* e = rt::set_device(w->device);
+        if (!e) e = rt::event_sync(w->ev_dev_done);
+        if (e) { claim.release(); return fail(TSGPU_E_CUDA, "event_sync: %s", e); }
+        w->dev_pending = false;
+    }
     return TSGPU_OK;
 }
 
@@ -393,7 +466,6 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
     const uint32_t n = (uint32_t)len.size();
     if (!dst) return fail(TSGPU_E_ARG, "dst cannot be null");
 
-    std::lock_guard<std::mutex> lock(c->mu);
     if (flags == 0) {       // TransformFinisher no-transform fast path (TransformFinisher.java:135-140): bytes unchanged
         if (dst_cap < src_len) return fail(TSGPU_E_SHORT, "dst too small");
         memcpy(dst, src, src_len);
@@ -405,11 +477,13 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
     if (flags & TSGPU_FLAG_AES) rk = aes256_expand_key(key);
 
     const uint32_t nbatches = (n + c->max_batch - 1) / c->max_batch;
-    const uint32_t nwork = (uint32_t)c->lanes.size() * c->nslot;
+    SlotClaim claim;
+    { int rcc = claim_slots(c, nbatches, claim); if (rcc) return rcc; }
+    const uint32_t nwork = (uint32_t)claim.slots.size();
     std::vector<XfBatch> inflight(nbatches);
     uint64_t dst_off = 0;
     int rc = TSGPU_OK;
-    auto work_of = [&](uint32_t b) -> Work& { return c->lanes[b % c->lanes.size()].w[(b / c->lanes.size()) % c->nslot]; };
+    auto work_of = [&](uint32_t b) -> Work& { return *claim.slots[b % nwork]; };
     auto drain = [&](uint32_t b) -> int {        // sizes of batch b are ready -> copy its chunks out, in order
         XfBatch& xb = inflight[b];
         Work& w = *xb.w;
@@ -435,11 +509,11 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
             if (drained <= b - nwork) { rc = drain(drained++); if (rc) break; }
         }
         uint32_t c0 = b * c->max_batch, nb = std::min(c->max_batch, n - c0);
-        if (!work_of(b).ready) { rc = work_init(c, work_of(b), c->lanes[b % c->lanes.size()].device); if (rc) break; }
         rc = transform_issue(c, work_of(b), flags, src, off.data(), len.data(), cs, c0, nb, rk, aad, aad_len, ivs, inflight[b]);
     }
     while (rc == TSGPU_OK && drained < nbatches) rc = drain(drained++);
-    for (auto& l : c->lanes) for (auto& w : l.w) if (w.busy) {   // always leave the context idle
+    for (Work* wp : claim.slots) if (wp->busy) {                 // always leave the claimed slots idle
+        Work& w = *wp;
         rt::set_device(w.device);
         const char* e = rt::stream_sync(w.stream);
         if (!e) e = rt::stream_sync(w.out_stream);
@@ -532,7 +606,6 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     for (uint32_t i = 0; i < n_chunks; i++) need += transformed_sizes[i];
     if (need > src_len) return fail(TSGPU_E_SHORT, "Stream has fewer bytes than expected");
 
-    std::lock_guard<std::mutex> lock(c->mu);
     if (flags == 0) {       // DetransformFinisher pass-through (DetransformFinisher.java:48-51)
         if (dst_cap < need) return fail(TSGPU_E_SHORT, "dst too small");
         memcpy(dst, src, need);
@@ -543,7 +616,9 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     if (flags & TSGPU_FLAG_AES) rk = aes256_expand_key(key);
 
     const uint32_t nbatches = (n_chunks + c->max_batch - 1) / c->max_batch;
-    const uint32_t nwork = (uint32_t)c->lanes.size() * c->nslot;
+    SlotClaim claim;
+    { int rcc = claim_slots(c, nbatches, claim); if (rcc) return rcc; }
+    const uint32_t nwork = (uint32_t)claim.slots.size();
     std::vector<DxBatch> inflight(nbatches);
     std::vector<uint64_t> in_pos(nbatches + 1, 0);
     for (uint32_t b = 0; b < nbatches; b++) {
@@ -553,7 +628,7 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     }
     uint64_t dst_off = 0;
     int rc = TSGPU_OK, soft = TSGPU_OK;
-    auto work_of = [&](uint32_t b) -> Work& { return c->lanes[b % c->lanes.size()].w[(b / c->lanes.size()) % c->nslot]; };
+    auto work_of = [&](uint32_t b) -> Work& { return *claim.slots[b % nwork]; };
     auto drain = [&](uint32_t b) -> int {
         DxBatch& db = inflight[b];
         Work& w = *db.w;
@@ -582,11 +657,11 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
             if (drained <= b - nwork) { rc = drain(drained++); if (rc) break; }
         }
         uint32_t c0 = b * c->max_batch, nb = std::min(c->max_batch, n_chunks - c0);
-        if (!work_of(b).ready) { rc = work_init(c, work_of(b), c->lanes[b % c->lanes.size()].device); if (rc) break; }
         rc = detransform_issue(c, work_of(b), flags, src + in_pos[b], transformed_sizes, c0, nb, rk, aad, aad_len, inflight[b]);
     }
     while (rc == TSGPU_OK && drained < nbatches) rc = drain(drained++);
-    for (auto& l : c->lanes) for (auto& w : l.w) if (w.busy) {
+    for (Work* wp : claim.slots) if (wp->busy) {
+        Work& w = *wp;
         rt::set_device(w.device);
         const char* e = rt::stream_sync(w.stream);
         if (!e) e = rt::stream_sync(w.out_stream);
@@ -605,6 +680,8 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
 // any streams: the host waits until the previous call's descriptor upload has left the pinned block before rewriting it,
 // and the new call's stream waits for the previous call's kernels before touching the shared scratch.
 static int dev_call_begin(Work& w, rt::stream_t st) {
+    // (claim_slots has already waited for the previous device call's END when one was pending; the waits below matter when
+    // this begins to be relaxed, and cost nothing on completed events)
     if (w.dev_pending) { RT(rt::event_sync(w.ev_dev_desc)); RT(rt::stream_wait_event(st, w.ev_dev_done)); }
     return TSGPU_OK;
 }
@@ -635,7 +712,8 @@ extern "C" int tsgpu_transform_device(tsgpu_ctx* c, int device_index, uint32_t f
     if (slot_stride < tsgpu_slot_stride(flags, chunk_size) || (slot_stride & 15)) return fail(TSGPU_E_ARG, "slot_stride too small or not a multiple of 16");
     if ((flags & TSGPU_FLAG_AES) && (!key || !ivs || aad_len > MAX_AAD)) return fail(TSGPU_E_ARG, "key/ivs/aad invalid");
     const uint32_t nb = (uint32_t)n64, cs = chunk_size;
-    std::lock_guard<std::mutex> lock(c->mu);
+    SlotClaim claim;                                         // slot 0 of the device, for the duration of the enqueue
+    { int rcc = claim_slots(c, 1, claim, device_index, 0, /*wait_dev=*/false); if (rcc) return rcc; }
     RT(rt::set_device(w.device));
     rt::stream_t st = (rt::stream_t)stream;
     { int rb = dev_call_begin(w, st); if (rb) return rb; }
@@ -688,7 +766,8 @@ extern "C" int tsgpu_detransform_device(tsgpu_ctx* c, int device_index, uint32_t
     if ((flags & TSGPU_FLAG_AES) && (!key || aad_len > MAX_AAD)) return fail(TSGPU_E_ARG, "key/aad invalid");
     if (slot_stride < tsgpu_slot_stride(flags, chunk_size) || (slot_stride & 15)) return fail(TSGPU_E_ARG, "slot_stride too small or not a multiple of 16");
     if (!d_slots || !d_transformed_sizes || !d_dst || !d_original_sizes || !d_status) return fail(TSGPU_E_ARG, "null device pointer");
-    std::lock_guard<std::mutex> lock(c->mu);
+    SlotClaim claim;                                         // slot 0 of the device, for the duration of the enqueue
+    { int rcc = claim_slots(c, 1, claim, device_index, 0, /*wait_dev=*/false); if (rcc) return rcc; }
     RT(rt::set_device(w.device));
     rt::stream_t st = (rt::stream_t)stream;
     { int rb = dev_call_begin(w, st); if (rb) return rb; }
@@ -769,8 +848,9 @@ extern "C" int tsgpu_decode_path_stats(tsgpu_ctx* c, uint64_t out[4]) {
 // ------------------------------------------------------------------------------------------ ChunkIndex plumbing
 extern "C" int tsgpu_chunk_positions(tsgpu_ctx* c, const uint32_t* sizes, uint32_t n, uint64_t* positions) {
     if (!c || !positions || (n && !sizes)) return fail(TSGPU_E_ARG, "null argument");
-    std::lock_guard<std::mutex> lock(c->mu);
-    Work& w = c->lanes[0].w[0];
+    SlotClaim claim;
+    { int rcc = claim_slots(c, 1, claim); if (rcc) return rcc; }
+    Work& w = *claim.slots[0];
     RT(rt::set_device(w.device));
     uint32_t* d_sizes = nullptr; uint64_t* d_pos = nullptr;
     const char* e = rt::malloc_device((void**)&d_sizes, 4ull * (n + 1));
