@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--zstd-mode", default="speed", choices=["speed", "dense"],
+                    help="speed: independent 8 KiB blocks (default, TSGPU_FLAG_ZSTD); dense: 64 KiB regions, shared tables "
+                         "(TSGPU_FLAG_ZSTD | TSGPU_FLAG_ZSTD_DENSE) — denser, slower, byte-identical frames on every run")
     ap.add_argument("--direction", default="transform", choices=["transform", "fetch"],
                     help="fetch = BASELINE configs[4]: ranged fetchLogSegment, 16 MiB windows of a 1 GiB segment")
     ap.add_argument("--frames", default="own", choices=["own", "libzstd"],
@@ -61,8 +64,9 @@ def parse():
     return a
 
 
-def flags_of(workload):
-    return {"zstd+aes": 3, "aes": 2, "zstd": 1, "none": 0}[workload]
+def flags_of(workload, mode="speed"):
+    f = {"zstd+aes": 3, "aes": 2, "zstd": 1, "none": 0}[workload]
+    return f | (4 if (f & 1) and mode == "dense" else 0)
 
 
 def config_index(args):
@@ -77,7 +81,7 @@ def config_of(args, n_gpus):
             ("ranged fetch of %d MiB windows (%s-written frames) from a " % (args.window_mib, args.frames)) if args.direction == "fetch" else "",
             args.segment_mib, args.chunk_mib, args.workload, args.corpus, config_index(args)),
         "segment_bytes": args.segment_mib * MIB, "chunk_bytes": args.chunk_mib * MIB,
-        "transform": args.workload, "corpus": args.corpus,
+        "transform": args.workload, "corpus": args.corpus, "zstd_mode": args.zstd_mode if "zstd" in args.workload else None,
         "parallelism": "segments sharded across %d GPU(s), no data-path collective" % n_gpus,
         "l2_policy": "inputs (segment >= 1 GiB) larger than the 126 MB L2; no explicit flush",
     }
@@ -206,12 +210,13 @@ class CpuArm:
         if fetch:                                # the reference-written chunks to be fetched (produced before anything is timed)
             objects = []
             for i in range(self.nch):
-                t, _ = ora.transform_segment(flags, src[i * self.cs:(i + 1) * self.cs], self.cs, key, aad, ivs[12 * i:12 * i + 12])
+                t, _ = ora.transform_segment(flags & 3, src[i * self.cs:(i + 1) * self.cs], self.cs, key, aad, ivs[12 * i:12 * i + 12])
                 objects.append(np.array(t, copy=True))
         self.rounds = max(1, -(-min_chunks_per_worker * threads // self.nch)) if threads > 1 else 1
         total = self.nch * self.rounds
         per = (total + threads - 1) // threads
         self.ranges = [(k * per, min(total, (k + 1) * per)) for k in range(threads) if k * per < total]
+        flags &= 3                                # the CPU chain has one compressor: libzstd level 3
         _POOL_STATE.update(ora=ora, flags=flags, src=src[:self.nch * self.cs], cs=self.cs, key=key, aad=aad, ivs=ivs, objects=objects)
         self.pool = None
         self.cpu_seconds = 0.0
@@ -245,7 +250,7 @@ def main_reference(args):
     if rank != 0:
         return 0
     from oracle import oracle as ora
-    flags = flags_of(args.workload)
+    flags = flags_of(args.workload, args.zstd_mode)
     threads = os.cpu_count() or 1
     # a bounded sample of the same workload: the first sample_mib of the segment, all host cores
     sample_mib = args.cpu_sample_mib or min(args.segment_mib, 64 * threads)
@@ -296,7 +301,7 @@ def make_object(args, flags, src_np, ctx_host, key, aad, ivs):
     if args.frames == "own":
         return ctx_host.transform(flags, src_np, cs, key, aad, ivs)
     from oracle import oracle as ora
-    return ora.transform_segment(flags, src_np, cs, key, aad, ivs)
+    return ora.transform_segment(flags & 3, src_np, cs, key, aad, ivs)
 
 
 def main_fetch(args):
@@ -315,7 +320,7 @@ def main_fetch(args):
     bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    flags = flags_of(args.workload)
+    flags = flags_of(args.workload, args.zstd_mode)
     seg, cs = args.segment_mib * MIB, args.chunk_mib * MIB
     nch, wch = seg // cs, max(1, args.window_mib // args.chunk_mib)
     key, aad, ivs = corpus.fixed_key_material(nch)
@@ -428,10 +433,10 @@ def main_fetch(args):
         from oracle import oracle as ora
         f = firsts[0]
         part = obj[pos[f]:pos[f + wch]]
-        ora.detransform_chunks(flags, part, tsz[f:f + wch], win_bytes, key, aad)
+        ora.detransform_chunks(flags & 3, part, tsz[f:f + wch], win_bytes, key, aad)
         t0 = time.perf_counter(); reps = 0
         while time.perf_counter() - t0 < 5.0:
-            ora.detransform_chunks(flags, part, tsz[f:f + wch], win_bytes, key, aad); reps += 1
+            ora.detransform_chunks(flags & 3, part, tsz[f:f + wch], win_bytes, key, aad); reps += 1
         dtc = (time.perf_counter() - t0) / reps
         cpu = {"value": win_bytes / GIB / dtc, "unit": "GiB/s", "cores": 1, "kind": "port", "ms_per_window": 1000.0 * dtc,
                "sample": "%d x one %d MiB window, chunk-sequential on 1 thread like DefaultChunkManager.getChunk; libzstd %s + "
@@ -523,7 +528,7 @@ def main_tsgpu(args):
     bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    flags = flags_of(args.workload)
+    flags = flags_of(args.workload, args.zstd_mode)
     seg, cs = args.segment_mib * MIB, args.chunk_mib * MIB
     nch = seg // cs
     key, aad, ivs = corpus.fixed_key_material(nch)
@@ -693,7 +698,7 @@ def main_tsgpu(args):
             good = True
             for i in pick:
                 t = slots_np[i, 4:4 + int(sz_now[i])]
-                back, osz = ora.detransform_chunks(flags, t, [int(sz_now[i])], cs, key, aad)
+                back, osz = ora.detransform_chunks(flags & 3, t, [int(sz_now[i])], cs, key, aad)
                 good = good and np.array_equal(back, src_np[i * cs:(i + 1) * cs])
             verified["cpu_chain_decodes_sample_chunks"] = {"chunks": pick, "ok": bool(good)}
             if not good:

@@ -13,7 +13,7 @@ from oracle import oracle as ora
 
 pytestmark = pytest.mark.gpu
 
-Z, A = tsgpu.FLAG_ZSTD, tsgpu.FLAG_AES
+Z, A, D = tsgpu.FLAG_ZSTD, tsgpu.FLAG_AES, tsgpu.FLAG_ZSTD_DENSE
 MIB = 1 << 20
 SEG, CS = 1024 * MIB, 4 * MIB
 NCH = SEG // CS
@@ -84,7 +84,7 @@ def test_device_aes_whole_segment_bit_exact(torch, ctx, segments, kind):
         assert np.array_equal(slots[i, tsgpu.binding.SLOT_HEAD:tsgpu.binding.SLOT_HEAD + CS + 28], want), "chunk %d" % i
 
 
-@pytest.mark.parametrize("kind,flags", [("K", Z | A), ("R", Z | A), ("K", Z)])
+@pytest.mark.parametrize("kind,flags", [("K", Z | A), ("R", Z | A), ("K", Z), ("K", Z | A | D), ("R", Z | D)])
 def test_device_zstd_pipeline_decodes_with_libzstd_and_openssl(torch, ctx, segments, kind, flags):
     src = segments(kind)
     slots, sizes, (key, aad, ivs) = _run_device(torch, ctx, flags, src)
@@ -97,7 +97,7 @@ def test_device_zstd_pipeline_decodes_with_libzstd_and_openssl(torch, ctx, segme
     sample = sorted(set([0, NCH - 1] + rng.choice(NCH, 30, replace=False).tolist()))
     for i in sample:
         t = slots[i, tsgpu.binding.SLOT_HEAD:tsgpu.binding.SLOT_HEAD + int(sizes[i])]
-        back, osz = ora.detransform_chunks(flags, t, [int(sizes[i])], CS, key, aad)
+        back, osz = ora.detransform_chunks(flags & 3, t, [int(sizes[i])], CS, key, aad)
         assert osz == [CS] and np.array_equal(back, src[i * CS:(i + 1) * CS]), "chunk %d" % i
         if not (flags & A):
             assert ora.zstd_content_size(t) == CS

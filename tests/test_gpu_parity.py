@@ -13,7 +13,7 @@ from oracle import oracle as ora
 
 pytestmark = pytest.mark.gpu
 
-Z, A = tsgpu.FLAG_ZSTD, tsgpu.FLAG_AES
+Z, A, D = tsgpu.FLAG_ZSTD, tsgpu.FLAG_AES, tsgpu.FLAG_ZSTD_DENSE      # D modifies Z: the dense (region) compressor
 MIB = 1 << 20
 
 
@@ -95,11 +95,12 @@ def test_aes_empty_aad_and_odd_aad(small_ctx):
 
 
 # ------------------------------------------------------------------ zstd: cross-decodability both ways
+@pytest.mark.parametrize("mode", [0, D])
 @pytest.mark.parametrize("kind", ["K", "R", "Z"])
-def test_zstd_gpu_frames_decode_with_libzstd(ctx, kind):
+def test_zstd_gpu_frames_decode_with_libzstd(ctx, kind, mode):
     n, cs = 3 * 4 * MIB - 777, 4 * MIB
     src = corpus.gen_segment(kind, 3, n, cs)
-    got, gs = ctx.transform(Z, src, cs)
+    got, gs = ctx.transform(Z | mode, src, cs)
     pos = 0
     for i, s in enumerate(gs):
         frame = got[pos:pos + s]
@@ -140,7 +141,7 @@ def test_zstd_corrupt_frames_are_errors(ctx):
 
 
 # ------------------------------------------------------------------ full chain: TransformsEndToEndTest grid
-@pytest.mark.parametrize("flags", [A, Z, Z | A])
+@pytest.mark.parametrize("flags", [A, Z, Z | A, Z | D, Z | A | D])
 @pytest.mark.parametrize("cs", [0, 1, 2, 3, 5, 13, 1024, 2048, 5123, 181200 - 1, 181200 * 2])
 def test_transforms_end_to_end_grid(small_ctx, flags, cs):
     n = 181200 if cs == 0 or cs >= 13 else 700           # tiny chunk sizes: keep the chunk count sane
@@ -153,22 +154,23 @@ def test_transforms_end_to_end_grid(small_ctx, flags, cs):
     got, gs = small_ctx.transform(flags, src, cs, key, aad, ivs)
     assert len(gs) == nch
     # the reference-side reader recovers the segment from our bytes (IT: RemoteStorageManagerTest.java:327-381)
-    back_ref, _ = ora.detransform_chunks(flags, got, gs, n, key, aad)
+    back_ref, _ = ora.detransform_chunks(flags & 3, got, gs, n, key, aad)      # (the reader does not care how it was compressed)
     assert np.array_equal(back_ref, src)
     # and we read what the reference writes
-    ref, rs = ora.transform_segment(flags, src, cs, key, aad, ivs)
+    ref, rs = ora.transform_segment(flags & 3, src, cs, key, aad, ivs)
     back, osz = small_ctx.detransform(flags, ref, rs, n, key, aad)
     assert np.array_equal(back, src)
     back2, _ = small_ctx.detransform(flags, got, gs, n, key, aad)
     assert np.array_equal(back2, src)
 
 
+@pytest.mark.parametrize("mode", [0, D])
 @pytest.mark.parametrize("kind", ["K", "R"])
-def test_full_pipeline_4mib(ctx, kind):
+def test_full_pipeline_4mib(ctx, kind, mode):
     n, cs = 16 * 4 * MIB + 4321, 4 * MIB                  # 17 chunks -> 3 batches of 8
     src = corpus.gen_segment(kind, 6, n, cs)
     key, aad, ivs = corpus.fixed_key_material(17)
-    got, gs = ctx.transform(Z | A, src, cs, key, aad, ivs)
+    got, gs = ctx.transform(Z | A | mode, src, cs, key, aad, ivs)
     back_ref, _ = ora.detransform_chunks(Z | A, got, gs, n, key, aad)
     assert np.array_equal(back_ref, src)
     back, osz = ctx.detransform(Z | A, got, gs, n, key, aad)
@@ -238,8 +240,9 @@ def test_single_process_multi_device_context():
     c.close(); one.close()
 
 
+@pytest.mark.parametrize("mode", [0, D])
 @pytest.mark.parametrize("shape", ["skewed_high_bytes", "gauss_around_128", "alphabet_200", "period_1000", "long_runs"])
-def test_zstd_binary_payload_shapes(ctx, shape):
+def test_zstd_binary_payload_shapes(ctx, shape, mode):
     # binary Kafka payloads: alphabets above byte value 128 (FSE-compressed Huffman weights), literal-only blocks
     # (zero sequences), long-distance repeats and long runs (warp-wide match extension)
     rng = np.random.default_rng(42)
@@ -254,7 +257,7 @@ def test_zstd_binary_payload_shapes(ctx, shape):
         src = np.tile(rng.integers(0, 256, 1000, dtype=np.uint8), n // 1000 + 1)[:n].copy()
     else:
         src = np.repeat(rng.integers(0, 256, n // 3000 + 1, dtype=np.uint8), 3000)[:n].copy()
-    got, gs = ctx.transform(Z, src, cs)
+    got, gs = ctx.transform(Z | mode, src, cs)
     pos = 0
     for i, s in enumerate(gs):
         assert ora.zstd_decompress_chunk(got[pos:pos + s]) == src[i * cs:min(n, (i + 1) * cs)].tobytes()

@@ -66,14 +66,14 @@ def test_gpu_decode_paths_libzstd_frames_and_own_regions():
 
 @pytest.mark.gpu
 def test_gpu_frames_are_identical_across_runs():
-    # hash-slot winners are deterministic (highest position of a step): the same input gives the same object every time
+    # dense mode: hash-slot winners are deterministic (highest position of a step) — the same input gives the same object
     ctx = tsgpu.Context(max_chunk_bytes=4 << 20, max_batch=8)
     try:
         src = corpus.gen_segment("K", 5, 24 << 20, 4 << 20)
-        first, fs = ctx.transform(Z, src, 4 << 20)
+        first, fs = ctx.transform(Z | tsgpu.FLAG_ZSTD_DENSE, src, 4 << 20)
         first = first.copy()
         for _ in range(4):
-            again, sz = ctx.transform(Z, src, 4 << 20)
+            again, sz = ctx.transform(Z | tsgpu.FLAG_ZSTD_DENSE, src, 4 << 20)
             assert sz == fs and np.array_equal(again, first)
     finally:
         ctx.close()

@@ -46,14 +46,15 @@ def shapes(rng, n):
     yield "long_repeat_far", np.concatenate([blk, rng.integers(0, 256, 5000, dtype=np.uint8), blk, blk])[:n] if n >= 14000 else np.tile(blk, 2)[:n]
 
 
+@pytest.mark.parametrize("mode", [0, tsgpu.FLAG_ZSTD_DENSE])        # both compressors: independent blocks / 64 KiB regions
 @pytest.mark.parametrize("n", [700, 8191, 8192, 8193, 40000, 123457])
-def test_simt_fuzz_shapes(ctx, n):
+def test_simt_fuzz_shapes(ctx, n, mode):
     rng = np.random.default_rng(n)
     for name, src in shapes(rng, n):
         src = np.ascontiguousarray(src[:n])
         m = src.size
         for cs in (0, 50000):
-            out, sizes = ctx.transform(Z, src, cs)
+            out, sizes = ctx.transform(Z | mode, src, cs)
             c = cs if cs else m
             pos = 0
             for i, s in enumerate(sizes):

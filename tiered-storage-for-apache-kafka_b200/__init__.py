@@ -6,4 +6,4 @@ Transform/DetransformChunkEnumeration operator surface) and corpus.py (synthetic
 The directory name has a hyphen, so import it through the `tsgpu` shim at the repo root or importlib.
 """
 from . import binding  # noqa: F401
-from .binding import (FLAG_AES, FLAG_ZSTD, IV_SIZE, TAG_SIZE, Context, TsgpuError)  # noqa: F401
+from .binding import (FLAG_AES, FLAG_ZSTD, FLAG_ZSTD_DENSE, IV_SIZE, TAG_SIZE, Context, TsgpuError)  # noqa: F401

@@ -13,6 +13,7 @@ DEFAULT_LIB = os.path.join(_HERE, "libtsgpu.so")
 
 FLAG_ZSTD = 1
 FLAG_AES = 2
+FLAG_ZSTD_DENSE = 4
 IV_SIZE = 12
 TAG_SIZE = 16
 SLOT_HEAD = 4

@@ -23,6 +23,7 @@
 #include "rt.h"
 #include "launch_prof.h"
 #include "zstd_enc.cuh"
+#include "zstd_enc_blk.cuh"
 #include "zstd_dec.cuh"
 #include "host_index.hpp"
 
@@ -73,7 +74,8 @@ struct Work {
     Desc dd{}, hd{};               // device / pinned-host views of the descriptor block
     uint4* d_partials = nullptr;  uint32_t max_ranges = 0;
     GcmKeyCtx* d_keyctx = nullptr;
-    ZstdEncScratch zenc{};
+    ZstdEncScratch zenc{};         // region kernel (TSGPU_FLAG_ZSTD_DENSE), allocated on first use
+    ZstdBlkScratch zblk{};         // block kernel (default), allocated on first use
     ZstdDecScratch zdec{};
     uint32_t* h_sizes = nullptr;   // pinned: sizes/status coming back
     // bookkeeping of the batch currently owning this slot
@@ -85,6 +87,7 @@ struct Lane { int device = 0; Work w[NSLOT_MAX]; };
 }  // namespace
 
 struct tsgpu_ctx {
+    bool dense_default = false;    // TSGPU_ZSTD_MODE=dense: TSGPU_FLAG_ZSTD alone already means the region kernel
     std::mutex mu;                 // guards slot ownership (Work::claimed, active_calls) and lazy slot allocation — NOT held while a call runs
     std::condition_variable cv;
     uint32_t active_calls = 0;
@@ -139,9 +142,7 @@ static int work_init_impl(tsgpu_ctx* c, Work& w, int device) {
     RT(rt::malloc_device((void**)&w.d_partials, sizeof(uint4) * (size_t)w.max_ranges * nb));
     RT(rt::malloc_device((void**)&w.d_keyctx, sizeof(GcmKeyCtx)));
     RT(rt::malloc_host((void**)&w.h_sizes, 4ull * nb * 2 + 64));
-    const char* e = zstd_enc_scratch_alloc(w.zenc, c->chunk_cap, c->max_batch);
-    if (e) return fail(TSGPU_E_CUDA, "zstd enc scratch: %s", e);
-    e = zstd_dec_scratch_alloc(w.zdec, c->chunk_cap, c->max_batch);
+    const char* e = zstd_dec_scratch_alloc(w.zdec, c->chunk_cap, c->max_batch);
     if (e) return fail(TSGPU_E_CUDA, "zstd dec scratch: %s", e);
     return TSGPU_OK;
 }
@@ -154,7 +155,7 @@ static void work_free(Work& w) {
     rt::free_device(w.d_orig); rt::free_device(w.d_frames); rt::free_device(w.d_xf); rt::free_device(w.d_pack);
     rt::free_device(w.d_desc); rt::free_host(w.h_desc);
     rt::free_device(w.d_partials); rt::free_device(w.d_keyctx); rt::free_host(w.h_sizes);
-    zstd_enc_scratch_free(w.zenc); zstd_dec_scratch_free(w.zdec);
+    zstd_enc_scratch_free(w.zenc); zstd_blk_scratch_free(w.zblk); zstd_dec_scratch_free(w.zdec);
     memset(&w.key_rk, 0, sizeof w.key_rk); w.key_valid = false;
     rt::event_destroy(w.ev_sizes); rt::event_destroy(w.ev_done);
     rt::event_destroy(w.ev_dev_desc); rt::event_destroy(w.ev_dev_done);
@@ -195,6 +196,7 @@ extern "C" int tsgpu_create(const int* device_ids, int n_devices, uint32_t max_c
     c->chunk_cap = max_chunk_bytes; c->max_batch = max_batch;
     if (const char* e = getenv("TSGPU_SLOTS")) { int v = atoi(e); if (v >= 1 && v <= NSLOT_MAX) c->nslot = (uint32_t)v; }       // tuning knobs
     if (const char* e = getenv("TSGPU_SPLIT_OUT")) c->split_out = atoi(e) != 0;
+    if (const char* e = getenv("TSGPU_ZSTD_MODE")) c->dense_default = strcmp(e, "dense") == 0;
     c->frame_stride = align_up(frame_bound(max_chunk_bytes), 16) + 16;
     c->slot_stride = tsgpu_slot_stride(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES, max_chunk_bytes);
     c->lanes.resize(ids.size());
@@ -230,6 +232,30 @@ extern "C" void* tsgpu_host_alloc(size_t bytes) {
 }
 extern "C" void tsgpu_host_free(void* p) { rt::free_host(p); }
 extern "C" uint64_t tsgpu_launch_count(const tsgpu_ctx* c) { return c ? c->prof.launches.load() : 0; }
+
+// ------------------------------------------------------------------------------------------ zstd stage (compress)
+// Two kernels, one contract (zstd_enc_blk.cuh: independent 8 KiB blocks, fastest; zstd_enc.cuh: 64 KiB regions with shared
+// tables and history, densest).  Their scratch is allocated the first time a slot runs the mode.
+static int zstd_stage(tsgpu_ctx* c, Work& w, rt::stream_t st, uint32_t flags, const uint8_t* in_base, const uint64_t* d_in_off,
+                      const uint32_t* d_in_len, uint32_t nb, uint32_t cs, uint8_t* out_base, const uint64_t* d_out_off, uint32_t* d_out_len) {
+    const bool dense = (flags & TSGPU_FLAG_ZSTD_DENSE) || c->dense_default;
+    int rc;
+    if (dense) {
+        if (!w.zenc.seqs) {
+            const char* e = zstd_enc_scratch_alloc(w.zenc, c->chunk_cap, c->max_batch);
+            if (e) { zstd_enc_scratch_free(w.zenc); return fail(TSGPU_E_CUDA, "zstd enc scratch: %s", e); }
+        }
+        rc = zstd_compress_batch(w.zenc, st, in_base, d_in_off, d_in_len, nb, cs, out_base, d_out_off, d_out_len, c->prof);
+    } else {
+        if (!w.zblk.seqs) {
+            const char* e = zstd_blk_scratch_alloc(w.zblk, c->chunk_cap, c->max_batch);
+            if (e) { zstd_blk_scratch_free(w.zblk); return fail(TSGPU_E_CUDA, "zstd enc scratch: %s", e); }
+        }
+        rc = zstd_compress_batch_blocks(w.zblk, st, in_base, d_in_off, d_in_len, nb, cs, out_base, d_out_off, d_out_len, c->prof);
+    }
+    if (rc) return fail(rc, "zstd compress: %s", zstd_last_error());
+    return TSGPU_OK;
+}
 
 // ------------------------------------------------------------------------------------------ AES-GCM stage
 // Runs key set-up (once per call and work slot), the main kernel over (ranges x chunks) and the finalize kernel.
@@ -372,8 +398,8 @@ static int transform_issue(tsgpu_ctx* c, Work& w, uint32_t flags, const uint8_t*
     uint32_t cur_max = cs;
     xb.final_base = w.d_orig; xb.final_stride = cs; xb.final_head = 0;
     if (flags & TSGPU_FLAG_ZSTD) {
-        int rc = zstd_compress_batch(w.zenc, st, cur_base, cur_off, cur_len, nb, cs, w.d_frames, w.dd.b_off, w.dd.b_len, c->prof);
-        if (rc) return fail(rc, "zstd compress: %s", zstd_last_error());
+        int rc = zstd_stage(c, w, st, flags, cur_base, cur_off, cur_len, nb, cs, w.d_frames, w.dd.b_off, w.dd.b_len);
+        if (rc) return rc;
         cur_base = w.d_frames; cur_off = w.dd.b_off; cur_len = w.dd.b_len; cur_max = (uint32_t)frame_bound(cs);
         xb.final_base = w.d_frames; xb.final_stride = c->frame_stride; xb.final_head = 0;
     }
@@ -413,7 +439,7 @@ static int transform_args_ok(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, u
     if (!c) return fail(TSGPU_E_ARG, "ctx cannot be null");
     if (!n_chunks || !transformed_sizes) return fail(TSGPU_E_ARG, "transformed_sizes/n_chunks cannot be null");
     if (src_len && !src) return fail(TSGPU_E_ARG, "inputStream cannot be null");
-    if (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES)) return fail(TSGPU_E_ARG, "unknown flags %u", flags);
+    if (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES | TSGPU_FLAG_ZSTD_DENSE)) return fail(TSGPU_E_ARG, "unknown flags %u", flags);
     if ((flags & TSGPU_FLAG_AES) && (!key || !ivs)) return fail(TSGPU_E_ARG, "key and ivs are required for encryption");
     if ((flags & TSGPU_FLAG_AES) && aad_len > MAX_AAD) return fail(TSGPU_E_ARG, "aad longer than %u bytes", MAX_AAD);
     if ((flags & TSGPU_FLAG_AES) && aad_len && !aad) return fail(TSGPU_E_ARG, "aad cannot be null");
@@ -465,6 +491,7 @@ static int transform_common(tsgpu_ctx* c, uint32_t flags, const uint8_t* src, ui
                             const uint8_t* ivs, uint8_t* dst, uint64_t dst_cap, uint32_t* transformed_sizes, uint32_t* n_chunks) {
     const uint32_t n = (uint32_t)len.size();
     if (!dst) return fail(TSGPU_E_ARG, "dst cannot be null");
+    if (!(flags & TSGPU_FLAG_ZSTD)) flags &= ~TSGPU_FLAG_ZSTD_DENSE;   // a modifier of ZSTD: meaningless (and harmless) without it
 
     if (flags == 0) {       // TransformFinisher no-transform fast path (TransformFinisher.java:135-140): bytes unchanged
         if (dst_cap < src_len) return fail(TSGPU_E_SHORT, "dst too small");
@@ -599,9 +626,10 @@ extern "C" int tsgpu_detransform(tsgpu_ctx* c, uint32_t flags, const uint8_t* sr
     if (!src) return fail(TSGPU_E_ARG, "inputStream cannot be null");
     if (!transformed_sizes) return fail(TSGPU_E_ARG, "chunks cannot be null");
     if (!dst) return fail(TSGPU_E_ARG, "dst cannot be null");
-    if (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES)) return fail(TSGPU_E_ARG, "unknown flags %u", flags);
+    if (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES | TSGPU_FLAG_ZSTD_DENSE)) return fail(TSGPU_E_ARG, "unknown flags %u", flags);
     if ((flags & TSGPU_FLAG_AES) && !key) return fail(TSGPU_E_ARG, "key is required for decryption");
     if ((flags & TSGPU_FLAG_AES) && aad_len > MAX_AAD) return fail(TSGPU_E_ARG, "aad longer than %u bytes", MAX_AAD);
+    flags &= ~TSGPU_FLAG_ZSTD_DENSE;                         // how a frame was compressed does not matter to the reader
     uint64_t need = 0;
     for (uint32_t i = 0; i < n_chunks; i++) need += transformed_sizes[i];
     if (need > src_len) return fail(TSGPU_E_SHORT, "Stream has fewer bytes than expected");
@@ -704,7 +732,7 @@ extern "C" int tsgpu_transform_device(tsgpu_ctx* c, int device_index, uint32_t f
                                       uint32_t* d_transformed_sizes, void* stream) {
     Work* wp = nullptr; int rc = pick_work(c, device_index, &wp); if (rc) return rc;
     Work& w = *wp;
-    if (flags == 0 || (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES))) return fail(TSGPU_E_ARG, "flags must name zstd and/or aes");
+    if ((flags & (TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES)) == 0 || (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES | TSGPU_FLAG_ZSTD_DENSE))) return fail(TSGPU_E_ARG, "flags must name zstd and/or aes");
     if (chunk_size == 0 || chunk_size > c->chunk_cap) return fail(TSGPU_E_ARG, "chunk_size out of range for this context");
     if (src_len == 0) return TSGPU_OK;
     const uint64_t n64 = (src_len + chunk_size - 1) / chunk_size;
@@ -740,8 +768,8 @@ extern "C" int tsgpu_transform_device(tsgpu_ctx* c, int device_index, uint32_t f
         uint8_t* fb = to_slots ? d_slots : w.d_frames;
         const uint64_t* fo = to_slots ? w.dd.c_off : w.dd.b_off;
         uint32_t* fl = to_slots ? d_transformed_sizes : w.dd.b_len;
-        int zr = zstd_compress_batch(w.zenc, st, cur_base, cur_off, cur_len, nb, cs, fb, fo, fl, c->prof);
-        if (zr) return fail(zr, "zstd compress: %s", zstd_last_error());
+        int zr = zstd_stage(c, w, st, flags, cur_base, cur_off, cur_len, nb, cs, fb, fo, fl);
+        if (zr) return zr;
         cur_base = fb; cur_off = fo; cur_len = fl; cur_max = (uint32_t)frame_bound(cs);
     }
     if (flags & TSGPU_FLAG_AES) {
@@ -759,7 +787,7 @@ extern "C" int tsgpu_detransform_device(tsgpu_ctx* c, int device_index, uint32_t
                                         uint8_t* d_dst, uint32_t* d_original_sizes, uint32_t* d_status, void* stream) {
     Work* wp = nullptr; int rc = pick_work(c, device_index, &wp); if (rc) return rc;
     Work& w = *wp;
-    if (flags == 0 || (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES))) return fail(TSGPU_E_ARG, "flags must name zstd and/or aes");
+    if ((flags & (TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES)) == 0 || (flags & ~(TSGPU_FLAG_ZSTD | TSGPU_FLAG_AES | TSGPU_FLAG_ZSTD_DENSE))) return fail(TSGPU_E_ARG, "flags must name zstd and/or aes");
     if (chunk_size == 0 || chunk_size > c->chunk_cap) return fail(TSGPU_E_ARG, "chunk_size out of range for this context");
     if (n_chunks == 0) return TSGPU_OK;
     if (n_chunks > c->max_batch) return fail(TSGPU_E_ARG, "%u chunks exceed the context's max_batch %u", n_chunks, c->max_batch);

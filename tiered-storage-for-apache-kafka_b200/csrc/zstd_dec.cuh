@@ -23,6 +23,7 @@
 #include "launch_prof.h"
 #include "zstd_format.h"
 #include "zstd_enc.cuh"
+#include "zstd_enc_blk.cuh"
 
 namespace ts {
 
@@ -1133,6 +1134,7 @@ constexpr uint32_t ZD_SMEM_BYTES = ZD_WPB * sizeof(ZdWarpCtx);
 inline const char* zstd_kernels_configure() {
     const char* e;
     if ((e = rt::allow_smem(zstd_enc_regions_kernel, ZE_SMEM_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_enc_blocks_kernel, ZB_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_frames_kernel, ZD_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_par_entropy_kernel, ZD_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_regions_kernel, ZX_REGION_SMEM))) return e;
