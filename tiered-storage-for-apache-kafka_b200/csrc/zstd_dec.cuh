@@ -612,6 +612,23 @@ __device__ __forceinline__ bool zx_all_done(const uint32_t* dbits, uint32_t ja, 
     return true;
 }
 
+// Copy n (<= 64) bytes from HBM to the window by ONE thread: the loads of a 16-byte piece are issued together (one memory
+// latency per piece instead of one per byte — a byte loop through generic pointers waits for every load before the next).
+__device__ __forceinline__ void zx_copy_from_hbm(uint8_t* d, const uint8_t* s, uint32_t n) {
+    uint32_t k = 0;
+    for (; k + 16 <= n; k += 16) {
+        const uint32_t w0 = ld_u32_unaligned(s + k), w1 = ld_u32_unaligned(s + k + 4), w2 = ld_u32_unaligned(s + k + 8), w3 = ld_u32_unaligned(s + k + 12);
+        _Pragma("unroll")
+        for (int q = 0; q < 4; q++) { d[k + q] = (uint8_t)(w0 >> (8 * q)); d[k + 4 + q] = (uint8_t)(w1 >> (8 * q)); d[k + 8 + q] = (uint8_t)(w2 >> (8 * q)); d[k + 12 + q] = (uint8_t)(w3 >> (8 * q)); }
+    }
+    if (k < n) {                                         // tail: up to 15 bytes, loads first (reads at most 3 bytes past the end of the source's last word)
+        const uint32_t r = n - k;
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (uint32_t q = 0; q * 4 < r; q++) w[q] = ld_u32_unaligned(s + k + 4 * q);
+        for (uint32_t q = 0; q < r; q++) d[k + q] = (uint8_t)(w[q >> 2] >> (8 * (q & 3)));
+    }
+}
+
 // Flush win[0..n) to dst (HBM), 128-bit stores when the destination allows.  All threads; no barrier inside.
 __device__ __forceinline__ void zx_flush(uint8_t* dst, const uint8_t* win, uint32_t n, uint32_t tid) {
     if ((((uintptr_t)dst) & 15) == 0) {
@@ -705,15 +722,7 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
                 const uint32_t quick = min(ll, 32u);
                 uint8_t* ld = wout + o_start;
                 if (rle_lit < 0x100) { for (uint32_t k = 0; k < quick; k++) ld[k] = (uint8_t)rle_lit; }
-                else {
-                    const uint8_t* ls = lit + l_start;
-                    uint32_t k = 0;
-                    for (; k + 4 <= quick; k += 4) {
-                        const uint8_t b0 = ls[k], b1 = ls[k + 1], b2 = ls[k + 2], b3 = ls[k + 3];
-                        ld[k] = b0; ld[k + 1] = b1; ld[k + 2] = b2; ld[k + 3] = b3;
-                    }
-                    for (; k < quick; k++) ld[k] = ls[k];
-                }
+                else zx_copy_from_hbm(ld, lit + l_start, quick);
                 uint32_t longs = __ballot_sync(TS_FULL, ll > 32);
                 while (longs) {
                     const uint32_t f = (uint32_t)__ffs((int)longs) - 1;
@@ -735,26 +744,33 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
             uint32_t ja = 0, jb = 0;
             bool inside = false;                                          // does the source reach into this step's output?
             if (mine && ml) {
+                uint32_t top = tid;                                       // producers are searched below this index
                 for (uint32_t hop = 0; ; hop++) {
                     inside = false;
-                    if (s_hi <= op) break;
+                    if (s_hi <= op) break;                                // everything it reads was complete before the step
                     inside = true;
-                    uint32_t lo = 0, hi = tid;                            // last j <= tid with ostart[j] <= x
+                    uint32_t lo = 0, hi = top;                            // ja: last j <= top with ostart[j] <= x
                     const uint32_t x = max(s_lo, op);
                     while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] <= x) lo = mid; else hi = mid - 1; }
                     ja = lo;
-                    hi = tid;
-                    while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] < s_hi) lo = mid; else hi = mid - 1; }
-                    jb = lo;
-                    if (jb == tid) { if (tid == 0 || ja == tid) { inside = false; break; } jb = tid - 1; }   // own literals precede the match: never a producer
-                    if (hop >= 12 || off < ml || ja != jb || s_lo < op) break;
-                    const uint32_t pend_ = sh->ostart[ja + 1], pst = pend_ - sh->mlen[ja];   // producer's match bytes [pst, pend_)
-                    if (s_lo < pst || s_hi > pend_) {
-                        if (s_hi <= pst) inside = false;                  // only the producer's literals: written already
+                    const uint32_t pend_ = sh->ostart[ja + 1];            // end of sequence ja's output = end of its match
+                    if (ja < tid && s_hi <= pend_ && s_lo >= op) {        // the whole source lies in ONE earlier sequence of the step
+                        jb = ja;
+                        const uint32_t pst = pend_ - sh->mlen[ja];        // its match bytes are [pst, pend_)
+                        if (s_hi <= pst) { inside = false; break; }       // only its literals: written already
+                        if (s_lo >= pst && off >= ml && hop < 12) {       // inside its match: read what IT reads
+                            const uint32_t po = sh->moff[ja];
+                            off += po; s_lo -= po; s_hi -= po;
+                            top = ja;
+                            continue;
+                        }
                         break;
                     }
-                    const uint32_t po = sh->moff[ja];
-                    off += po; s_lo -= po; s_hi -= po;                    // read what the producer reads
+                    lo = ja; hi = tid;                                    // jb: last j <= tid with ostart[j] < s_hi
+                    while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] < s_hi) lo = mid; else hi = mid - 1; }
+                    jb = lo;
+                    if (jb == tid) { if (tid == 0 || ja == tid) inside = false; else jb = tid - 1; }   // own literals precede the match: never a producer
+                    break;
                 }
             }
             // ---- matches: every warp runs its own loop; a lane copies once the done bits of its producers are set
@@ -769,7 +785,7 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
                     if (!done) ready = !inside || zx_all_done(sh->dbits, ja, jb);
                     if (ready) __threadfence_block();                      // acquire: the producers' bytes are visible
                     if (ready && ml <= 64) {
-                        if (from_far) { const uint8_t* ms = far + s_lo; for (uint32_t k = 0; k < ml; k++) d[k] = ms[k]; }
+                        if (from_far) zx_copy_from_hbm(d, far + s_lo, ml);
                         else if (straddle) { for (uint32_t k = 0; k < ml; k++) { const uint32_t q = s_lo + k; d[k] = q < win_pos0 ? far[q] : wout[q]; } }
                         else {
                             const uint8_t* ms = d - off;
