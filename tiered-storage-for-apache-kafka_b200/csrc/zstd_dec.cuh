@@ -570,27 +570,28 @@ __device__ __forceinline__ uint32_t zd_block_entropy(const uint8_t* blk, uint32_
 //     by binary search in the step's positions; a match spins on their done bits (one 32-bit word per warp, written only by
 //     that warp) and copies as soon as they are set.  Text compressed against its nearest earlier occurrence makes chains
 //     of dozens of dependent matches inside one step: a hop along such a chain costs a shared-memory poll, not a barrier.
-constexpr int ZX_T = 512;
-struct ZxShared {
-    uint32_t ostart[ZX_T + 1];               // output position of each sequence of the step (+ end)
-    uint32_t mlen[ZX_T], moff[ZX_T];         // match length / offset of each sequence of the step (source forwarding)
-    uint32_t dbits[ZX_T / 32];               // done bit per sequence of the step; word w is written by warp w only
-    uint64_t wsum[ZX_T / 32];
+constexpr int ZX_T = 512;                 // threads of the region executor; the frame executor runs ZX_TF
+constexpr int ZX_TF = 1024;
+template <int T> struct ZxShared {
+    uint32_t ostart[T + 1];               // output position of each sequence of the step (+ end)
+    uint32_t mlen[T], moff[T];         // match length / offset of each sequence of the step (source forwarding)
+    uint32_t dbits[T / 32];               // done bit per sequence of the step; word w is written by warp w only
+    uint64_t wsum[T / 32];
     uint64_t tot;
     uint32_t rep[3];
     int32_t err;
 };
 
-__device__ __forceinline__ uint64_t zx_block_scan(uint64_t v, uint32_t tid, ZxShared* sh, uint64_t* total) {
+template <int T> __device__ __forceinline__ uint64_t zx_block_scan(uint64_t v, uint32_t tid, ZxShared<T>* sh, uint64_t* total) {
     const uint32_t lane = tid & 31, w = tid >> 5;
     uint64_t inc = warp_inclusive_scan_u64(v, lane);
     if (lane == 31) sh->wsum[w] = inc;
     __syncthreads();
     if (w == 0) {
-        const uint64_t x = lane < ZX_T / 32 ? sh->wsum[lane] : 0;
+        const uint64_t x = lane < T / 32 ? sh->wsum[lane] : 0;
         const uint64_t xi = warp_inclusive_scan_u64(x, lane);
-        if (lane < ZX_T / 32) sh->wsum[lane] = xi - x;
-        if (lane == ZX_T / 32 - 1) sh->tot = xi;
+        if (lane < T / 32) sh->wsum[lane] = xi - x;
+        if (lane == T / 32 - 1) sh->tot = xi;
     }
     __syncthreads();
     inc += sh->wsum[w];
@@ -630,12 +631,12 @@ __device__ __forceinline__ void zx_copy_from_hbm(uint8_t* d, const uint8_t* s, u
 }
 
 // Flush win[0..n) to dst (HBM), 128-bit stores when the destination allows.  All threads; no barrier inside.
-__device__ __forceinline__ void zx_flush(uint8_t* dst, const uint8_t* win, uint32_t n, uint32_t tid) {
+template <int T> __device__ __forceinline__ void zx_flush(uint8_t* dst, const uint8_t* win, uint32_t n, uint32_t tid) {
     if ((((uintptr_t)dst) & 15) == 0) {
-        for (uint32_t k = tid * 16; k + 16 <= n; k += ZX_T * 16) stg128_stream((uint4*)(dst + k), *(const uint4*)(win + k));
-        for (uint32_t k = (n & ~15u) + tid; k < n; k += ZX_T) dst[k] = win[k];
+        for (uint32_t k = tid * 16; k + 16 <= n; k += T * 16) stg128_stream((uint4*)(dst + k), *(const uint4*)(win + k));
+        for (uint32_t k = (n & ~15u) + tid; k < n; k += T) dst[k] = win[k];
     } else {
-        for (uint32_t k = tid; k < n; k += ZX_T) dst[k] = win[k];
+        for (uint32_t k = tid; k < n; k += T) dst[k] = win[k];
     }
 }
 
@@ -645,11 +646,11 @@ __device__ __forceinline__ void zx_flush(uint8_t* dst, const uint8_t* win, uint3
 //   far             HBM image of the output, position 0 at far[0] (nullptr: nothing before the window may be referenced)
 //   per_block       true: the window restarts at every block and is flushed to `far` after it (whole frames)
 //                   false: one window for all blocks, the caller flushes (regions)
-__device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, const uint32_t* bo, const ZdBlkMeta* meta,
+template <int T> __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, const uint32_t* bo, const ZdBlkMeta* meta,
                                                       uint32_t b_first, uint32_t b_last, uint8_t* win, uint32_t win_cap,
                                                       uint8_t* far, bool per_block, uint32_t out_cap,
                                                       const uint8_t* lit_arena, const uint64_t* seq_arena, uint32_t frame_len,
-                                                      ZxShared* sh, uint32_t tid, bool no_carried_reps) {
+                                                      ZxShared<T>* sh, uint32_t tid, bool no_carried_reps) {
     const uint32_t lane = tid & 31, w = tid >> 5;
     uint32_t op = 0;
     uint32_t win_pos0 = 0;                               // frame position of win[0]
@@ -665,10 +666,10 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
         if (type == 0 || type == 1) {                    // Raw_Block / RLE_Block
             if (bsz > room || pos + 3 + (type == 0 ? bsz : 1) > frame_len) { if (tid == 0) sh->err = -1; __syncthreads(); return op; }
             const uint8_t v = frame[pos + 3];
-            if (type == 0) { for (uint32_t k = tid; k < bsz; k += ZX_T) wout[op + k] = frame[pos + 3 + k]; }
-            else { for (uint32_t k = tid; k < bsz; k += ZX_T) wout[op + k] = v; }
+            if (type == 0) { for (uint32_t k = tid; k < bsz; k += T) wout[op + k] = frame[pos + 3 + k]; }
+            else { for (uint32_t k = tid; k < bsz; k += T) wout[op + k] = v; }
             __syncthreads();
-            if (per_block) { zx_flush(far + op, win, bsz, tid); __syncthreads(); }
+            if (per_block) { zx_flush<T>(far + op, win, bsz, tid); __syncthreads(); }
             op += bsz;
             continue;
         }
@@ -685,7 +686,7 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
         const uint32_t R0 = sh->rep[0], R1 = sh->rep[1], R2 = sh->rep[2];     // repeat offsets at the start of the block
         const uint32_t blk_op0 = op;
         uint32_t lp = 0;
-        for (uint32_t base = 0; base < N; base += ZX_T) {
+        for (uint32_t base = 0; base < N; base += T) {
             const uint32_t i = base + tid;
             const bool mine = i < N;
             uint32_t ll = 0, ml = 0, off = 1;
@@ -702,7 +703,7 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
                 if (off == 0) bad = true;
             }
             uint64_t tot;
-            const uint64_t inc = zx_block_scan(((uint64_t)(ll + ml) << 32) | ll, tid, sh, &tot);
+            const uint64_t inc = zx_block_scan<T>(((uint64_t)(ll + ml) << 32) | ll, tid, sh, &tot);
             const uint32_t tot_o = (uint32_t)(tot >> 32), tot_l = (uint32_t)tot;
             const uint32_t o_start = op + (uint32_t)(inc >> 32) - ll - ml, l_start = lp + (uint32_t)inc - ll, m_start = o_start + ll;
             if (mine && (off > m_start || (!far && off > m_start - win_pos0))) bad = true;
@@ -710,7 +711,7 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
             sh->mlen[tid] = mine ? ml : 0; sh->moff[tid] = off;
             const uint32_t preset = __ballot_sync(TS_FULL, !mine || ml == 0);         // nothing to wait for on these
             if (lane == 0) sh->dbits[w] = preset;
-            if (tid == 0) sh->ostart[ZX_T] = op + tot_o;
+            if (tid == 0) sh->ostart[T] = op + tot_o;
             const bool any_bad = __syncthreads_or(bad) != 0;
             if (any_bad || lp + tot_l > regen || (uint64_t)(op - blk_op0) + tot_o > room) {
                 if (tid == 0) sh->err = -1;
@@ -837,12 +838,12 @@ __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, cons
                 return op;
             }
             const uint32_t ll = regen - lp;
-            if (rle_lit < 0x100) { for (uint32_t k = tid; k < ll; k += ZX_T) wout[op + k] = (uint8_t)rle_lit; }
-            else { for (uint32_t k = tid; k < ll; k += ZX_T) wout[op + k] = lit[lp + k]; }
+            if (rle_lit < 0x100) { for (uint32_t k = tid; k < ll; k += T) wout[op + k] = (uint8_t)rle_lit; }
+            else { for (uint32_t k = tid; k < ll; k += T) wout[op + k] = lit[lp + k]; }
             op += ll;
         }
         __syncthreads();
-        if (per_block) { zx_flush(far + blk_op0, win, op - blk_op0, tid); }
+        if (per_block) { zx_flush<T>(far + blk_op0, win, op - blk_op0, tid); }
         if (tid == 0) {                                                   // repeat offsets after the block
             uint32_t nr[3];
             for (int k = 0; k < 3; k++) {                                 // an offset that underflowed is only an error if it is used
@@ -1067,7 +1068,7 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_entropy_kernel(const
 constexpr uint32_t ZX_REGION_SMEM = ZR;
 __global__ void __launch_bounds__(ZX_T, 2) zstd_dec_regions_kernel(const __grid_constant__ ZstdDecArgs A) {
     TS_DYN_SMEM(obuf);
-    __shared__ ZxShared sh;
+    __shared__ ZxShared<ZX_T> sh;
     const uint32_t tid = threadIdx.x;
     const uint32_t chunk = blockIdx.y, region = blockIdx.x;
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
@@ -1079,7 +1080,7 @@ __global__ void __launch_bounds__(ZX_T, 2) zstd_dec_regions_kernel(const __grid_
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
     const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
-    const uint32_t made = zx_execute_blocks(p, bo, meta, b0, b1, obuf, ZR, nullptr, false, want,
+    const uint32_t made = zx_execute_blocks<ZX_T>(p, bo, meta, b0, b1, obuf, ZR, nullptr, false, want,
                                             A.par_lits + (size_t)chunk * A.par_lit_cap, A.par_seqs + (size_t)chunk * A.par_seq_cap,
                                             A.in_len[chunk], &sh, tid, region != 0);
     if (sh.err || made != want) {
@@ -1090,15 +1091,15 @@ __global__ void __launch_bounds__(ZX_T, 2) zstd_dec_regions_kernel(const __grid_
         return;
     }
     if (tid == 0) atomicAdd(&A.stats[0], 1ull);
-    zx_flush(A.out_base + A.out_off[chunk] + (size_t)region * ZR, obuf, made, tid);
+    zx_flush<ZX_T>(A.out_base + A.out_off[chunk] + (size_t)region * ZR, obuf, made, tid);
 }
 
 // 3c: one CTA per frame — execution stage straight into the frame's output in HBM (what libzstd-written frames need: their
 // matches reach back up to the whole window).
 constexpr uint32_t ZX_FRAME_SMEM = zf::BLOCK_MAX;      // the window is the current block
-__global__ void __launch_bounds__(ZX_T, 1) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
+__global__ void __launch_bounds__(ZX_TF, 1) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
     TS_DYN_SMEM(wbuf);
-    __shared__ ZxShared sh;
+    __shared__ ZxShared<ZX_TF> sh;
     const uint32_t tid = threadIdx.x;
     const uint32_t chunk = blockIdx.x;
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
@@ -1109,7 +1110,7 @@ __global__ void __launch_bounds__(ZX_T, 1) zstd_dec_par_execute_kernel(const __g
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
     const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
-    const uint32_t made = zx_execute_blocks(p, bo, meta, 0, nblk, wbuf, ZX_FRAME_SMEM, A.out_base + A.out_off[chunk], true, fcs,
+    const uint32_t made = zx_execute_blocks<ZX_TF>(p, bo, meta, 0, nblk, wbuf, ZX_FRAME_SMEM, A.out_base + A.out_off[chunk], true, fcs,
                                             A.par_lits + (size_t)chunk * A.par_lit_cap, A.par_seqs + (size_t)chunk * A.par_seq_cap,
                                             A.in_len[chunk], &sh, tid, false);
     if (tid == 0) {
@@ -1188,7 +1189,7 @@ inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     TS_LAUNCH_P(prof, "zstd_dec_regions", zstd_dec_regions_kernel, dim3(rpc, n_chunks), dim3(ZX_T), ZX_REGION_SMEM, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
-    TS_LAUNCH_P(prof, "zstd_dec_frame_exec", zstd_dec_par_execute_kernel, dim3(n_chunks), dim3(ZX_T), ZX_FRAME_SMEM, st, A);
+    TS_LAUNCH_P(prof, "zstd_dec_frame_exec", zstd_dec_par_execute_kernel, dim3(n_chunks), dim3(ZX_TF), ZX_FRAME_SMEM, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     TS_LAUNCH_P(prof, "zstd_dec_serial", zstd_dec_frames_kernel, dim3((n_chunks + ZD_WPB - 1) / ZD_WPB), dim3(ZD_WPB * 32),
                 ZD_SMEM_BYTES, st, A);

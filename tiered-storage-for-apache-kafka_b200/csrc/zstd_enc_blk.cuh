@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zstd_enc_blocks_kernel(const __gr
     uint16_t* ht = (uint16_t*)(wbase + ZB + ZB_BUF_PAD);
     uint2* pk = (uint2*)(buf + ZB_SEQ_AUX_OFF);
     uint32_t* sb = (uint32_t*)(pk + 96);
-// Stage + LZ parse + literal gather of one 8 KiB block (included inside a __global__ function body after
+// Stage + LZ parse of one 8 KiB block (included inside a __global__ function body after
 // zstd_enc_prologue.inc).  Leaves nseq sequences in `seqs`, nlit literals in `lits`.
     // ---- stage the block in shared memory (128-bit loads when the source is aligned), zero the pad, reset the table
     if ((((uintptr_t)src) & 15) == 0) {
@@ -490,8 +490,8 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zstd_enc_blocks_kernel(const __gr
     // ---- phase A: greedy LZ parse, 32 positions per step
     // Selection (which of the 32 candidate matches survive, left to right) is the only serial part and costs a
     // handful of instructions per taken match; sequences are then written by their own lanes in parallel and
-    // literals are gathered in one pass afterwards.
-    uint32_t anchor = 0, cur = 0, nseq = 0;
+    // the step's literals (the positions no taken match covers) leave in the same step.
+    uint32_t anchor = 0, cur = 0, nseq = 0, nlit = 0;
     while (cur + 4 <= bn && nseq + 8 <= ZE_MAXSEQ) {                // a step adds at most 8 sequences (min match 4)
         const uint32_t p = cur + lane;
         const bool valid = p + 4 <= bn;
@@ -571,50 +571,34 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zstd_enc_blocks_kernel(const __gr
             pos = end;
             f = nf;
         }
+        uint32_t cov = 0;                                          // positions of this step covered by a taken match
         if (taken) {
+            const bool mine_taken = (taken >> lane) & 1;
             const uint32_t my_end = p + len;                       // meaningful on taken lanes
             const uint32_t lower = taken & ((1u << lane) - 1);
             const uint32_t prev_lane = lower ? (uint32_t)(31 - __clz((int)lower)) : 0u;
             uint32_t prev_end = __shfl_sync(TS_FULL, my_end, prev_lane);
             if (!lower) prev_end = anchor;
-            if ((taken >> lane) & 1) {
-                const uint32_t bk = min(bkr, p - prev_end);            // "catch up": never into the previous match
+            const uint32_t bk = mine_taken ? min(bkr, p - max(prev_end, cur)) : 0u;   // "catch up" over this step's literals, never into the previous match
+            if (mine_taken)
                 seqs[nseq + (uint32_t)__popc(lower)] = make_uint2((p - bk - prev_end) | ((len + bk - 3) << 16), p - cand);
-            }
             nseq += (uint32_t)__popc(taken);
             anchor = cur + pos;
+            const uint32_t sl = lane - bk, tl = len + bk;
+            cov = __reduce_or_sync(TS_FULL, mine_taken ? (tl >= 32 - sl ? 0xffffffffu : (1u << tl) - 1) << sl : 0u);
+        }
+        // the step's literals, in order: one byte per position of the block no taken match covers
+        {
+            const uint32_t inside = bn - cur >= 32 ? 0xffffffffu : (1u << (bn - cur)) - 1;
+            const uint32_t lm = ~cov & inside;
+            if ((lm >> lane) & 1) lits[nlit + (uint32_t)__popc(lm & ((1u << lane) - 1))] = (uint8_t)v;
+            nlit += (uint32_t)__popc(lm);
         }
         cur = max(cur + 32, anchor);
     }
-    __syncwarp();
-    __threadfence_block();
-    // ---- literal gather: one lane per sequence copies its literal run; long runs are finished by the whole warp
-    uint32_t nlit = 0;
-    {
-        uint32_t src_pos = 0;
-        uint2 pre = lane < nseq ? seqs[lane] : make_uint2(0, 0);
-        for (uint32_t t0 = 0; t0 < nseq; t0 += 32) {
-            const uint32_t i = t0 + lane;
-            uint32_t ll = 0, ml = 0;
-            const uint2 sq = pre;
-            if (i + 32 < nseq) pre = seqs[i + 32];
-            if (i < nseq) { ll = sq.x & 0xffff; ml = (sq.x >> 16) + 3; }
-            const uint32_t inc_l = warp_inclusive_scan_u32(ll, lane), inc_s = warp_inclusive_scan_u32(ll + ml, lane);
-            const uint32_t lo = nlit + inc_l - ll, so = src_pos + inc_s - ll - ml;
-            const uint32_t quick = min(ll, 16u);
-            for (uint32_t k = 0; k < quick; k++) lits[lo + k] = buf[so + k];
-            uint32_t longs = __ballot_sync(TS_FULL, ll > 16);
-            while (longs) {
-                const uint32_t f = (uint32_t)__ffs((int)longs) - 1;
-                longs &= longs - 1;
-                const uint32_t flo = __shfl_sync(TS_FULL, lo, f), fso = __shfl_sync(TS_FULL, so, f), fll = __shfl_sync(TS_FULL, ll, f);
-                for (uint32_t k = 16 + lane; k < fll; k += 32) lits[flo + k] = buf[fso + k];
-            }
-            nlit += __shfl_sync(TS_FULL, inc_l, 31);
-            src_pos += __shfl_sync(TS_FULL, inc_s, 31);
-        }
-        const uint32_t ll = bn - anchor;                           // trailing literals
-        ze_warp_copy(lits + nlit, buf + anchor, ll, lane);
+    if (cur < bn) {                                                // the rest of the block is literals
+        const uint32_t ll = bn - cur;
+        for (uint32_t k = lane; k < ll; k += 32) lits[nlit + k] = buf[cur + k];
         nlit += ll;
     }
     __syncwarp();
