@@ -12,7 +12,7 @@ src = corpus.gen_segment(kind, 0, seg, cs)
 h_src = torch.empty(seg, dtype=torch.uint8).pin_memory(); h_src.numpy()[:] = src
 key, aad, ivs = corpus.fixed_key_material(nch)
 import os
-for flags, slots, split, mb in ((3, 8, 1, 4), (3, 16, 1, 4), (3, 16, 1, 2), (3, 12, 1, 4), (3, 8, 1, 2), (3, 16, 1, 1), (3, 8, 0, 4), (1, 8, 1, 4), (2, 8, 1, 4), (2, 16, 1, 2)):
+for flags, slots, split, mb in ((3, 16, 1, 4), (3, 16, 1, 8), (3, 16, 1, 2), (3, 16, 1, 16), (3, 16, 0, 4), (7, 16, 1, 4), (1, 16, 1, 4), (2, 16, 1, 4), (2, 16, 1, 8)):
     if True:
         os.environ['TSGPU_SLOTS'] = str(slots); os.environ['TSGPU_SPLIT_OUT'] = str(split)
         ctx = tsgpu.Context(max_chunk_bytes=cs, max_batch=mb)

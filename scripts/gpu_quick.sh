@@ -1,7 +1,10 @@
-# round 2 run G: decoder changes (cheaper forwarding, batched HBM copies) + ncu of the speed-mode compressor and the executors
 set -x
-R=${1:-r02g}
+R=${1:-r02h}
 python -m pytest tests/test_gpu_parity.py tests/test_gpu_paths.py -m gpu -q -x -k "zstd or full_pipeline or grid or ranged or paths or identical or libzstd" 2>&1 | tail -3
+python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>gpurun_out/${R}_bench.err | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('K speed: value %.1f GiB/s e2e %.1f ratio %.3f' % (d['value'], d['e2e']['value'], d['compression_ratio']), {k: round(v['ms'], 2) for k, v in d['kernels_ms_per_step'].items()}, d['verified'])"
 for F in libzstd own; do
 python bench.py --direction fetch --frames $F --steps 12 --warmup 3 --no-cpu-baseline 2>>gpurun_out/${R}_bench.err | python -c "
 import sys, json
@@ -12,6 +15,4 @@ python tests/perf/bench_detransform.py 256 2>>gpurun_out/${R}_bench.err | python
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 for k in ('own_frames_fast_path', 'libzstd_frames_general_path'): print(k, round(d[k]['GiB_per_s'], 1), 'GiB/s', d[k]['kernels_ms'], d[k]['bit_exact'])"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:zstd_enc_blocks -s 1 -c 1 -o gpurun_out/prof_${R}_enc_blocks -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-verify --segment-mib 256 > gpurun_out/ncu_${R}_encb.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:zstd_dec_par_execute -s 0 -c 1 -o gpurun_out/prof_${R}_dec_frame -f python bench.py --direction fetch --frames libzstd --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --segment-mib 64 > gpurun_out/ncu_${R}_decf.log 2>&1
-tail -3 gpurun_out/${R}_bench.err; ls -la gpurun_out/*${R}*
+tail -3 gpurun_out/${R}_bench.err

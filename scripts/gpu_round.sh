@@ -1,15 +1,22 @@
-# full end-of-round measurement: tests, bench lines, launch list, ncu captures of the two dominant kernels
+# end-of-round evidence: full GPU suite, driver-shaped bench lines for every BASELINE config, launch list, ncu captures at the bench configuration
 set -x
-R=${1:-r01}
-python -m pytest tests -m gpu -q -x 2>&1 | tail -5
-TSGPU_TEST_EXPERIMENTAL=1 python -m pytest tests/test_zz_gpu_experimental.py -m gpu -q 2>&1 | tail -5     # off-by-default variants
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_${R}_zstdaes_K.json 2> gpurun_out/bench_${R}.err; tail -c 1200 gpurun_out/bench_${R}_zstdaes_K.json
-python bench.py --corpus R --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${R}_zstdaes_R.json 2>/dev/null
-python bench.py --workload aes --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${R}_aes_K.json 2>/dev/null
-python bench.py --workload zstd --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${R}_zstd_K.json 2>/dev/null
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${R}_reference.json 2>/dev/null; tail -c 700 gpurun_out/bench_${R}_reference.json
-python tests/perf/bench_detransform.py 256 > gpurun_out/detransform_${R}.json 2> gpurun_out/detransform_${R}.err; tail -c 1500 gpurun_out/detransform_${R}.json; tail -3 gpurun_out/detransform_${R}.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 --csv --log-file gpurun_out/launches_${R}.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > /dev/null 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:zstd_enc_blocks -s 1 -c 1 -o gpurun_out/prof_${R}_zstd_enc_blocks -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > /dev/null 2>&1
-#timeout 900 ncu --set full --clock-control none --import-source on -k regex:gcm_main -s 1 -c 1 -o gpurun_out/prof_${R}_gcm_main -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > /dev/null 2>&1
-ls -la gpurun_out | tail -12
+R=${1:-r02}
+python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 > gpurun_out/${R}_bench_config3_speed.json 2> gpurun_out/${R}_bench.err; tail -c 600 gpurun_out/${R}_bench_config3_speed.json
+python bench.py --zstd-mode dense --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_bench_config3_dense.json 2>> gpurun_out/${R}_bench.err
+python bench.py --corpus R --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_bench_config3_R.json 2>> gpurun_out/${R}_bench.err
+python bench.py --config 0 --steps 3 --warmup 1 > gpurun_out/${R}_bench_config0.json 2>> gpurun_out/${R}_bench.err
+python bench.py --config 1 --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_bench_config1.json 2>> gpurun_out/${R}_bench.err
+python bench.py --config 2 --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_bench_config2.json 2>> gpurun_out/${R}_bench.err
+python bench.py --config 4 --steps 16 --warmup 3 > gpurun_out/${R}_bench_config4_own.json 2>> gpurun_out/${R}_bench.err
+python bench.py --config 4 --frames libzstd --steps 16 --warmup 3 > gpurun_out/${R}_bench_config4_libzstd.json 2>> gpurun_out/${R}_bench.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${R}_bench_reference.json 2>> gpurun_out/${R}_bench.err; tail -c 500 gpurun_out/${R}_bench_reference.json
+python tests/perf/bench_detransform.py 256 > gpurun_out/${R}_detransform.json 2>> gpurun_out/${R}_bench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 --csv --log-file gpurun_out/${R}_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-verify > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:zstd_enc_blocks -s 1 -c 1 -o gpurun_out/prof_${R}_zstd_enc_blocks -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-verify > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:zstd_enc_regions -s 1 -c 1 -o gpurun_out/prof_${R}_zstd_enc_regions -f python bench.py --zstd-mode dense --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-verify > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:gcm_main -s 1 -c 1 -o gpurun_out/prof_${R}_gcm_main -f python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-verify > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:zstd_dec_par_entropy -s 1 -c 1 -o gpurun_out/prof_${R}_zstd_dec_entropy -f python tests/perf/bench_detransform.py 256 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:zstd_dec_regions -s 1 -c 1 -o gpurun_out/prof_${R}_zstd_dec_regions -f python tests/perf/bench_detransform.py 256 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:zstd_dec_par_execute -s 0 -c 1 -o gpurun_out/prof_${R}_zstd_dec_frame_exec -f python bench.py --direction fetch --frames libzstd --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --segment-mib 64 > /dev/null 2>&1
+ls -la gpurun_out | grep ${R} | tail -30; tail -5 gpurun_out/${R}_bench.err

@@ -1,41 +1,24 @@
-#!/usr/bin/env python
-"""Aggregate an `ncu --page source --csv --print-source cuda,sass` dump by source line (instructions + stall samples)."""
-import collections
-import csv
-import os
-import sys
-
-path, top = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40
-rows = list(csv.reader(open(path)))
-agg, samp = collections.Counter(), collections.Counter()
-cur, hdr = None, None
-for r in rows:
-    if not r:
-        continue
-    if r[0] == "File Path":
-        cur, hdr = r[1], None
-        continue
-    if r[0] == "Function Name":
-        continue
-    if r[0] == "Line No":
-        hdr = r
-        continue
-    if hdr is None or not r[0].isdigit():
-        continue
-    d = dict(zip(hdr, r))
+import csv, sys, collections, os
+path=sys.argv[1]; top=int(sys.argv[2]) if len(sys.argv)>2 else 60
+agg=collections.OrderedDict()
+cur=None;hdr=None
+for r in csv.reader(open(path)):
+    if not r: continue
+    if r[0]=="File Path": cur=os.path.basename(r[1]); hdr=None; continue
+    if r[0]=="Function Name": continue
+    if r[0]=="Line No": hdr=r; continue
+    if hdr is None or not r[0].isdigit(): continue
+    d=dict(zip(hdr,r))
     try:
-        agg[(cur, int(r[0]))] += int(d["Instructions Executed"])
-        samp[(cur, int(r[0]))] += int(d["# Samples"])
-    except (ValueError, KeyError):
-        pass
-tot, tots = sum(agg.values()), sum(samp.values())
-print("total warp instructions %d, stall samples %d" % (tot, tots))
-cache = {}
-for (f, ln), v in sorted(agg.items(), key=lambda kv: -samp[kv[0]])[:top]:
-    if f not in cache:
-        try:
-            cache[f] = open(f).read().splitlines()
-        except OSError:
-            cache[f] = []
-    text = cache[f][ln - 1].strip()[:100] if ln - 1 < len(cache[f]) else ""
-    print("%5.1f%% inst %5.1f%% samples  %s:%d  %s" % (100.0 * v / tot, 100.0 * samp[(f, ln)] / max(tots, 1), os.path.basename(f), ln, text))
+        ins=int(r[hdr.index("Instructions Executed")]); smp=int(r[hdr.index("# Samples")]); thr=int(r[hdr.index("Thread Instructions Executed")])
+    except ValueError: continue
+    k=(cur,int(r[0]))
+    a=agg.setdefault(k,[0,0,0,r[1]]); a[0]+=ins; a[1]+=smp; a[2]+=thr
+tot=sum(a[0] for a in agg.values()); tots=sum(a[1] for a in agg.values())
+print("total",tot,tots)
+mode=sys.argv[3] if len(sys.argv)>3 else "top"
+items=list(agg.items())
+if mode=="top": items=sorted(items,key=lambda kv:-kv[1][0])[:top]
+else: items=[kv for kv in items if kv[0][0]==mode]; items.sort(key=lambda kv: kv[0][1])
+for (f,ln),a in items:
+    print("%5.2f%% ins %5.2f%% smp lanes %4.1f %s:%d  %s"%(100*a[0]/tot,100*a[1]/max(1,tots),a[2]/max(1,a[0]),f,ln,a[3].strip()[:110]))

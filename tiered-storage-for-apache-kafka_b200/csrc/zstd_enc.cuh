@@ -318,7 +318,7 @@ __device__ __forceinline__ void ze_publish(unsigned long long* w, uint64_t inclu
 __device__ __forceinline__ uint64_t ze_wait(unsigned long long* w) {
     unsigned long long v;
 #ifdef TSGPU_SIMT
-    v = *w;                                              // the emulator runs CTAs in launch order: the word is already there
+    while (!((v = *(volatile unsigned long long*)w) >> 63)) simt::yield();    // other warps of the CTA are fibers: let them run
 #else
     do { v = atomicAdd(w, 0ull); } while (!(v >> 63));
 #endif

@@ -10,7 +10,7 @@
 //   zstd_enc_blocks_kernel    one WARP per block: block staged in shared memory; 32 positions hashed and verified per step
 //                             against a per-warp hash table, greedy left-to-right selection by ballot/ffs, match extension
 //                             per lane then warp-wide; literals (Raw / RLE / Huffman) + sequences (per-block FSE tables)
-//   zstd_enc_assemble_kernel  one CTA per chunk: frame header, exclusive scan of block sizes, gather of the blocks
+//                             placement: look-back over the previous blocks' sizes, the block copies itself into the frame
 // Hash-slot winners inside a step are whichever lane the hardware keeps (every outcome is a valid parse: candidates are
 // verified before use), so frames of this mode may differ between runs in bytes, never in what they decode to; the region
 // kernel is deterministic.
@@ -47,11 +47,12 @@ struct ZstdBlkScratch {
     uint32_t* blk_size = nullptr;    // blocks
     uint2* seqs = nullptr;           // blocks * ZE_MAXSEQ
     uint8_t* lits = nullptr;         // blocks * ZB
+    unsigned long long* blk_state = nullptr;   // blocks: look-back words (ready bit 63 | inclusive frame bytes)
     uint32_t blocks_per_chunk = 0, max_batch = 0;
 };
 struct ZstdBlkArgs {
     const uint8_t* in_base; const uint64_t* in_off; const uint32_t* in_len;
-    uint8_t* blk_out; uint32_t* blk_size; uint2* seqs; uint8_t* lits;
+    uint8_t* blk_out; uint32_t* blk_size; uint2* seqs; uint8_t* lits; unsigned long long* blk_state;
     uint32_t blocks_per_chunk;
     uint8_t* out_base; const uint64_t* out_off; uint32_t* out_len;
 };
@@ -456,6 +457,15 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zstd_enc_blocks_kernel(const __gr
     const uint32_t chunk = blockIdx.y;
     const uint32_t blk = blockIdx.x * ZB_WPB + warp;
     const uint32_t clen = A.in_len[chunk];
+    if (clen == 0 && blk == 0) {                                  // empty chunk: header + empty last raw block
+        if (lane == 0) {
+            uint8_t* frame = A.out_base + A.out_off[chunk];
+            const uint32_t hl = ze_frame_header(frame, 0);
+            frame[hl] = 1; frame[hl + 1] = 0; frame[hl + 2] = 0;
+            A.out_len[chunk] = hl + 3;
+        }
+        return;
+    }
     if ((uint64_t)blk * ZB >= clen) return;                       // whole warp
     const uint32_t bn = min(ZB, clen - blk * ZB);
     const bool last_block = (uint64_t)(blk + 1) * ZB >= clen;
@@ -646,57 +656,22 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zstd_enc_blocks_kernel(const __gr
         out[0] = (uint8_t)hdr; out[1] = (uint8_t)(hdr >> 8); out[2] = (uint8_t)(hdr >> 16);
         A.blk_size[gblk] = 3 + bsize;
     }
-}
-
-__global__ void __launch_bounds__(256) zstd_enc_assemble_kernel(const __grid_constant__ ZstdBlkArgs A) {
-    __shared__ uint32_t pos[1024 + 1];
-    __shared__ uint32_t hdr_len;
-    const uint32_t chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t clen = A.in_len[chunk];
-    const uint32_t nblk = (clen + ZB - 1) / ZB;
-    uint8_t* frame = A.out_base + A.out_off[chunk];
-    const uint32_t* bs = A.blk_size + (size_t)chunk * A.blocks_per_chunk;
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < nblk; base += 1024) {          // chunks of up to 1024 blocks at a time
-        const uint32_t cnt = min(1024u, nblk - base);
-        if (warp == 0) {
-            uint32_t run = carry;
-            for (uint32_t b0 = 0; b0 < cnt; b0 += 32) {
-                const uint32_t i = b0 + lane;
-                const uint32_t v = i < cnt ? bs[base + i] : 0;
-                const uint32_t inc = warp_inclusive_scan_u32(v, lane);
-                if (i < cnt) pos[i] = run + inc - v;
-                run += __shfl_sync(TS_FULL, inc, 31);
-            }
-            if (lane == 0) {
-                pos[cnt] = run;
-                if (base == 0) {
-                    uint8_t h[16];
-                    const uint32_t hl = ze_frame_header(h, clen);
-                    for (uint32_t k = 0; k < hl; k++) frame[k] = h[k];
-                    hdr_len = hl;
-                }
-            }
+    // ---- placement: the block claims its place in the frame by a look-back over the blocks before it (they were launched
+    // earlier — CTAs start in grid order — so the wait is for work in flight, never for work not yet scheduled) and copies
+    // itself there while it is still hot in L2: no assemble launch, no second pass over the compressed bytes.
+    {
+        const uint32_t bsize_all = 3 + (payload == 0xffffffffu ? bn : payload);
+        unsigned long long* st = A.blk_state + (size_t)chunk * A.blocks_per_chunk;
+        uint8_t* frame = A.out_base + A.out_off[chunk];
+        uint32_t base = 0;
+        if (lane == 0) {
+            base = blk == 0 ? ze_frame_header(frame, clen) : (uint32_t)ze_wait(&st[blk - 1]);
+            if (!last_block) ze_publish(&st[blk], (uint64_t)base + bsize_all);
+            else A.out_len[chunk] = base + bsize_all;
         }
-        __syncthreads();
-        const uint32_t hl = hdr_len;
-        for (uint32_t b = warp; b < cnt; b += blockDim.x >> 5) {
-            const uint8_t* s = A.blk_out + ((size_t)chunk * A.blocks_per_chunk + base + b) * ZB_SLOT;
-            ze_warp_copy(frame + hl + pos[b], s, pos[b + 1] - pos[b], lane);
-        }
-        carry = pos[cnt];
-        __syncthreads();
-    }
-    if (tid == 0) {
-        uint32_t total = hdr_len + carry;
-        if (nblk == 0) {                                           // empty chunk: header + empty last raw block
-            uint8_t h[16];
-            const uint32_t hl = ze_frame_header(h, 0);
-            for (uint32_t k = 0; k < hl; k++) frame[k] = h[k];
-            frame[hl] = 1; frame[hl + 1] = 0; frame[hl + 2] = 0;
-            total = hl + 3;
-        }
-        A.out_len[chunk] = total;
+        base = __shfl_sync(TS_FULL, base, 0);
+        __syncwarp();
+        ze_warp_copy(frame + base, out, bsize_all, lane);
     }
 }
 
@@ -710,10 +685,11 @@ inline const char* zstd_blk_scratch_alloc(ZstdBlkScratch& s, uint32_t chunk_cap,
     if ((e = rt::malloc_device((void**)&s.blk_size, nblk * 4 + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.seqs, nblk * ZE_MAXSEQ * sizeof(uint2) + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.lits, nblk * ZB + 256))) return e;
+    if ((e = rt::malloc_device((void**)&s.blk_state, nblk * 8 + 256))) return e;
     return nullptr;
 }
 inline void zstd_blk_scratch_free(ZstdBlkScratch& s) {
-    rt::free_device(s.blk_out); rt::free_device(s.blk_size); rt::free_device(s.seqs); rt::free_device(s.lits);
+    rt::free_device(s.blk_out); rt::free_device(s.blk_size); rt::free_device(s.seqs); rt::free_device(s.lits); rt::free_device(s.blk_state);
     s = ZstdBlkScratch{};
 }
 constexpr uint32_t ZB_SMEM_BYTES = ZB_WPB * ZB_SMEM_WARP_AL;
@@ -726,16 +702,14 @@ inline int zstd_compress_batch_blocks(ZstdBlkScratch& s, rt::stream_t st, const 
     if (bpc > s.blocks_per_chunk) { g_zstd_err = "chunk larger than the context"; return -1; }
     ZstdBlkArgs A;
     A.in_base = in_base; A.in_off = d_in_off; A.in_len = d_in_len;
-    A.blk_out = s.blk_out; A.blk_size = s.blk_size; A.seqs = s.seqs; A.lits = s.lits;
+    A.blk_out = s.blk_out; A.blk_size = s.blk_size; A.seqs = s.seqs; A.lits = s.lits; A.blk_state = s.blk_state;
     A.blocks_per_chunk = s.blocks_per_chunk;
     A.out_base = out_base; A.out_off = d_out_off; A.out_len = d_out_len;
-    if (bpc) {
-        TS_LAUNCH_P(prof, "zstd_enc_blocks", zstd_enc_blocks_kernel, dim3((bpc + ZB_WPB - 1) / ZB_WPB, n_chunks), dim3(ZB_WPB * 32), ZB_SMEM_BYTES, st, A);
-        const char* e = rt::last_error();
-        if (e) { g_zstd_err = e; return -7; }
-    }
-    TS_LAUNCH_P(prof, "zstd_enc_assemble", zstd_enc_assemble_kernel, dim3(n_chunks), dim3(256), 0, st, A);
-    const char* e = rt::last_error();
+    const uint32_t gx = bpc ? (bpc + ZB_WPB - 1) / ZB_WPB : 1;   // (empty chunks still get their frame from block 0)
+    const char* e = rt::memset_async(s.blk_state, 0, (size_t)s.blocks_per_chunk * n_chunks * 8, st);
+    if (e) { g_zstd_err = e; return -7; }
+    TS_LAUNCH_P(prof, "zstd_enc_blocks", zstd_enc_blocks_kernel, dim3(gx, n_chunks), dim3(ZB_WPB * 32), ZB_SMEM_BYTES, st, A);
+    e = rt::last_error();
     if (e) { g_zstd_err = e; return -7; }
     return 0;
 }
