@@ -621,20 +621,22 @@ def main_tsgpu(args):
             alg = seg + transformed_total
         peak, how = load_peaks()
         achieved = alg / 1e9 / (ms_k / 1000.0)
-        traffic = None
+        traffic, traffic_capture = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(name)
-                if isinstance(traffic, dict):
-                    traffic = traffic.get("bytes")
+                # keys are kernel names ("zstd_enc_blocks"); values {"bytes": per-launch DRAM read + write, "capture": file}
+                tj = json.load(open(tpath))
+                ent = tj.get(name, tj.get(name.rsplit("_", 1)[0]))
+                traffic = ent.get("bytes") if isinstance(ent, dict) else ent
+                traffic_capture = ent.get("capture") if isinstance(ent, dict) else None
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                     "traffic_source": None if traffic is None else
-                    "STATIC: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture "
-                    "named in profiles/traffic.json (not measured in this run)",
+                    "STATIC: dram__bytes_read.sum + dram__bytes_write.sum of one launch at this configuration from the ncu --set "
+                    "full capture %s (not measured in this run)" % traffic_capture,
                     "algorithmic_bytes_per_launch": alg, "kernel_ms": ms_k,
                     "note": "integer/LDS-bound kernels: see DESIGN.md for the ALU/shared-memory ceilings"}
 

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Turn what `scripts/gpu_round.sh rNN` left in gpurun_out/ into the tracked evidence under profiles/ (run here, no GPU):
+bench lines copied as they are, every .ncu-rep summarised (scripts/ncu_summary.py), the launch list reduced to per-kernel
+shares, and profiles/traffic.json refreshed from the full captures (the per-launch DRAM bytes bench.py quotes as STATIC).
+usage: make_profiles.py r02"""
+import collections
+import csv
+import glob
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = sys.argv[1] if len(sys.argv) > 1 else "r02"
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+for f in sorted(glob.glob(os.path.join(G, R + "_bench_*.json")) + glob.glob(os.path.join(G, R + "_detransform.json"))):
+    txt = open(f).read().strip()
+    if not txt:
+        continue
+    line = txt.splitlines()[-1]
+    try:
+        json.loads(line)
+    except ValueError:
+        continue
+    open(os.path.join(P, os.path.basename(f)), "w").write(line + "\n")
+    print("bench line", os.path.basename(f))
+
+traffic = {}
+for rep in sorted(glob.glob(os.path.join(G, "prof_" + R + "_*.ncu-rep"))):
+    name = os.path.basename(rep)[len("prof_"):-len(".ncu-rep")]
+    out = os.path.join(P, name + ".ncu.json")
+    txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, out], capture_output=True, text=True).stdout
+    try:
+        d = json.loads(txt)[0]
+    except (ValueError, IndexError):
+        print("could not read", rep)
+        continue
+    def num(s):
+        v, _, u = s.partition(" ")
+        return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u.strip(), 1.0)
+    if "dram_read" in d and "dram_write" in d:
+        key = name[len(R) + 1:]                      # e.g. zstd_enc_blocks
+        traffic[key] = {"bytes": num(d["dram_read"]) + num(d["dram_write"]), "capture": "profiles/%s.ncu.json" % name,
+                        "duration_under_ncu": d.get("duration")}
+    print("ncu summary", name, d.get("duration"), d.get("issue_active_pct"))
+if traffic:
+    json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+
+lst = os.path.join(G, R + "_launches.csv")
+if os.path.exists(lst):
+    shutil.copy(lst, os.path.join(P, R + "_launches_zstdaes_1GiB.csv"))
+    rows = [r for r in csv.reader(open(lst)) if len(r) > 5]
+    hdr = next(r for r in rows if "Kernel Name" in r)
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    acc = collections.Counter(); cnt = collections.Counter()
+    for r in rows:
+        if r is hdr or len(r) <= vi:
+            continue
+        try:
+            acc[r[ki].split("(")[0]] += float(r[vi].replace(",", "")); cnt[r[ki].split("(")[0]] += 1
+        except ValueError:
+            pass
+    tot = sum(acc.values())
+    json.dump({k: {"launches": cnt[k], "ns_total": acc[k], "share": acc[k] / tot} for k in acc}, open(os.path.join(P, R + "_launch_shares_zstdaes_1GiB.json"), "w"), indent=1)
+    print("launch shares", {k: round(v / tot, 3) for k, v in acc.items()})

@@ -773,10 +773,14 @@ extern "C" int tsgpu_transform_device(tsgpu_ctx* c, int device_index, uint32_t f
         cur_base = fb; cur_off = fo; cur_len = fl; cur_max = (uint32_t)frame_bound(cs);
     }
     if (flags & TSGPU_FLAG_AES) {
-        w.key_valid = false;                                 // built on the caller's stream: do not reuse across calls
-        rc = gcm_stage<true>(c, w, st, rk, false, cur_base, cur_off, cur_len, d_slots, w.dd.c_off, d_transformed_sizes,
+        // the slot's key tables are reused while the key stays the same: device calls are ordered behind each other by
+        // events (dev_call_begin) and host calls only take the slot once device work on it has completed
+        const bool key_ready = w.key_valid && memcmp(&w.key_rk, &rk, sizeof rk) == 0;
+        w.key_rk = rk; w.key_valid = false;
+        rc = gcm_stage<true>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, d_slots, w.dd.c_off, d_transformed_sizes,
                              w.dd.ivs, w.dd.aad, aad_len, w.dd.status, nb, cur_max, w.d_partials, w.max_ranges);
         if (rc) return rc;
+        w.key_valid = true;
     }
     return dev_call_end(w, st);
 }
@@ -820,11 +824,13 @@ extern "C" int tsgpu_detransform_device(tsgpu_ctx* c, int device_index, uint32_t
         const uint64_t* oo = z ? w.dd.b_off : w.dd.a_off;
         uint32_t* ol = z ? w.dd.b_len : d_original_sizes;
         uint32_t max_t = (uint32_t)(slot_stride - TSGPU_SLOT_HEAD);
-        w.key_valid = false;
+        const bool key_ready = w.key_valid && memcmp(&w.key_rk, &rk, sizeof rk) == 0;
+        w.key_rk = rk; w.key_valid = false;
         const uint32_t out_room = z ? (uint32_t)std::min<uint64_t>(c->frame_stride - 16, in_room - 28) : chunk_size;
-        rc = gcm_stage<false>(c, w, st, rk, false, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
+        rc = gcm_stage<false>(c, w, st, rk, key_ready, cur_base, cur_off, cur_len, ob, oo, ol, nullptr, w.dd.aad, aad_len,
                               d_status, n_chunks, max_t, w.d_partials, w.max_ranges, out_room);
         if (rc) return rc;
+        w.key_valid = true;
         cur_base = ob; cur_off = oo; cur_len = ol;
     }
     if (flags & TSGPU_FLAG_ZSTD) {

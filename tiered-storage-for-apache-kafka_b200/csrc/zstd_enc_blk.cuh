@@ -656,20 +656,17 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zstd_enc_blocks_kernel(const __gr
         out[0] = (uint8_t)hdr; out[1] = (uint8_t)(hdr >> 8); out[2] = (uint8_t)(hdr >> 16);
         A.blk_size[gblk] = 3 + bsize;
     }
-    // ---- placement: the block claims its place in the frame by a look-back over the blocks before it (they were launched
-    // earlier — CTAs start in grid order — so the wait is for work in flight, never for work not yet scheduled) and copies
-    // itself there while it is still hot in L2: no assemble launch, no second pass over the compressed bytes.
+    // ---- placement: the block claims its place in the frame by a decoupled look-back over the sizes of the blocks before
+    // it (ze_lookback; they were launched earlier — CTAs start in grid order — so a wait is for work in flight, never for
+    // work not yet scheduled) and copies itself there while it is still hot in L2: no assemble launch, no second pass.
     {
         const uint32_t bsize_all = 3 + (payload == 0xffffffffu ? bn : payload);
         unsigned long long* st = A.blk_state + (size_t)chunk * A.blocks_per_chunk;
         uint8_t* frame = A.out_base + A.out_off[chunk];
-        uint32_t base = 0;
-        if (lane == 0) {
-            base = blk == 0 ? ze_frame_header(frame, clen) : (uint32_t)ze_wait(&st[blk - 1]);
-            if (!last_block) ze_publish(&st[blk], (uint64_t)base + bsize_all);
-            else A.out_len[chunk] = base + bsize_all;
-        }
-        base = __shfl_sync(TS_FULL, base, 0);
+        if (blk == 0 && lane == 0) ze_frame_header(frame, clen);
+        __threadfence();                                           // (the slot's bytes are this warp's own: ordered by the warp sync below)
+        const uint32_t base = ze_lookback(st, blk, bsize_all, ze_frame_header_size(clen), last_block, lane);
+        if (last_block && lane == 0) A.out_len[chunk] = base + bsize_all;
         __syncwarp();
         ze_warp_copy(frame + base, out, bsize_all, lane);
     }
