@@ -9,3 +9,5 @@ import json
 a = json.loads(open('gpurun_out/${R}_bench_1gpu_same_box.json').read().strip().splitlines()[-1]); b = json.loads(open('gpurun_out/${R}_bench_2gpu.json').read().strip().splitlines()[-1])
 print('1 GPU value %.1f e2e %.1f | 2 GPUs value %.1f e2e %.1f | e2e scaling %.3f' % (a['value'], a['e2e']['value'], b['value'], b['e2e']['value'], b['e2e']['value'] / (2 * a['e2e']['value'])))
 PY
+python scripts/pcie_ceiling.py > gpurun_out/${R}_pcie_1rank.json 2>/dev/null; cat gpurun_out/${R}_pcie_1rank.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 scripts/pcie_ceiling.py > gpurun_out/${R}_pcie_2ranks.json 2>/dev/null; cat gpurun_out/${R}_pcie_2ranks.json

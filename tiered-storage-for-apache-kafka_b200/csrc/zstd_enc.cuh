@@ -38,6 +38,12 @@ constexpr uint32_t ZR = ZB * ZR_SLICES;        // 64 KiB region
 #ifndef ZE_TUNE_HLOG_H
 #define ZE_TUNE_HLOG_H 11
 #endif
+#ifndef ZE_TUNE_DET      // 0: plain hash-table stores (whichever lane wins) — A/B runs only: what determinism costs
+#define ZE_TUNE_DET 1
+#endif
+#ifndef ZE_TUNE_HIST     // 0: no history tables (matches stay inside their 8 KiB slice) — A/B runs only: what the 64 KiB window costs
+#define ZE_TUNE_HIST 1
+#endif
 constexpr int ZE_HLOG = ZE_TUNE_HLOG;          // per-slice running tables: 2^10 x u16 (region-relative position)
 constexpr uint32_t ZE_HSIZE = 1u << ZE_HLOG;
 constexpr int ZE_HLOG_H = ZE_TUNE_HLOG_H;      // history tables (last occurrence in all earlier slices): 7 of them
@@ -125,12 +131,13 @@ static inline unsigned __match_any_sync(unsigned, unsigned v) {
 
 __device__ __forceinline__ void ze_insert_max(uint16_t* ht, uint32_t h, uint32_t p, bool valid) {
     if (valid) ht[h] = (uint16_t)p;
-    while (true) {
+    while (ZE_TUNE_DET) {
         __syncwarp();
         const bool lost = valid && ht[h] < p;            // a lower position of this step sits in the slot
         if (!__any_sync(TS_FULL, lost)) break;
         if (lost) ht[h] = (uint16_t)p;
     }
+    if (!ZE_TUNE_DET) __syncwarp();
 }
 
 }  // namespace ts
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__(ZE_THREADS, 2) zstd_enc_regions_kernel(const _
     const bool have_slice = s0 < rn;
 
     // ---- phase 1: history tables.  Pre-pass: last occurrence of every hash inside each slice ...
-    if (have_slice && nslice > 1 && w + 1 < nslice) {    // the last slice's table would serve nobody
+    if (ZE_TUNE_HIST && have_slice && nslice > 1 && w + 1 < nslice) {    // the last slice's table would serve nobody
         uint16_t* fin = ht_fin_all + w * ZE_HSIZE_H;
         for (uint32_t cur = s0; cur < s1; cur += 32) {
             const uint32_t p = cur + lane;
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(ZE_THREADS, 2) zstd_enc_regions_kernel(const _
         }
         __syncthreads();
     }
-    const uint16_t* ht_hist = w > 0 ? ht_fin_all + (w - 1) * ZE_HSIZE_H : nullptr;
+    const uint16_t* ht_hist = (ZE_TUNE_HIST && w > 0) ? ht_fin_all + (w - 1) * ZE_HSIZE_H : nullptr;
 
     // ---- phase 2: greedy LZ parse of the slice, 32 positions per step
     // Straight-line work per lane (no loops, no divergence worth the name): hash, look up, verify the candidate on 4 bytes,
