@@ -150,10 +150,12 @@ int tsgpu_detransform_device(tsgpu_ctx* ctx, int device_index, uint32_t flags,
                              void* stream);
 /* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
 uint64_t tsgpu_launch_count(const tsgpu_ctx* ctx);
-/* Which decode path zstd frames took so far on this context: out[0] 64 KiB regions executed in shared memory (frames of this
- * library's writer), out[1] frames handed from a region to the frame executor, out[2] frames executed whole (frames written by
- * libzstd, i.e. by the reference), out[3] frames on the serial fallback kernel.  Synchronises the context's devices. */
-int tsgpu_decode_path_stats(tsgpu_ctx* ctx, uint64_t out[4]);
+/* Which decode path zstd frames took so far on this context: out[0] 64 KiB regions executed in shared memory (dense-mode frames
+ * of this library's writer), out[1] frames handed from a region / block to the frame executor, out[2] frames executed whole
+ * (frames written by libzstd, i.e. by the reference), out[3] frames on the serial fallback kernel, out[4] self-contained 8 KiB
+ * blocks executed by a warp each (speed-mode frames of this library's writer), out[5..7] reserved (0).
+ * Synchronises the context's devices. */
+int tsgpu_decode_path_stats(tsgpu_ctx* ctx, uint64_t out[8]);
 /* Optional per-kernel timing with CUDA events recorded on the launching stream (bench.py's roofline numbers).
  * report: JSON {"kernel": {"launches": n, "ms": total}, ...}; synchronises the context's devices. */
 int tsgpu_profile_enable(tsgpu_ctx* ctx, int on);

@@ -111,14 +111,15 @@ template <class T> inline T xchg(T v, int src) {
 #define warpSize 32
 
 static inline void __syncthreads() { simt::block_barrier(); }
-static inline int __syncthreads_or(int pred) {
+static inline int __syncthreads_count(int pred) {
     simt::Block& b = *simt::g_blk;
-    const int my = b.bar_gen, k = b.or_gen;          // or_gen moves only when an or-barrier completes
-    if (pred) b.or_acc[k % 3] = 1;
+    const int my = b.bar_gen, k = b.or_gen;          // or_gen moves only when a voting barrier completes
+    if (pred) b.or_acc[k % 3] += 1;
     if (++b.bar_count >= b.alive) { b.bar_count = 0; b.or_acc[(k + 1) % 3] = 0; b.or_gen++; b.bar_gen++; }
     else while (b.bar_gen == my) simt::yield();
     return b.or_acc[k % 3];
 }
+static inline int __syncthreads_or(int pred) { return __syncthreads_count(pred) != 0; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_barrier(); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}

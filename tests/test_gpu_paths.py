@@ -42,16 +42,19 @@ def test_gpu_decode_paths_libzstd_frames_and_own_regions():
             assert osz == [n] and np.array_equal(back, src), (kind, n, level)
         st0 = ctx.decode_path_stats()
         assert st0["whole_frames"] == 5 and st0["regions"] == 0 and st0["serial_frames"] == 0
-        srcs = [corpus.gen_chunk("K", 9 + i, 0, 1 << 20) for i in range(3)]
+        # one batch: two libzstd frames, a speed-mode frame (a warp per self-contained block), a dense-mode frame (a CTA per region)
+        srcs = [corpus.gen_chunk("K", 9 + i, 0, 1 << 20) for i in range(2)]
         frames = [np.frombuffer(ora.zstd_compress_chunk(s), dtype=np.uint8) for s in srcs]
         mine, msz = ctx.transform(Z, srcs[0], 0)
         frames.append(mine[:msz[0]])
+        dense, dsz = ctx.transform(Z | 4, srcs[1], 0)
+        frames.append(dense[:dsz[0]])
         back, _ = ctx.detransform(Z, np.concatenate(frames), [f.size for f in frames], 4 << 20)
-        assert np.array_equal(back, np.concatenate(srcs + [srcs[0]]))
+        assert np.array_equal(back, np.concatenate(srcs + srcs))
         names = set(ctx.profile_report())
-        assert "zstd_dec_entropy" in names and "zstd_dec_frame_exec" in names and "zstd_dec_regions" in names
+        assert {"zstd_dec_entropy", "zstd_dec_frame_exec", "zstd_dec_regions", "zstd_dec_blk_literals", "zstd_dec_blk_sequences", "zstd_dec_blk_exec"} <= names
         st1 = ctx.decode_path_stats()
-        assert st1["whole_frames"] == 8 and st1["regions"] == 16 and st1["region_fallback_frames"] == 0
+        assert st1["whole_frames"] == 7 and st1["regions"] == 16 and st1["blocks"] == 128 and st1["region_fallback_frames"] == 0
         rng = np.random.default_rng(4)
         for trial in range(40):
             bad = frames[1].copy()

@@ -179,20 +179,24 @@ def test_simt_decode_paths_libzstd_frames_and_own_regions():
             back, osz = c2.detransform(Z, frame, [frame.size], n)
             assert osz == [n] and np.array_equal(back, src), (kind, n, level)
         st0 = c2.decode_path_stats()
-        # (the 5-byte frame is a single small block: that shape also qualifies for the region path)
-        assert st0["whole_frames"] == 8 and st0["regions"] == 1 and st0["serial_frames"] == 0
-        # several frames in one batch, mixed with this library's own frames (region path)
-        srcs = [corpus.gen_chunk("K", 9 + i, 0, 300000) for i in range(3)]
+        # (the 5-byte frame is a single small block: that shape qualifies for the independent-block path)
+        assert st0["whole_frames"] == 8 and st0["blocks"] == 1 and st0["regions"] == 0 and st0["serial_frames"] == 0
+        # several frames in one batch, mixed with this library's own frames: speed mode (a warp per self-contained block) and
+        # dense mode (a CTA per 64 KiB region)
+        srcs = [corpus.gen_chunk("K", 9 + i, 0, 300000) for i in range(2)]
         frames = [np.frombuffer(ora.zstd_compress_chunk(s), dtype=np.uint8) for s in srcs]
         mine, msz = c2.transform(Z, srcs[0], 0)
         frames.append(mine[:msz[0]])
+        dense, dsz = c2.transform(Z | 4, srcs[1], 0)
+        frames.append(dense[:dsz[0]])
         blob = np.concatenate(frames)
         back, osz = c2.detransform(Z, blob, [f.size for f in frames], 4 * 300000)
-        assert np.array_equal(back, np.concatenate(srcs + [srcs[0]]))
+        assert np.array_equal(back, np.concatenate(srcs + srcs))
         names = set(c2.profile_report())
-        assert "zstd_dec_entropy" in names and "zstd_dec_frame_exec" in names and "zstd_dec_regions" in names
+        assert {"zstd_dec_entropy", "zstd_dec_frame_exec", "zstd_dec_regions", "zstd_dec_blk_literals", "zstd_dec_blk_sequences", "zstd_dec_blk_exec"} <= names
         st1 = c2.decode_path_stats()
-        assert st1["whole_frames"] == st0["whole_frames"] + 3 and st1["regions"] == 1 + 5 and st1["region_fallback_frames"] == 0
+        assert st1["whole_frames"] == st0["whole_frames"] + 2 and st1["regions"] == 5 and st1["blocks"] == 1 + 37
+        assert st1["region_fallback_frames"] == 0 and st1["serial_frames"] == 0
         rng = np.random.default_rng(4)
         base = frames[1]
         for trial in range(60):
@@ -204,5 +208,38 @@ def test_simt_decode_paths_libzstd_frames_and_own_regions():
                 assert e.code == binding.E_CORRUPT
             else:
                 assert len(out) == 300000
+    finally:
+        c2.close()
+
+
+def _executor_shapes():
+    """Inputs whose libzstd frames drive the frame executor's pointer-jumping steps into every branch."""
+    rng = np.random.default_rng(77)
+    out = {}
+    out["zeros"] = np.zeros(400000, dtype=np.uint8)                                   # one giant match, offset 1 (periodic source)
+    blk = rng.integers(0, 256, 5000, dtype=np.uint8)
+    out["period5000"] = np.tile(blk, 70)                                              # giant matches, offset 5000 >= the CTA (rounds)
+    blk2 = rng.integers(0, 256, 700, dtype=np.uint8)
+    out["period700"] = np.tile(blk2, 400)                                             # giant matches, offset < the CTA
+    rec = rng.integers(97, 123, 120, dtype=np.uint8)                                  # records that differ in one byte: ~1 literal + ~100
+    recs = np.tile(rec, 3000).reshape(3000, 120).copy()                               # bytes of match per sequence, chained back record
+    recs[np.arange(3000), rng.integers(0, 120, 3000)] = rng.integers(65, 91, 3000, dtype=np.uint8)   # by record: a step of 1024
+    out["records"] = recs.reshape(-1)                                                 # sequences spans > 32 KiB (cut) and chains deep
+    mix = np.concatenate([out["records"][:100000], np.zeros(70000, dtype=np.uint8), rng.integers(0, 256, 30000, dtype=np.uint8),
+                          out["period700"][:90000], out["records"][5000:90000]])
+    out["mixed"] = mix
+    return out
+
+
+def test_simt_frame_executor_pointer_jumping_shapes():
+    c2 = tsgpu.Context(max_chunk_bytes=1 << 20, max_batch=2, lib_path=SIMT_LIB)
+    try:
+        for name, src in _executor_shapes().items():
+            for level in (1, 3, 19):
+                frame = np.frombuffer(ora.zstd_compress_level(src, level), dtype=np.uint8)
+                back, osz = c2.detransform(Z, frame, [frame.size], src.size)
+                assert osz == [src.size] and np.array_equal(back, src), (name, level)
+        st = c2.decode_path_stats()
+        assert st["whole_frames"] == 15 and st["serial_frames"] == 0
     finally:
         c2.close()

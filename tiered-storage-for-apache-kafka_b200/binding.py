@@ -128,10 +128,10 @@ class Context:
         return int(self.lib.tsgpu_launch_count(self._h))
 
     def decode_path_stats(self):
-        """{'regions': n, 'region_fallback_frames': n, 'whole_frames': n, 'serial_frames': n} since the context was created"""
-        v = (C.c_uint64 * 4)()
+        """{'regions': n, 'region_fallback_frames': n, 'whole_frames': n, 'serial_frames': n, 'blocks': n} since the context was created"""
+        v = (C.c_uint64 * 8)()
         self._check(self.lib.tsgpu_decode_path_stats(self._h, v))
-        return dict(zip(("regions", "region_fallback_frames", "whole_frames", "serial_frames"), [int(x) for x in v]))
+        return dict(zip(("regions", "region_fallback_frames", "whole_frames", "serial_frames", "blocks"), [int(x) for x in v]))
 
     def profile_enable(self, on=True):
         self._check(self.lib.tsgpu_profile_enable(self._h, 1 if on else 0))

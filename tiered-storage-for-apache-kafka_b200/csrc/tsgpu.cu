@@ -861,20 +861,20 @@ extern "C" int tsgpu_profile_report(tsgpu_ctx* c, char* out, uint32_t* out_len) 
 }
 
 // Which decode path the zstd frames of this context's calls took so far (summed over devices and work slots):
-// out[0] regions executed in shared memory, out[1] frames a region handed to the frame executor, out[2] frames executed
-// whole (libzstd-shaped), out[3] frames on the serial kernel.  Lets tests and bench.py assert that a workload ran on the
-// path it is supposed to measure.
-extern "C" int tsgpu_decode_path_stats(tsgpu_ctx* c, uint64_t out[4]) {
+// out[0] regions executed in shared memory, out[1] frames a region / block handed to the frame executor, out[2] frames executed
+// whole (libzstd-shaped), out[3] frames on the serial kernel, out[4] independent blocks executed by a warp each, out[5..7] 0.
+// Lets tests and bench.py assert that a workload ran on the path it is supposed to measure.
+extern "C" int tsgpu_decode_path_stats(tsgpu_ctx* c, uint64_t out[8]) {
     if (!c || !out) return fail(TSGPU_E_ARG, "null argument");
     std::lock_guard<std::mutex> lock(c->mu);
-    for (int k = 0; k < 4; k++) out[k] = 0;
+    for (int k = 0; k < 8; k++) out[k] = 0;
     for (auto& l : c->lanes) for (auto& w : l.w) if (w.ready && w.zdec.stats) {
         RT(rt::set_device(w.device));
         RT(rt::device_sync());
-        unsigned long long v[4];
+        unsigned long long v[8];
         RT(rt::d2h(v, w.zdec.stats, sizeof v, nullptr));
         RT(rt::device_sync());
-        for (int k = 0; k < 4; k++) out[k] += v[k];
+        for (int k = 0; k < 8; k++) out[k] += v[k];
     }
     return TSGPU_OK;
 }

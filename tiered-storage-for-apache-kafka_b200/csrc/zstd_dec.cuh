@@ -53,6 +53,7 @@ struct ZdWarpCtx {                        // per-warp shared-memory working set 
     uint32_t rep[3];
     int32_t err;                          // 0 ok, <0 corrupt, >0 "needs the general path"
     uint32_t tmp[8];
+    static constexpr int kTabLogCap = 9;  // largest FSE table this context holds
 };
 
 struct ZstdDecScratch {
@@ -67,7 +68,8 @@ struct ZstdDecScratch {
     uint64_t* par_seqs = nullptr;    // n_chunks * par_seq_cap
     uint32_t par_lit_cap = 0, par_seq_cap = 0;
     unsigned long long* stats = nullptr;   // [0] regions executed in shared memory, [1] frames sent to the frame executor after a
-                                           // region refused, [2] frames executed whole (libzstd-shaped), [3] frames on the serial kernel
+                                           // region / block refused, [2] frames executed whole (libzstd-shaped), [3] frames on the serial
+                                           // kernel, [4] independent blocks executed by a warp each
 };
 
 struct ZstdDecArgs {
@@ -79,7 +81,8 @@ struct ZstdDecArgs {
     uint8_t* par_meta; uint8_t* par_lits; uint64_t* par_seqs; uint32_t par_lit_cap, par_seq_cap;
     unsigned long long* stats;
 };
-constexpr int ZD_INFO = 8;     // fcs, nblk, fast-path eligible, need_general / failed, header size, parallel-general, literal bump, sequence bump
+constexpr int ZD_INFO = 12;    // fcs, nblk, region-path eligible, state bits (1 executor refused -> frame executor, 2 failed, 4 independent-
+                               // block entropy stage refused), header size, parallel-general, literal bump, sequence bump, [8] independent-block guess
 
 // ------------------------------------------------------------------------------------------ bit readers
 __device__ __forceinline__ uint64_t zd_ld64(const uint8_t* p) {          // unaligned little-endian 64-bit window
@@ -182,7 +185,7 @@ __device__ TS_NOINLINE uint32_t zd_read_ncount(const uint8_t* src, uint32_t size
 }
 
 // Huffman tree description -> decoding table.  Returns bytes consumed, 0 on error.  One lane.
-__device__ TS_NOINLINE uint32_t zd_read_huf_table(const uint8_t* src, uint32_t size, ZdWarpCtx* cx) {
+template <class CX> __device__ TS_NOINLINE uint32_t zd_read_huf_table(const uint8_t* src, uint32_t size, CX* cx) {
     if (size < 1) return 0;
     const uint32_t hb = src[0];
     uint32_t nw = 0, used = 0;
@@ -251,7 +254,7 @@ __device__ TS_NOINLINE uint32_t zd_read_huf_table(const uint8_t* src, uint32_t s
     return used;
 }
 // All lanes: fill the decoding table from the per-symbol start cells computed above.
-__device__ __forceinline__ void zd_fill_huf_warp(ZdWarpCtx* cx, uint32_t lane) {
+template <class CX> __device__ __forceinline__ void zd_fill_huf_warp(CX* cx, uint32_t lane) {
     const uint32_t nw = cx->huf_nw, max_bits = cx->huf_log;
     for (uint32_t s = 0; s < nw; s++) {
         const uint32_t w = cx->weights[s];
@@ -277,11 +280,51 @@ __device__ __forceinline__ bool zd_huf_stream(const uint16_t* __restrict__ huf, 
     return b.bits == 0;
 }
 
+// The same for a destination in global memory: symbols leave four at a time as one 32-bit store once the destination is
+// aligned, and the bit window is reloaded once per four symbols (4 * 11 bits fit behind the <= 7 already-consumed bits of a
+// byte-aligned 64-bit window).  Overruns inside a group of four only read zeros (the peek zero-extends) and are caught after it.
+__device__ __forceinline__ bool zd_huf_stream_packed(const uint16_t* __restrict__ huf, uint32_t log, const uint8_t* src, uint32_t size,
+                                                     uint8_t* dst, uint32_t count) {
+    ZdBack b;
+    if (!zd_back_init(b, src, size)) return false;
+    uint32_t i = 0;
+    const uint32_t head = min(count, (4u - (uint32_t)((uintptr_t)dst & 3)) & 3u);
+    for (; i < head; i++) {
+        const uint16_t e = huf[zd_back_peek(b, log)];
+        dst[i] = (uint8_t)e;
+        b.bits -= (int32_t)(e >> 8);
+    }
+    if (b.bits < 0) return false;
+    const uint32_t mask = (1u << log) - 1;
+    while (i + 4 <= count && b.bits >= 64) {
+        const int32_t cbase = ((b.bits + 7) & ~7) - 64;
+        const uint64_t C = zd_ld64(b.p + (cbase >> 3));
+        int32_t pos = b.bits - cbase;                    // 57..64 unread bits of C
+        uint32_t out = 0;
+        _Pragma("unroll")
+        for (int k = 0; k < 4; k++) {
+            const uint16_t e = huf[(uint32_t)(C >> (pos - (int32_t)log)) & mask];
+            out |= (uint32_t)(e & 0xff) << (8 * k);
+            pos -= (int32_t)(e >> 8);
+        }
+        *(uint32_t*)(dst + i) = out;
+        b.bits = cbase + pos;
+        i += 4;
+    }
+    for (; i < count; i++) {
+        const uint16_t e = huf[zd_back_peek(b, log)];
+        dst[i] = (uint8_t)e;
+        b.bits -= (int32_t)(e >> 8);
+        if (b.bits < 0) return false;
+    }
+    return b.bits == 0;
+}
+
 // Sequence table of one kind according to its compression mode.  Lane 0.  Returns bytes consumed, -1 on error.
 // Warp-parallel build of a sequence decoding table whose distribution has no "less than one" symbols (what this
 // library's writer emits): the spread then has the closed form pos(i) = i*step & mask, a cell's symbol is found by
 // binary search in the cumulative counts, and cells of a symbol are numbered in position order with match_any.
-__device__ __forceinline__ void zd_build_dtable_warp(int kind, ZdWarpCtx* cx, uint32_t lane) {
+template <class CX> __device__ __forceinline__ void zd_build_dtable_warp(int kind, CX* cx, uint32_t lane) {
     zf::FseDEntry* T = kind == 0 ? cx->ll : kind == 1 ? cx->of : cx->ml;
     const int16_t* nm = cx->norm3[kind];
     const uint32_t log = cx->pend_log[kind], nsym = cx->pend_nsym[kind];
@@ -319,12 +362,13 @@ __device__ __forceinline__ void zd_build_dtable_warp(int kind, ZdWarpCtx* cx, ui
     }
 }
 
-__device__ TS_NOINLINE int32_t zd_seq_table(uint32_t mode, int kind, const uint8_t* src, uint32_t size, ZdWarpCtx* cx, bool fast_nonfirst, uint32_t* pending) {
+template <class CX> __device__ TS_NOINLINE int32_t zd_seq_table(uint32_t mode, int kind, const uint8_t* src, uint32_t size, CX* cx, bool fast_nonfirst, uint32_t* pending) {
     zf::FseDEntry* T = kind == 0 ? cx->ll : kind == 1 ? cx->of : cx->ml;
     uint32_t* logp = kind == 0 ? &cx->ll_log : kind == 1 ? &cx->of_log : &cx->ml_log;
     uint32_t* validp = kind == 0 ? &cx->ll_valid : kind == 1 ? &cx->of_valid : &cx->ml_valid;
     const int max_sym = kind == 0 ? 35 : kind == 1 ? 31 : 52;
-    const int max_log = kind == 0 ? zf::LL_MAX_LOG : kind == 1 ? zf::OF_MAX_LOG : zf::ML_MAX_LOG;
+    const int fmt_log = kind == 0 ? zf::LL_MAX_LOG : kind == 1 ? zf::OF_MAX_LOG : zf::ML_MAX_LOG;
+    const int max_log = fmt_log < CX::kTabLogCap ? fmt_log : CX::kTabLogCap;      // (a lean context refuses larger tables)
     if (mode == 0) {                                    // Predefined_Mode
         const int16_t* nm = kind == 0 ? g_seq_tables.ll_norm : kind == 1 ? g_seq_tables.of_norm : g_seq_tables.ml_norm;
         const int ns = kind == 0 ? 36 : kind == 1 ? 29 : 53;
@@ -354,6 +398,68 @@ __device__ TS_NOINLINE int32_t zd_seq_table(uint32_t mode, int kind, const uint8
     // Repeat_Mode: the previous block's table of this kind
     if (fast_nonfirst) { cx->err = 1; return 0; }
     return *validp ? 0 : -1;
+}
+
+// Literals_Section_Header of a Compressed_Block, one lane; a Huffman tree description is read into cx.  out: type, header
+// size, Regenerated_Size, Compressed_Size (incl. the tree), streams, tree-description bytes.  false: malformed.
+// Treeless literals with no_inherit set cx->err = 1 ("needs the general path") and still return true.
+template <class CX> __device__ __forceinline__ bool zd_parse_lit_header(const uint8_t* blk, uint32_t bsize, uint32_t limit, uint32_t litcap,
+                                                                        bool no_inherit, CX* cx, uint32_t* out) {
+    if (bsize < 2) return false;                        // Compressed_Block needs at least literals header + seq header
+    const uint32_t b0 = blk[0], type = b0 & 3, sf = (b0 >> 2) & 3;
+    uint32_t hs, regen, comp = 0, streams = 1;
+    if (type < 2) {
+        if ((sf & 1) == 0) { hs = 1; regen = b0 >> 3; }
+        else if (sf == 1) { hs = 2; regen = (b0 >> 4) | ((uint32_t)blk[1] << 4); }
+        else { if (bsize < 3) return false; hs = 3; regen = (b0 >> 4) | ((uint32_t)blk[1] << 4) | ((uint32_t)blk[2] << 12); }
+        comp = type == 0 ? regen : 1;
+    } else {
+        if (bsize < 5) return false;
+        const uint32_t h = blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
+        if (sf <= 1) { hs = 3; regen = (h >> 4) & 0x3ff; comp = (h >> 14) & 0x3ff; streams = sf == 0 ? 1 : 4; }
+        else if (sf == 2) { hs = 4; regen = (h >> 4) & 0x3fff; comp = h >> 18; streams = 4; }
+        else { hs = 5; regen = (h >> 4) & 0x3ffff; comp = (h >> 22) | ((uint32_t)blk[4] << 10); streams = 4; }
+    }
+    if (hs + comp > bsize || regen > limit || regen > zf::BLOCK_MAX) return false;
+    if (type >= 2 && regen > litcap) return false;
+    uint32_t tree = 0;
+    if (type == 2) {
+        tree = zd_read_huf_table(blk + hs, comp, cx);
+        if (!tree) return false;
+    } else if (type == 3) {
+        if (no_inherit) { cx->err = 1; }
+        else if (!cx->huf_valid) return false;
+    }
+    out[0] = type; out[1] = hs; out[2] = regen; out[3] = comp; out[4] = streams; out[5] = tree;
+    return true;
+}
+
+// Sequences_Section_Header, one lane: Number_of_Sequences, the modes byte and the three tables (serial builds happen here,
+// FSE_Compressed tables without "less than one" symbols are left pending for the warp).  out: nseq, bytes before the bit
+// stream, pending mask.  false: malformed.  Repeat_Mode with no_inherit sets cx->err = 1.
+template <class CX> __device__ __forceinline__ bool zd_parse_seq_header(const uint8_t* sp, uint32_t ssize, bool no_inherit, CX* cx, uint32_t* out) {
+    if (ssize < 1) return false;
+    uint32_t nseq = sp[0], hs = 1;
+    if (nseq >= 128) {
+        if (nseq == 255) { if (ssize < 3) return false; nseq = sp[1] + ((uint32_t)sp[2] << 8) + 0x7f00; hs = 3; }
+        else { if (ssize < 2) return false; nseq = ((nseq - 128) << 8) + sp[1]; hs = 2; }
+    }
+    uint32_t pos = hs, pend = 0;
+    if (nseq) {
+        if (ssize < hs + 1) return false;
+        const uint32_t modes = sp[hs];
+        if (modes & 3) return false;                    // reserved bits
+        pos = hs + 1;
+        const uint32_t m3[3] = { modes >> 6, (modes >> 4) & 3, (modes >> 2) & 3 };   // LL, OF, ML
+        for (int k = 0; k < 3; k++) {
+            const int32_t used = zd_seq_table(m3[k], k, sp + pos, ssize - pos, cx, no_inherit, &pend);
+            if (used < 0) return false;
+            pos += (uint32_t)used;
+        }
+        if (pos > ssize) return false;
+    }
+    out[0] = nseq; out[1] = pos; out[2] = pend;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------ one compressed block
@@ -582,9 +688,20 @@ template <int T> struct ZxShared {
     int32_t err;
 };
 
+// T == 32: the "CTA" is one warp among several of its thread block, so barriers are warp barriers.
+template <int T> __device__ __forceinline__ void zx_barrier() { if (T == 32) __syncwarp(); else __syncthreads(); }
+template <int T> __device__ __forceinline__ bool zx_barrier_or(bool p) {
+    if (T == 32) return __any_sync(TS_FULL, p) != 0;
+    return __syncthreads_or(p) != 0;
+}
+template <int T> __device__ __forceinline__ uint32_t zx_barrier_count(bool p) {
+    if (T == 32) return (uint32_t)__popc(__ballot_sync(TS_FULL, p));
+    return (uint32_t)__syncthreads_count(p);
+}
 template <int T> __device__ __forceinline__ uint64_t zx_block_scan(uint64_t v, uint32_t tid, ZxShared<T>* sh, uint64_t* total) {
     const uint32_t lane = tid & 31, w = tid >> 5;
     uint64_t inc = warp_inclusive_scan_u64(v, lane);
+    if (T == 32) { *total = __shfl_sync(TS_FULL, inc, 31); return inc; }
     if (lane == 31) sh->wsum[w] = inc;
     __syncthreads();
     if (w == 0) {
@@ -624,9 +741,18 @@ __device__ __forceinline__ void zx_copy_from_hbm(uint8_t* d, const uint8_t* s, u
     }
     if (k < n) {                                         // tail: up to 15 bytes, loads first (reads at most 3 bytes past the end of the source's last word)
         const uint32_t r = n - k;
-        uint32_t w[4] = {0, 0, 0, 0};
-        for (uint32_t q = 0; q * 4 < r; q++) w[q] = ld_u32_unaligned(s + k + 4 * q);
-        for (uint32_t q = 0; q < r; q++) d[k + q] = (uint8_t)(w[q >> 2] >> (8 * (q & 3)));
+        const uint32_t w0 = ld_u32_unaligned(s + k);
+        uint32_t w1 = 0, w2 = 0, w3 = 0;
+        if (r > 4) w1 = ld_u32_unaligned(s + k + 4);
+        if (r > 8) w2 = ld_u32_unaligned(s + k + 8);
+        if (r > 12) w3 = ld_u32_unaligned(s + k + 12);
+        uint32_t q = 0;
+        for (; q + 4 <= r; q += 4) {
+            const uint32_t w = q == 0 ? w0 : q == 4 ? w1 : w2;
+            d[k + q] = (uint8_t)w; d[k + q + 1] = (uint8_t)(w >> 8); d[k + q + 2] = (uint8_t)(w >> 16); d[k + q + 3] = (uint8_t)(w >> 24);
+        }
+        uint32_t w = q == 0 ? w0 : q == 4 ? w1 : q == 8 ? w2 : w3;
+        for (; q < r; q++) { d[k + q] = (uint8_t)w; w >>= 8; }
     }
 }
 
@@ -646,16 +772,24 @@ template <int T> __device__ __forceinline__ void zx_flush(uint8_t* dst, const ui
 //   far             HBM image of the output, position 0 at far[0] (nullptr: nothing before the window may be referenced)
 //   per_block       true: the window restarts at every block and is flushed to `far` after it (whole frames)
 //                   false: one window for all blocks, the caller flushes (regions)
-template <int T> __device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, const uint32_t* bo, const ZdBlkMeta* meta,
+//   PJ / pj         false: matches of a step resolve by exact dependency tracking (done bits, see above);
+//                   true: by POINTER JUMPING over the step's bytes.  pj[r] (r relative to the step's first byte; identity on entry
+//                   and on exit) names the byte that byte r is a copy of; bytes copied from before the step, and literals, are
+//                   roots.  Every thread then replaces pj[r] by pj[pj[r]] for its bytes until all of them point at roots — a
+//                   chain of d dependent copies (text matched against its nearest earlier occurrence makes d ~ 50..100 per
+//                   1024 sequences) resolves in log2 d sweeps with one barrier each, not in d hand-overs — and fetches the
+//                   bytes.  A step is cut so that it spans at most 32 * T bytes (32 bytes per thread, one mask word).
+template <int T, bool PJ = false>
+__device__ __forceinline__ uint32_t zx_execute_blocks(const uint8_t* frame, const uint32_t* bo, const ZdBlkMeta* meta,
                                                       uint32_t b_first, uint32_t b_last, uint8_t* win, uint32_t win_cap,
                                                       uint8_t* far, bool per_block, uint32_t out_cap,
                                                       const uint8_t* lit_arena, const uint64_t* seq_arena, uint32_t frame_len,
-                                                      ZxShared<T>* sh, uint32_t tid, bool no_carried_reps) {
+                                                      ZxShared<T>* sh, uint32_t tid, bool no_carried_reps, uint16_t* pj = nullptr) {
     const uint32_t lane = tid & 31, w = tid >> 5;
     uint32_t op = 0;
     uint32_t win_pos0 = 0;                               // frame position of win[0]
     if (tid == 0) { sh->rep[0] = 1; sh->rep[1] = 4; sh->rep[2] = 8; sh->err = 0; }
-    __syncthreads();
+    zx_barrier<T>();
     for (uint32_t b = b_first; b < b_last; b++) {
         const uint32_t pos = bo[b];
         const uint32_t h = frame[pos] | (frame[pos + 1] << 8) | ((uint32_t)frame[pos + 2] << 16);
@@ -664,17 +798,17 @@ template <int T> __device__ __forceinline__ uint32_t zx_execute_blocks(const uin
         const uint32_t room = min(min((uint32_t)zf::BLOCK_MAX, out_cap - op), win_cap - (op - win_pos0));
         uint8_t* wout = win - win_pos0;                  // wout[position] for positions inside the window
         if (type == 0 || type == 1) {                    // Raw_Block / RLE_Block
-            if (bsz > room || pos + 3 + (type == 0 ? bsz : 1) > frame_len) { if (tid == 0) sh->err = -1; __syncthreads(); return op; }
+            if (bsz > room || pos + 3 + (type == 0 ? bsz : 1) > frame_len) { if (tid == 0) sh->err = -1; zx_barrier<T>(); return op; }
             const uint8_t v = frame[pos + 3];
             if (type == 0) { for (uint32_t k = tid; k < bsz; k += T) wout[op + k] = frame[pos + 3 + k]; }
             else { for (uint32_t k = tid; k < bsz; k += T) wout[op + k] = v; }
-            __syncthreads();
-            if (per_block) { zx_flush<T>(far + op, win, bsz, tid); __syncthreads(); }
+            zx_barrier<T>();
+            if (per_block) { zx_flush<T>(far + op, win, bsz, tid); zx_barrier<T>(); }
             op += bsz;
             continue;
         }
         const ZdBlkMeta m = meta[b];
-        if (m.status != 1) { if (tid == 0) sh->err = m.status == 3 ? 3 : -1; __syncthreads(); return op; }
+        if (m.status != 1) { if (tid == 0) sh->err = m.status == 3 ? 3 : -1; zx_barrier<T>(); return op; }
         const uint8_t* blk = frame + pos + 3;
         const uint8_t* lit = nullptr;
         uint32_t rle_lit = 0x100;
@@ -686,9 +820,10 @@ template <int T> __device__ __forceinline__ uint32_t zx_execute_blocks(const uin
         const uint32_t R0 = sh->rep[0], R1 = sh->rep[1], R2 = sh->rep[2];     // repeat offsets at the start of the block
         const uint32_t blk_op0 = op;
         uint32_t lp = 0;
-        for (uint32_t base = 0; base < N; base += T) {
+        uint32_t n_take = T;                                  // sequences a step consumed (PJ: a step may be cut short)
+        for (uint32_t base = 0; base < N; base += n_take) {
             const uint32_t i = base + tid;
-            const bool mine = i < N;
+            bool mine = i < N;
             uint32_t ll = 0, ml = 0, off = 1;
             bool bad = false;
             if (mine) {
@@ -703,7 +838,40 @@ template <int T> __device__ __forceinline__ uint32_t zx_execute_blocks(const uin
                 if (off == 0) bad = true;
             }
             uint64_t tot;
-            const uint64_t inc = zx_block_scan<T>(((uint64_t)(ll + ml) << 32) | ll, tid, sh, &tot);
+            uint64_t inc = zx_block_scan<T>(((uint64_t)(ll + ml) << 32) | ll, tid, sh, &tot);
+            n_take = T;
+            if (PJ && (uint32_t)(tot >> 32) > 32u * T) {                  // cut the step after the last sequence that ends inside the span
+                const uint32_t fit = zx_barrier_count<T>(mine && (uint32_t)(inc >> 32) <= 32u * T);
+                if (fit == 0) {
+                    // one sequence larger than the span: literal run and match by the whole CTA, then on with the next sequence
+                    if (tid == 0) { sh->ostart[0] = ll; sh->mlen[0] = ml; sh->moff[0] = off; sh->dbits[0] = bad ? 1u : 0u; }
+                    zx_barrier<T>();
+                    const uint32_t gl = sh->ostart[0], gm = sh->mlen[0], go = sh->moff[0];
+                    const bool gbad = sh->dbits[0] != 0 || lp + gl > regen || (uint64_t)(op - blk_op0) + gl + gm > room ||
+                                      go > op + gl || (!far && go > op + gl - win_pos0);
+                    zx_barrier<T>();
+                    if (gbad) { if (tid == 0) sh->err = -1; zx_barrier<T>(); return op; }
+                    if (rle_lit < 0x100) { for (uint32_t k = tid; k < gl; k += T) wout[op + k] = (uint8_t)rle_lit; }
+                    else { for (uint32_t k = tid; k < gl; k += T) wout[op + k] = lit[lp + k]; }
+                    zx_barrier<T>();
+                    const uint32_t gs = op + gl;                          // match start
+                    if (go < T) {                                         // periodic source: the go bytes before the match, all written
+                        for (uint32_t k = tid; k < gm; k += T) { const uint32_t q = gs - go + k % go; wout[gs + k] = q < win_pos0 ? far[q] : wout[q]; }
+                    } else {
+                        for (uint32_t k0 = 0; k0 < gm; k0 += T) {         // T <= go bytes per round never read what the round writes
+                            const uint32_t k = k0 + tid;
+                            if (k < gm) { const uint32_t q = gs - go + k; wout[gs + k] = q < win_pos0 ? far[q] : wout[q]; }
+                            zx_barrier<T>();
+                        }
+                    }
+                    zx_barrier<T>();
+                    op += gl + gm; lp += gl; n_take = 1;
+                    continue;
+                }
+                n_take = fit;
+                if (tid >= fit) { mine = false; ll = 0; ml = 0; off = 1; bad = false; }
+                inc = zx_block_scan<T>(((uint64_t)(ll + ml) << 32) | ll, tid, sh, &tot);
+            }
             const uint32_t tot_o = (uint32_t)(tot >> 32), tot_l = (uint32_t)tot;
             const uint32_t o_start = op + (uint32_t)(inc >> 32) - ll - ml, l_start = lp + (uint32_t)inc - ll, m_start = o_start + ll;
             if (mine && (off > m_start || (!far && off > m_start - win_pos0))) bad = true;
@@ -712,10 +880,10 @@ template <int T> __device__ __forceinline__ uint32_t zx_execute_blocks(const uin
             const uint32_t preset = __ballot_sync(TS_FULL, !mine || ml == 0);         // nothing to wait for on these
             if (lane == 0) sh->dbits[w] = preset;
             if (tid == 0) sh->ostart[T] = op + tot_o;
-            const bool any_bad = __syncthreads_or(bad) != 0;
+            const bool any_bad = zx_barrier_or<T>(bad);
             if (any_bad || lp + tot_l > regen || (uint64_t)(op - blk_op0) + tot_o > room) {
                 if (tid == 0) sh->err = -1;
-                __syncthreads();
+                zx_barrier<T>();
                 return op;
             }
             // ---- literal runs: short ones by their own thread, long ones by the warp
@@ -733,108 +901,164 @@ template <int T> __device__ __forceinline__ uint32_t zx_execute_blocks(const uin
                     else { for (uint32_t k = 32 + lane; k < fn; k += 32) wout[fo + k] = lit[fl + k]; }
                 }
             }
-            __syncthreads();                                              // literals, ostart, mlen, moff, dbits visible to everyone
-            // ---- producers of this match inside the step: sequences [ja, jb] cover the part of its source other sequences write.
-            // Source forwarding first: text matched against its nearest earlier occurrence makes chains of dozens of matches
-            // inside one step, each copying what the previous one wrote.  When a source lies entirely inside ONE earlier match
-            // of the step, the bytes are, by the definition of an LZ copy, the bytes that match itself copies — so this match
-            // can read THEM instead (offset += that match's offset) and no longer depends on it.  A few hops shorten the
-            // chains to what really is a partial overlap.
-            uint32_t s_lo = m_start - off;                                // first source byte
-            uint32_t s_hi = min(s_lo + ml, m_start);                      // one past the last source byte written by someone else
-            uint32_t ja = 0, jb = 0;
-            bool inside = false;                                          // does the source reach into this step's output?
-            if (mine && ml) {
-                uint32_t top = tid;                                       // producers are searched below this index
-                for (uint32_t hop = 0; ; hop++) {
-                    inside = false;
-                    if (s_hi <= op) break;                                // everything it reads was complete before the step
-                    inside = true;
-                    uint32_t lo = 0, hi = top;                            // ja: last j <= top with ostart[j] <= x
-                    const uint32_t x = max(s_lo, op);
-                    while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] <= x) lo = mid; else hi = mid - 1; }
-                    ja = lo;
-                    const uint32_t pend_ = sh->ostart[ja + 1];            // end of sequence ja's output = end of its match
-                    if (ja < tid && s_hi <= pend_ && s_lo >= op) {        // the whole source lies in ONE earlier sequence of the step
-                        jb = ja;
-                        const uint32_t pst = pend_ - sh->mlen[ja];        // its match bytes are [pst, pend_)
-                        if (s_hi <= pst) { inside = false; break; }       // only its literals: written already
-                        if (s_lo >= pst && off >= ml && hop < 12) {       // inside its match: read what IT reads
-                            const uint32_t po = sh->moff[ja];
-                            off += po; s_lo -= po; s_hi -= po;
-                            top = ja;
-                            continue;
+            zx_barrier<T>();                                              // literals, ostart, mlen, moff, dbits visible to everyone
+            if (PJ) {
+                // ---- matches by pointer jumping
+                const uint32_t s_lo = m_start - off;
+                const uint32_t s_hi = min(s_lo + ml, m_start);            // one past the last source byte somebody else wrote
+                const bool has = mine && ml != 0;
+                const bool inside = has && s_hi > op;                     // reads bytes of this step
+                uint8_t* d = wout + m_start;
+                if (has && !inside && ml <= 64) {                         // complete before the step: copy now, these bytes are roots
+                    if (s_hi <= win_pos0) zx_copy_from_hbm(d, far + s_lo, ml);
+                    else if (s_lo < win_pos0) { for (uint32_t k = 0; k < ml; k++) { const uint32_t q = s_lo + k; d[k] = q < win_pos0 ? far[q] : wout[q]; } }
+                    else { const uint8_t* ms = d - off; for (uint32_t k = 0; k < ml; k++) d[k] = ms[k]; }
+                }
+                if (inside && ml <= 64) {
+                    for (uint32_t k = 0; k < ml; k++) {
+                        const uint32_t q = m_start + k, sq_ = q - off;
+                        if (sq_ < op) d[k] = sq_ < win_pos0 ? far[sq_] : wout[sq_];
+                        else pj[q - op] = (uint16_t)(sq_ - op);
+                    }
+                }
+                uint32_t big = __ballot_sync(TS_FULL, has && ml > 64);
+                while (big) {                                             // long matches: 32 lanes per match
+                    const uint32_t f = (uint32_t)__ffs((int)big) - 1;
+                    big &= big - 1;
+                    const uint32_t fm = __shfl_sync(TS_FULL, m_start, f), fl = __shfl_sync(TS_FULL, ml, f), fo = __shfl_sync(TS_FULL, off, f);
+                    for (uint32_t k = lane; k < fl; k += 32) {
+                        const uint32_t q = fm + k;
+                        const uint32_t sq_ = q - fo;
+                        if (sq_ >= op) pj[q - op] = (uint16_t)(sq_ - op);  // (includes every byte of an overlapping match past its first period)
+                        else wout[q] = sq_ < win_pos0 ? far[sq_] : wout[sq_];
+                    }
+                }
+                zx_barrier<T>();                                          // pointers and roots are in place
+                uint32_t nonroot = 0;
+                for (uint32_t j = 0; j * T + tid < tot_o; j++) { const uint32_t r = j * T + tid; if (pj[r] != r) nonroot |= 1u << j; }
+                uint32_t pend = nonroot;
+                while (true) {
+                    bool changed = false;
+                    uint32_t m = pend;
+                    while (m) {
+                        const uint32_t j = (uint32_t)__ffs((int)m) - 1;
+                        m &= m - 1;
+                        const uint32_t r = j * T + tid;
+                        const uint32_t s1 = *(volatile uint16_t*)&pj[r];
+                        const uint32_t s2 = *(volatile uint16_t*)&pj[s1];
+                        if (s2 != s1) { *(volatile uint16_t*)&pj[r] = (uint16_t)s2; changed = true; }
+                        else pend &= ~(1u << j);                          // points at a root
+                    }
+                    if (!zx_barrier_or<T>(changed)) break;
+                }
+                for (uint32_t m = nonroot; m; m &= m - 1) {
+                    const uint32_t r = ((uint32_t)__ffs((int)m) - 1) * T + tid;
+                    wout[op + r] = wout[op + pj[r]];                      // roots are final and nobody writes them here
+                    pj[r] = (uint16_t)r;
+                }
+            } else {
+                // ---- producers of this match inside the step: sequences [ja, jb] cover the part of its source other sequences write.
+                // Source forwarding first: text matched against its nearest earlier occurrence makes chains of dozens of matches
+                // inside one step, each copying what the previous one wrote.  When a source lies entirely inside ONE earlier match
+                // of the step, the bytes are, by the definition of an LZ copy, the bytes that match itself copies — so this match
+                // can read THEM instead (offset += that match's offset) and no longer depends on it.  A few hops shorten the
+                // chains to what really is a partial overlap.
+                uint32_t s_lo = m_start - off;                                // first source byte
+                uint32_t s_hi = min(s_lo + ml, m_start);                      // one past the last source byte written by someone else
+                uint32_t ja = 0, jb = 0;
+                bool inside = false;                                          // does the source reach into this step's output?
+                if (mine && ml) {
+                    uint32_t top = tid;                                       // producers are searched below this index
+                    for (uint32_t hop = 0; ; hop++) {
+                        inside = false;
+                        if (s_hi <= op) break;                                // everything it reads was complete before the step
+                        inside = true;
+                        uint32_t lo = 0, hi = top;                            // ja: last j <= top with ostart[j] <= x
+                        const uint32_t x = max(s_lo, op);
+                        while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] <= x) lo = mid; else hi = mid - 1; }
+                        ja = lo;
+                        const uint32_t pend_ = sh->ostart[ja + 1];            // end of sequence ja's output = end of its match
+                        if (ja < tid && s_hi <= pend_ && s_lo >= op) {        // the whole source lies in ONE earlier sequence of the step
+                            jb = ja;
+                            const uint32_t pst = pend_ - sh->mlen[ja];        // its match bytes are [pst, pend_)
+                            if (s_hi <= pst) { inside = false; break; }       // only its literals: written already
+                            if (s_lo >= pst && off >= ml && hop < 12) {       // inside its match: read what IT reads
+                                const uint32_t po = sh->moff[ja];
+                                off += po; s_lo -= po; s_hi -= po;
+                                top = ja;
+                                continue;
+                            }
+                            break;
                         }
+                        lo = ja; hi = tid;                                    // jb: last j <= tid with ostart[j] < s_hi
+                        while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] < s_hi) lo = mid; else hi = mid - 1; }
+                        jb = lo;
+                        if (jb == tid) { if (tid == 0 || ja == tid) inside = false; else jb = tid - 1; }   // own literals precede the match: never a producer
                         break;
                     }
-                    lo = ja; hi = tid;                                    // jb: last j <= tid with ostart[j] < s_hi
-                    while (hi - lo > 0) { const uint32_t mid = (lo + hi + 1) >> 1; if (sh->ostart[mid] < s_hi) lo = mid; else hi = mid - 1; }
-                    jb = lo;
-                    if (jb == tid) { if (tid == 0 || ja == tid) inside = false; else jb = tid - 1; }   // own literals precede the match: never a producer
-                    break;
                 }
-            }
-            // ---- matches: every warp runs its own loop; a lane copies once the done bits of its producers are set
-            {
-                bool done = !mine || ml == 0;
-                const bool from_far = s_hi <= win_pos0 && ml != 0;        // whole source before the window: flushed long ago
-                const bool straddle = !from_far && s_lo < win_pos0;       // (only with off >= ml, else s_hi would be m_start)
-                uint8_t* d = wout + m_start;
-                uint32_t pend = __ballot_sync(TS_FULL, !done);
-                while (pend) {
-                    bool ready = false;
-                    if (!done) ready = !inside || zx_all_done(sh->dbits, ja, jb);
-                    if (ready) __threadfence_block();                      // acquire: the producers' bytes are visible
-                    if (ready && ml <= 64) {
-                        if (from_far) zx_copy_from_hbm(d, far + s_lo, ml);
-                        else if (straddle) { for (uint32_t k = 0; k < ml; k++) { const uint32_t q = s_lo + k; d[k] = q < win_pos0 ? far[q] : wout[q]; } }
-                        else {
-                            const uint8_t* ms = d - off;
-                            uint32_t k = 0;
-                            if (off >= 4) {
-                                for (; k + 4 <= ml; k += 4) {
-                                    const uint8_t b0 = ms[k], b1 = ms[k + 1], b2 = ms[k + 2], b3 = ms[k + 3];
-                                    d[k] = b0; d[k + 1] = b1; d[k + 2] = b2; d[k + 3] = b3;
+                // ---- matches: every warp runs its own loop; a lane copies once the done bits of its producers are set
+                {
+                    bool done = !mine || ml == 0;
+                    const bool from_far = s_hi <= win_pos0 && ml != 0;        // whole source before the window: flushed long ago
+                    const bool straddle = !from_far && s_lo < win_pos0;       // (only with off >= ml, else s_hi would be m_start)
+                    uint8_t* d = wout + m_start;
+                    uint32_t pend = __ballot_sync(TS_FULL, !done);
+                    while (pend) {
+                        bool ready = false;
+                        if (!done) ready = !inside || zx_all_done(sh->dbits, ja, jb);
+                        if (ready) __threadfence_block();                      // acquire: the producers' bytes are visible
+                        if (ready && ml <= 64) {
+                            if (from_far) zx_copy_from_hbm(d, far + s_lo, ml);
+                            else if (straddle) { for (uint32_t k = 0; k < ml; k++) { const uint32_t q = s_lo + k; d[k] = q < win_pos0 ? far[q] : wout[q]; } }
+                            else {
+                                const uint8_t* ms = d - off;
+                                uint32_t k = 0;
+                                if (off >= 4) {
+                                    for (; k + 4 <= ml; k += 4) {
+                                        const uint8_t b0 = ms[k], b1 = ms[k + 1], b2 = ms[k + 2], b3 = ms[k + 3];
+                                        d[k] = b0; d[k + 1] = b1; d[k + 2] = b2; d[k + 3] = b3;
+                                    }
                                 }
+                                for (; k < ml; k++) d[k] = ms[k];             // byte-serial: overlap (off < ml) is fine
                             }
-                            for (; k < ml; k++) d[k] = ms[k];             // byte-serial: overlap (off < ml) is fine
                         }
-                    }
-                    uint32_t big = __ballot_sync(TS_FULL, ready && ml > 64);
-                    while (big) {                                         // long matches: 32 lanes per match
-                        const uint32_t f = (uint32_t)__ffs((int)big) - 1;
-                        big &= big - 1;
-                        const uint32_t fm = __shfl_sync(TS_FULL, m_start, f), fl = __shfl_sync(TS_FULL, ml, f), fo = __shfl_sync(TS_FULL, off, f);
-                        uint8_t* dd = wout + fm;
-                        const uint32_t fs = fm - fo;                      // source position
-                        if (fo >= 32) {
-                            for (uint32_t k0 = 0; k0 < fl; k0 += 32) {
-                                const uint32_t k = k0 + lane;
-                                if (k < fl) { const uint32_t q = fs + k; dd[k] = q < win_pos0 ? far[q] : wout[q]; }
-                                if (fo < fl) __syncwarp();               // later strides may read what this one wrote
+                        uint32_t big = __ballot_sync(TS_FULL, ready && ml > 64);
+                        while (big) {                                         // long matches: 32 lanes per match
+                            const uint32_t f = (uint32_t)__ffs((int)big) - 1;
+                            big &= big - 1;
+                            const uint32_t fm = __shfl_sync(TS_FULL, m_start, f), fl = __shfl_sync(TS_FULL, ml, f), fo = __shfl_sync(TS_FULL, off, f);
+                            uint8_t* dd = wout + fm;
+                            const uint32_t fs = fm - fo;                      // source position
+                            if (fo >= 32) {
+                                for (uint32_t k0 = 0; k0 < fl; k0 += 32) {
+                                    const uint32_t k = k0 + lane;
+                                    if (k < fl) { const uint32_t q = fs + k; dd[k] = q < win_pos0 ? far[q] : wout[q]; }
+                                    if (fo < fl) __syncwarp();               // later strides may read what this one wrote
+                                }
+                            } else {
+                                // periodic source: the fo bytes before the destination, all of them already written
+                                for (uint32_t k = lane; k < fl; k += 32) { const uint32_t q = fs + k % fo; dd[k] = q < win_pos0 ? far[q] : wout[q]; }
                             }
-                        } else {
-                            // periodic source: the fo bytes before the destination, all of them already written
-                            for (uint32_t k = lane; k < fl; k += 32) { const uint32_t q = fs + k % fo; dd[k] = q < win_pos0 ? far[q] : wout[q]; }
                         }
-                    }
-                    __syncwarp();                                         // the warp's copies of this round are ordered before ...
-                    if (ready) done = true;
-                    const uint32_t now = __ballot_sync(TS_FULL, !done);
-                    if (now != pend) {                                    // ... the release of their done bits
-                        if (lane == 0) { __threadfence_block(); *(volatile uint32_t*)&sh->dbits[w] = ~now; }
-                        pend = now;
+                        __syncwarp();                                         // the warp's copies of this round are ordered before ...
+                        if (ready) done = true;
+                        const uint32_t now = __ballot_sync(TS_FULL, !done);
+                        if (now != pend) {                                    // ... the release of their done bits
+                            if (lane == 0) { __threadfence_block(); *(volatile uint32_t*)&sh->dbits[w] = ~now; }
+                            pend = now;
+                        }
                     }
                 }
             }
-            __syncthreads();                                              // the step is complete
+            zx_barrier<T>();                                              // the step is complete
             op += tot_o; lp += tot_l;
         }
         // trailing literals of the block
         {
             if (lp > regen || (uint64_t)(op - blk_op0) + (regen - lp) > room) {
                 if (tid == 0) sh->err = -1;
-                __syncthreads();
+                zx_barrier<T>();
                 return op;
             }
             const uint32_t ll = regen - lp;
@@ -842,7 +1066,7 @@ template <int T> __device__ __forceinline__ uint32_t zx_execute_blocks(const uin
             else { for (uint32_t k = tid; k < ll; k += T) wout[op + k] = lit[lp + k]; }
             op += ll;
         }
-        __syncthreads();
+        zx_barrier<T>();
         if (per_block) { zx_flush<T>(far + blk_op0, win, op - blk_op0, tid); }
         if (tid == 0) {                                                   // repeat offsets after the block
             uint32_t nr[3];
@@ -856,7 +1080,7 @@ template <int T> __device__ __forceinline__ uint32_t zx_execute_blocks(const uin
             }
             sh->rep[0] = nr[0]; sh->rep[1] = nr[1]; sh->rep[2] = nr[2];
         }
-        __syncthreads();                                                  // (also: the flushed bytes are visible before the next block reads `far`)
+        zx_barrier<T>();                                                  // (also: the flushed bytes are visible before the next block reads `far`)
         if (sh->err) return op;
     }
     return op;
@@ -895,7 +1119,7 @@ __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_consta
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t n = A.in_len[chunk];
     uint64_t fcs = 0;
-    info[0] = 0; info[1] = 0; info[2] = 0; info[3] = 0; info[4] = 0; info[5] = 0; info[6] = 0; info[7] = 0;
+    for (int k = 0; k < ZD_INFO; k++) info[k] = 0;
     if (A.status[chunk] != 0) { A.out_len[chunk] = 0; info[3] = 2; return; }      // e.g. tag mismatch upstream: nothing to decode
     if (n > A.in_cap) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; info[3] = 2; return; }
     const uint32_t hs = zd_frame_header(p, n, &fcs);
@@ -926,6 +1150,21 @@ __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_consta
     // the frame to the frame-level executor.
     info[2] = (last && nblk == want && nblk <= A.blocks_per_chunk) ? 1 : 0;
     info[5] = (last && nblk <= A.blocks_per_chunk) ? 1 : 0;                       // entropy stage per block + CTA executors (else: serial kernel)
+    // Speed-mode frames of this library have self-contained blocks (own tables, no match leaves the block): guessed from the
+    // second block — it inherits nothing — and verified by the kernels that rely on it (a wrong guess costs time, never bytes).
+    if (info[2]) {
+        uint32_t indep = 1;
+        if (nblk >= 2) {
+            const uint32_t p1 = bo[1];
+            const uint32_t h1 = p[p1] | (p[p1 + 1] << 8) | ((uint32_t)p[p1 + 2] << 16);
+            if (((h1 >> 1) & 3) == 2 && (h1 >> 3) >= 2) {
+                const uint32_t t1 = p[p1 + 3] & 3;
+                if (t1 == 3) indep = 0;                                           // Treeless literals
+                // (Repeat_Mode tables behind Raw / RLE literals are found by the entropy stage itself)
+            }
+        }
+        info[8] = indep;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ kernel 4: serial fallback
@@ -1001,6 +1240,7 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_par_entropy_kernel(const
     const uint32_t chunk = blockIdx.y, b = blockIdx.x * ZD_WPB + warp;
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
     if (!info[5] || b >= info[1]) return;
+    if (info[8] && !(info[3] & 4)) return;                                // the independent-block entropy stage did this frame
     ZdWarpCtx* cx = (ZdWarpCtx*)(smem + (size_t)warp * sizeof(ZdWarpCtx));
     ZdBlkMeta* meta = (ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk + b;
     const uint8_t* p = A.in_base + A.in_off[chunk];
@@ -1073,6 +1313,7 @@ __global__ void __launch_bounds__(ZX_T, 2) zstd_dec_regions_kernel(const __grid_
     const uint32_t chunk = blockIdx.y, region = blockIdx.x;
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
     if (!info[5] || !info[2] || (info[3] & 2)) return;
+    if (info[8] && !(info[3] & 4)) return;                                // executed block by block (or handed to the frame executor)
     const uint32_t fcs = info[0], nblk = info[1];
     if ((uint64_t)region * ZR >= fcs) return;
     const uint32_t want = min(ZR, fcs - region * ZR);
@@ -1096,7 +1337,7 @@ __global__ void __launch_bounds__(ZX_T, 2) zstd_dec_regions_kernel(const __grid_
 
 // 3c: one CTA per frame — execution stage straight into the frame's output in HBM (what libzstd-written frames need: their
 // matches reach back up to the whole window).
-constexpr uint32_t ZX_FRAME_SMEM = zf::BLOCK_MAX;      // the window is the current block
+constexpr uint32_t ZX_FRAME_SMEM = zf::BLOCK_MAX + 32 * ZX_TF * 2;      // the window is the current block; + the pointer array of a step
 __global__ void __launch_bounds__(ZX_TF, 1) zstd_dec_par_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
     TS_DYN_SMEM(wbuf);
     __shared__ ZxShared<ZX_TF> sh;
@@ -1104,19 +1345,446 @@ __global__ void __launch_bounds__(ZX_TF, 1) zstd_dec_par_execute_kernel(const __
     const uint32_t chunk = blockIdx.x;
     uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
     if (!info[5] || (info[3] & 2)) return;
-    if (info[2] && !(info[3] & 1)) return;                                // the region executors finished this frame
+    if (info[2] && !(info[3] & 1)) return;                                // the region / block executors finished this frame
     if (tid == 0) atomicAdd(&A.stats[info[2] ? 1 : 2], 1ull);
     const uint32_t fcs = info[0], nblk = info[1];
     const uint8_t* p = A.in_base + A.in_off[chunk];
     const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
     const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
-    const uint32_t made = zx_execute_blocks<ZX_TF>(p, bo, meta, 0, nblk, wbuf, ZX_FRAME_SMEM, A.out_base + A.out_off[chunk], true, fcs,
+    uint16_t* pj = (uint16_t*)(wbuf + zf::BLOCK_MAX);
+    for (uint32_t r = tid; r < 32u * ZX_TF; r += ZX_TF) pj[r] = (uint16_t)r;
+    __syncthreads();
+    const uint32_t made = zx_execute_blocks<ZX_TF, true>(p, bo, meta, 0, nblk, wbuf, zf::BLOCK_MAX, A.out_base + A.out_off[chunk], true, fcs,
                                             A.par_lits + (size_t)chunk * A.par_lit_cap, A.par_seqs + (size_t)chunk * A.par_seq_cap,
-                                            A.in_len[chunk], &sh, tid, false);
+                                            A.in_len[chunk], &sh, tid, false, pj);
     if (tid == 0) {
         if (sh.err == 3) info[5] = 0;                                     // a field too wide for the sequence word: the serial kernel decodes this frame
         else if (sh.err || made != fcs) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------ kernels 2a / 2b / 2c: independent blocks
+// Frames of this library's SPEED mode: every 8 KiB block carries its own tables and no match leaves it.  The serial parts of a
+// block's entropy stage (header parsing, table descriptions, the FSE state chain: one lane, ~55 instructions per sequence)
+// then no longer need a warp each — one warp takes EIGHT blocks, four lanes per block:
+//   * lane 4g (the leader of block g) parses headers and walks block g's state chain, all eight chains at once;
+//   * lanes 4g..4g+3 decode the four Huffman streams of block g, 32 streams at once;
+//   * table fills and the per-sequence value extraction stay warp-wide, block after block.
+// Such a warp is latency-bound, so what matters is how many fit on an SM, i.e. shared memory per block: literals and
+// sequences are two kernels with lean contexts (literals: the 4 KiB Huffman table, 5 warps per SM; sequences: three tables of
+// at most 2^7 cells — what the speed-mode writer emits — 9 warps = 72 chains per SM), and no serial loop waits for HBM:
+// the bytes a stream is about to consume are staged in shared memory, 64 / 128 at a time, by loads issued together.
+// Literals and sequences go to FIXED slots of the frame's arenas (block b: literals at b * ZB, sequences at b * ZB / 3), in
+// the format of the general entropy stage, so every executor can consume them.  Anything a self-contained speed-mode block
+// does not contain (Treeless literals, Repeat_Mode, a repeat-offset code, larger tables, more than ZB bytes) makes these
+// kernels REFUSE the frame: the general entropy stage then redoes it — they never declare a frame corrupt themselves.
+constexpr int ZDI_G = 8;                                  // blocks per warp
+constexpr uint32_t ZDI_SEQ_SLOT = ZB / 3;                 // most sequences ZB bytes of output can come from (minimum match 3)
+
+struct ZdLitCtx {                                         // literal phase of one block
+    uint16_t huf[1 << zf::HUF_MAX_LOG];
+    uint16_t hstart[256];
+    uint8_t weights[256];
+    zf::FseDEntry wt[1 << zf::HUFW_MAX_LOG];
+    uint32_t rank_start[16];
+    uint8_t symbol_of[1 << zf::HUFW_MAX_LOG];
+    uint16_t next[16];
+    int16_t norm[16];
+    uint32_t huf_nw, huf_log, huf_valid;
+    int32_t err;
+    static constexpr int kTabLogCap = 0;
+};
+struct ZdSeqCtx {                                         // sequence phase of one block
+    static constexpr int kTabLogCap = 7;
+    zf::FseDEntry ll[1 << kTabLogCap], ml[1 << kTabLogCap], of[1 << kTabLogCap];
+    int16_t norm3[3][64];
+    uint32_t cum[65];
+    uint8_t symbol_of[1 << kTabLogCap];
+    uint16_t next[64];
+    uint32_t s_ll[32], s_ml[32];
+    uint32_t stage[36];                                   // 128 bytes of the bit stream below the cursor (+ padding for the funnel shift)
+    uint32_t pend_log[3], pend_nsym[3];
+    uint32_t ll_log, ml_log, of_log, ll_valid, ml_valid, of_valid;
+    int32_t err;
+};
+constexpr uint32_t ZDL_STAGE_WORDS = 17;                  // per lane: 64 bytes of its Huffman stream (+ one word for the funnel shift)
+constexpr uint32_t ZDL_SMEM_BYTES = ZDI_G * sizeof(ZdLitCtx) + 32 * ZDL_STAGE_WORDS * 4;
+constexpr uint32_t ZDS_SMEM_BYTES = ZDI_G * sizeof(ZdSeqCtx);
+static_assert(5 * (ZDL_SMEM_BYTES + 1024) <= 228 * 1024, "five literal warps per SM");
+static_assert(9 * (ZDS_SMEM_BYTES + 1024) <= 228 * 1024, "nine sequence warps per SM");
+
+// Table fill for the lean literal kernel: symbols with few cells by a lane each, symbols with many cells by the warp.
+__device__ __forceinline__ void zd_fill_huf_lean(ZdLitCtx* cx, uint32_t lane) {
+    const uint32_t nw = cx->huf_nw, max_bits = cx->huf_log;
+    for (uint32_t s0 = 0; s0 < nw; s0 += 32) {
+        const uint32_t sy = s0 + lane;
+        const uint32_t w = sy < nw ? cx->weights[sy] : 0u;
+        const uint32_t len = w ? 1u << (w - 1) : 0u, at = w ? cx->hstart[sy] : 0u;
+        const uint16_t e = (uint16_t)(sy | ((max_bits + 1 - w) << 8));
+        if (len && len < 16) for (uint32_t k = 0; k < len; k++) cx->huf[at + k] = e;
+        uint32_t big = __ballot_sync(TS_FULL, len >= 16);
+        while (big) {
+            const uint32_t f = (uint32_t)__ffs((int)big) - 1;
+            big &= big - 1;
+            const uint32_t fa = __shfl_sync(TS_FULL, at, f), fl = __shfl_sync(TS_FULL, len, f), fe = __shfl_sync(TS_FULL, (uint32_t)e, f);
+            uint32_t* t2 = (uint32_t*)(cx->huf + fa);                     // fa is a multiple of fl >= 16: word aligned
+            for (uint32_t k = lane; k < fl / 2; k += 32) t2[k] = fe | (fe << 16);
+        }
+    }
+    __syncwarp();
+}
+
+// One Huffman stream by one lane, destination in global memory.  The 64 bytes below the cursor are staged in the lane's
+// column of `stg` (word j at stg[32 * j]: conflict-free) by 16 loads issued together; ten groups of four symbols (<= 440
+// bits) are decoded per staging, each leaving as one 32-bit store.  The first symbols (until the destination is aligned) and
+// the last ones (fewer than 44 bits left: peeks zero-extend past the start of the stream) take the generic reader.
+// `base` / `lim`: 4-byte aligned bounds of the frame's buffer — staging never reads outside them.
+__device__ __forceinline__ bool zd_huf_stream_staged(const uint16_t* __restrict__ huf, uint32_t log, const uint8_t* src, uint32_t size,
+                                                     uint8_t* dst, uint32_t count, uint32_t* stg, const uint8_t* base, const uint8_t* lim) {
+    ZdBack b;
+    if (!zd_back_init(b, src, size)) return false;
+    uint32_t i = 0;
+    const uint32_t head = min(count, (4u - (uint32_t)((uintptr_t)dst & 3)) & 3u);
+    for (; i < head; i++) {
+        const uint16_t e = huf[zd_back_peek(b, log)];
+        dst[i] = (uint8_t)e;
+        b.bits -= (int32_t)(e >> 8);
+    }
+    if (b.bits < 0) return false;
+    const uint32_t mask = (1u << log) - 1;
+    int32_t bits = b.bits;
+    while (i + 4 <= count && bits >= 44) {
+        const int32_t tb = (bits + 7) >> 3;
+        const uint8_t* a0 = (const uint8_t*)(((uintptr_t)(src + tb) - 60) & ~(uintptr_t)3);
+        if (a0 < base) a0 = base;
+        const int32_t sbit0 = (int32_t)(a0 - src) * 8;                   // stream bit index of stg word 0, bit 0 (may be negative)
+        _Pragma("unroll")
+        for (int j = 0; j < 16; j++) { const uint8_t* q = a0 + 4 * j; stg[32 * j] = q < lim ? *(const uint32_t*)q : 0u; }
+        for (int r = 0; r < 10 && i + 4 <= count && bits >= 44; r++) {
+            uint32_t out = 0;
+            _Pragma("unroll")
+            for (int k = 0; k < 4; k++) {
+                const uint32_t rel = (uint32_t)(bits - (int32_t)log - sbit0);
+                const uint32_t v = __funnelshift_r(stg[32 * (rel >> 5)], stg[32 * ((rel >> 5) + 1)], rel & 31) & mask;
+                const uint16_t e = huf[v];
+                out |= (uint32_t)(e & 0xff) << (8 * k);
+                bits -= (int32_t)(e >> 8);
+            }
+            *(uint32_t*)(dst + i) = out;
+            i += 4;
+        }
+    }
+    b.bits = bits; b.cbase = 0x3fffffff;
+    for (; i < count; i++) {
+        const uint16_t e = huf[zd_back_peek(b, log)];
+        dst[i] = (uint8_t)e;
+        b.bits -= (int32_t)(e >> 8);
+        if (b.bits < 0) return false;
+    }
+    return b.bits == 0;
+}
+
+// Sizes of the literals section only (no tree): where the sequences section starts.
+__device__ __forceinline__ bool zd_lit_section_size(const uint8_t* blk, uint32_t bsize, uint32_t* total) {
+    if (bsize < 2) return false;
+    const uint32_t b0 = blk[0], type = b0 & 3, sf = (b0 >> 2) & 3;
+    uint32_t hs, comp;
+    if (type < 2) {
+        uint32_t regen;
+        if ((sf & 1) == 0) { hs = 1; regen = b0 >> 3; }
+        else if (sf == 1) { hs = 2; regen = (b0 >> 4) | ((uint32_t)blk[1] << 4); }
+        else { if (bsize < 3) return false; hs = 3; regen = (b0 >> 4) | ((uint32_t)blk[1] << 4) | ((uint32_t)blk[2] << 12); }
+        comp = type == 0 ? regen : 1;
+    } else {
+        if (bsize < 5) return false;
+        const uint32_t h = blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
+        if (sf <= 1) { hs = 3; comp = (h >> 14) & 0x3ff; }
+        else if (sf == 2) { hs = 4; comp = h >> 18; }
+        else { hs = 5; comp = (h >> 22) | ((uint32_t)blk[4] << 10); }
+    }
+    if ((uint64_t)hs + comp > bsize) return false;
+    *total = hs + comp;
+    return true;
+}
+
+// Common prologue: which block this group of four lanes owns.  live: a Compressed_Block to decode; refuse: malformed framing.
+struct ZdiBlock { uint32_t b, blk_off, bsize; bool live; uint32_t refuse; };
+__device__ __forceinline__ ZdiBlock zdi_block(const ZstdDecArgs& A, uint32_t chunk, uint32_t nblk, uint32_t g) {
+    ZdiBlock r; r.b = blockIdx.x * ZDI_G + g; r.blk_off = 0; r.bsize = 0; r.live = false; r.refuse = 0;
+    if (r.b < nblk) {
+        const uint8_t* p = A.in_base + A.in_off[chunk];
+        const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
+        uint32_t pos, type, bsz;
+        const bool comp = zd_blk_hdr(p, bo, r.b, &pos, &type, &bsz);
+        if (type == 2) {
+            if (!comp || pos + 3 + bsz > A.in_len[chunk]) r.refuse = 1;
+            else { r.live = true; r.blk_off = pos + 3; r.bsize = bsz; }
+        }
+    }
+    return r;
+}
+
+// 2a: literals.
+__global__ void __launch_bounds__(32) zstd_dec_blk_literals_kernel(const __grid_constant__ ZstdDecArgs A) {
+    TS_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x, g = lane >> 2, sub = lane & 3, lead = lane & ~3u;
+    const uint32_t chunk = blockIdx.y;
+    uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
+    if (!info[5] || !info[8] || (info[3] & 6)) return;                     // (bit 4 set by another warp of this launch: nothing left to win)
+    const uint32_t nblk = info[1];
+    if (blockIdx.x * ZDI_G >= nblk) return;
+    ZdLitCtx* ctx = (ZdLitCtx*)smem;
+    ZdLitCtx* cx = ctx + g;
+    uint32_t* stg = (uint32_t*)(smem + ZDI_G * sizeof(ZdLitCtx)) + lane;
+    stg[32 * 16] = 0;
+    const uint8_t* p = A.in_base + A.in_off[chunk];
+    const uint8_t* base = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)3);
+    const uint8_t* lim = (const uint8_t*)(((uintptr_t)p + A.in_len[chunk] + 3) & ~(uintptr_t)3);
+    ZdiBlock B = zdi_block(A, chunk, nblk, g);
+    const uint8_t* blk = p + B.blk_off;
+    ZdBlkMeta* meta = (ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk + B.b;
+    uint8_t* litbuf = A.par_lits + (size_t)chunk * A.par_lit_cap + (size_t)B.b * ZB;
+    bool live = B.live;
+    uint32_t refuse = B.refuse;
+
+    // header + tree description (leaders), table fill (warp), streams (4 lanes per block)
+    uint32_t ltype = 0, lhs = 0, regen = 0, lcomp = 0, streams = 1, tree = 0;
+    if (live && sub == 0) {
+        cx->err = 0; cx->huf_valid = 0;
+        uint32_t h[6];
+        if (!zd_parse_lit_header(blk, B.bsize, ZB, ZB, true, cx, h) || cx->err) refuse = 1;
+        else { ltype = h[0]; lhs = h[1]; regen = h[2]; lcomp = h[3]; streams = h[4]; tree = h[5]; }
+    }
+    ltype = __shfl_sync(TS_FULL, ltype, lead); lhs = __shfl_sync(TS_FULL, lhs, lead); regen = __shfl_sync(TS_FULL, regen, lead);
+    lcomp = __shfl_sync(TS_FULL, lcomp, lead); streams = __shfl_sync(TS_FULL, streams, lead); tree = __shfl_sync(TS_FULL, tree, lead);
+    refuse = __shfl_sync(TS_FULL, refuse, lead);
+    live = live && !refuse;
+    for (uint32_t gg = 0; gg < ZDI_G; gg++) {
+        if (__shfl_sync(TS_FULL, (uint32_t)(live && ltype == 2), gg * 4)) zd_fill_huf_lean(ctx + gg, lane);
+    }
+    __syncwarp();
+    if (live && ltype == 2) {
+        const uint8_t* hsrc = blk + lhs + tree;
+        const uint32_t hsize = lcomp - tree;
+        bool ok = true;
+        if (streams == 1) {
+            if (sub == 0) ok = zd_huf_stream_staged(cx->huf, cx->huf_log, hsrc, hsize, litbuf, regen, stg, base, lim);
+        } else if (hsize < 10) ok = false;
+        else {
+            const uint32_t s1 = hsrc[0] | (hsrc[1] << 8), s2 = hsrc[2] | (hsrc[3] << 8), s3 = hsrc[4] | (hsrc[5] << 8);
+            if (6 + s1 + s2 + s3 > hsize) ok = false;
+            else {
+                const uint32_t s4 = hsize - 6 - s1 - s2 - s3;
+                const uint32_t per = (regen + 3) / 4;
+                const uint32_t o = sub == 0 ? 0 : sub == 1 ? s1 : sub == 2 ? s1 + s2 : s1 + s2 + s3;
+                const uint32_t sz = sub == 0 ? s1 : sub == 1 ? s2 : sub == 2 ? s3 : s4;
+                const uint32_t first = sub * per;
+                if (first > regen || (sub == 3 && 3 * per > regen)) ok = false;
+                else ok = zd_huf_stream_staged(cx->huf, cx->huf_log, hsrc + 6 + o, sz, litbuf + first,
+                                               sub < 3 ? min(per, regen - first) : regen - first, stg, base, lim);
+            }
+        }
+        if (!ok) refuse = 1;
+    }
+    {   // a group's verdict is the OR of its four lanes
+        const uint32_t bad = __ballot_sync(TS_FULL, refuse != 0);
+        refuse = (bad >> lead) & 15u ? 1u : 0u;
+    }
+    if (B.b < nblk && sub == 0) {
+        if (refuse) atomicOr(&info[3], 4u);
+        else if (live) {
+            meta->lit_kind = ltype == 0 ? 1u : ltype == 1 ? 2u : 0u;
+            meta->lit_off = ltype == 0 ? lhs : ltype == 1 ? (uint32_t)blk[lhs] : B.b * ZB;
+            meta->regen = regen;
+        }
+    }
+}
+
+// 2b: sequences.
+__global__ void __launch_bounds__(32) zstd_dec_blk_sequences_kernel(const __grid_constant__ ZstdDecArgs A) {
+    TS_DYN_SMEM(smem);
+    const uint32_t lane = threadIdx.x, g = lane >> 2, sub = lane & 3, lead = lane & ~3u;
+    const uint32_t chunk = blockIdx.y;
+    uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
+    if (!info[5] || !info[8] || (info[3] & 6)) return;
+    const uint32_t nblk = info[1];
+    if (blockIdx.x * ZDI_G >= nblk) return;
+    ZdSeqCtx* ctx = (ZdSeqCtx*)smem;
+    ZdSeqCtx* cx = ctx + g;
+    const uint8_t* p = A.in_base + A.in_off[chunk];
+    const uint8_t* base = (const uint8_t*)((uintptr_t)p & ~(uintptr_t)3);
+    const uint8_t* lim = (const uint8_t*)(((uintptr_t)p + A.in_len[chunk] + 3) & ~(uintptr_t)3);
+    ZdiBlock B = zdi_block(A, chunk, nblk, g);
+    const uint8_t* blk = p + B.blk_off;
+    ZdBlkMeta* meta = (ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk + B.b;
+    uint64_t* sq_base = A.par_seqs + (size_t)chunk * A.par_seq_cap + (size_t)blockIdx.x * ZDI_G * ZDI_SEQ_SLOT;
+    bool live = B.live;
+    uint32_t refuse = B.refuse;
+    if (B.b < nblk && !live && !refuse && sub == 0) meta->status = 1;      // Raw / RLE blocks need no entropy stage
+
+    // ---- header + table descriptions (leaders), table builds (warp)
+    uint32_t nseq = 0, bs_off = 0, pend = 0, lsec = 0;
+    if (live && sub == 0) {
+        cx->err = 0; cx->ll_valid = 0; cx->ml_valid = 0; cx->of_valid = 0;
+        uint32_t h[3];
+        if (!zd_lit_section_size(blk, B.bsize, &lsec)) refuse = 1;
+        else if (!zd_parse_seq_header(blk + lsec, B.bsize - lsec, true, cx, h) || cx->err || h[0] > ZDI_SEQ_SLOT) refuse = 1;
+        else { nseq = h[0]; bs_off = h[1]; pend = h[2]; }
+    }
+    refuse = __shfl_sync(TS_FULL, refuse, lead);
+    live = live && !refuse;
+    for (uint32_t gg = 0; gg < ZDI_G; gg++) {
+        const uint32_t pg = __shfl_sync(TS_FULL, live ? pend : 0u, gg * 4);
+        for (int k = 0; k < 3; k++) if (pg & (1u << k)) zd_build_dtable_warp(k, ctx + gg, lane);
+    }
+    __syncwarp();
+    const uint32_t bs_frame_off = __shfl_sync(TS_FULL, B.blk_off + lsec + bs_off, lead);      // the bit stream, relative to the frame
+    const uint8_t* bs = p + bs_frame_off;
+    int32_t bits = 0;                                                     // unread bits of the stream (leaders; shared per round)
+    uint32_t st_ll = 0, st_of = 0, st_ml = 0;
+    if (live && sub == 0 && nseq) {
+        ZdBack br;
+        bool ok = zd_back_init(br, bs, B.bsize - lsec - bs_off);
+        if (ok) {
+            st_ll = zd_back_read(br, cx->ll_log); st_of = zd_back_read(br, cx->of_log); st_ml = zd_back_read(br, cx->ml_log);
+            if (br.bits < 0) ok = false;
+        }
+        if (!ok) refuse = 1;
+        bits = br.bits;
+    }
+    // ---- rounds of up to 32 sequences per block: the group stages the 128 bytes below the cursor, the leaders walk their
+    // chains (a chain stops early when it would leave the staged bytes), then the warp cuts the values out, block after block
+    uint32_t s0 = 0;
+    uint32_t r0 = ZD_OFF_SYM | (1u << 27), r1 = ZD_OFF_SYM | (2u << 27), r2 = ZD_OFF_SYM | (3u << 27);   // repeat offsets after the block
+    while (true) {
+        const bool more = live && !refuse && sub == 0 && s0 < nseq;
+        const uint32_t more_mask = __ballot_sync(TS_FULL, more);
+        if (!more_mask) break;
+        // stage: bytes [a0, a0 + 128) with a0 + 128 > the byte holding the cursor
+        const int32_t gbits = __shfl_sync(TS_FULL, bits, lead);
+        const bool gmore = (more_mask >> lead) & 1u;
+        const int32_t tb = (gbits + 7) >> 3;
+        const uint8_t* a0 = (const uint8_t*)(((uintptr_t)(bs + tb) - 124) & ~(uintptr_t)3);
+        if (a0 < base) a0 = base;
+        const int32_t sbit0 = (int32_t)(a0 - bs) * 8;
+        if (gmore) {
+            _Pragma("unroll")
+            for (int j = 0; j < 8; j++) { const uint8_t* q = a0 + 4 * (sub * 8 + j); cx->stage[sub * 8 + j] = q < lim ? *(const uint32_t*)q : 0u; }
+        }
+        __syncwarp();
+        uint32_t cnt = 0;
+        if (more) {
+            const uint32_t want = min(32u, nseq - s0);
+            const uint32_t* tof = (const uint32_t*)cx->of; const uint32_t* tml = (const uint32_t*)cx->ml; const uint32_t* tll = (const uint32_t*)cx->ll;
+            const uint32_t n_upd = min(want, nseq - 1 - s0);             // sequences of this round that are followed by another one
+            bool bad = false;
+            uint32_t i = 0;
+            for (; i < n_upd; i++) {
+                const uint32_t eo = tof[st_of], em = tml[st_ml], el = tll[st_ll];
+                const uint32_t t = eo + em + el;                         // bits 0..5: state-update bits, bits 6..11: extra bits
+                const int32_t hi = bits - (int32_t)((t >> 6) & 63);
+                const int32_t lo = hi - (int32_t)(t & 63);
+                if (lo < sbit0) { if (lo < 0) bad = true; break; }       // leaves the staged bytes (or the stream: corrupt)
+                cx->s_ll[i] = st_of | (st_ml << 10) | (st_ll << 20);
+                cx->s_ml[i] = (uint32_t)(bits - sbit0);
+                const uint32_t rel = (uint32_t)(lo - sbit0);
+                uint32_t W = __funnelshift_r(cx->stage[rel >> 5], cx->stage[(rel >> 5) + 1], rel & 31);
+                const uint32_t u_of = eo & 63, u_ml = em & 63, u_ll = el & 63;
+                st_of = (eo >> 18) + (W & ((1u << u_of) - 1)); W >>= u_of;
+                st_ml = (em >> 18) + (W & ((1u << u_ml) - 1)); W >>= u_ml;
+                st_ll = (el >> 18) + (W & ((1u << u_ll) - 1));
+                bits = lo;
+            }
+            if (!bad && i == n_upd && i < want) {                        // the block's last sequence: values only
+                const uint32_t t = tof[st_of] + tml[st_ml] + tll[st_ll];
+                const int32_t hi = bits - (int32_t)((t >> 6) & 63);
+                if (hi >= sbit0 || hi < 0) {
+                    cx->s_ll[i] = st_of | (st_ml << 10) | (st_ll << 20);
+                    cx->s_ml[i] = (uint32_t)(bits - sbit0);
+                    bits = hi;
+                    if (bits != 0) bad = true;                           // the stream ends exactly with the last sequence's bits
+                    i++;
+                }
+            }
+            cnt = i;
+            if (bad) { refuse = 1; cnt = 0; }
+        }
+        __syncwarp();
+        for (uint32_t gg = 0; gg < ZDI_G; gg++) {
+            const uint32_t c = __shfl_sync(TS_FULL, cnt, gg * 4);
+            if (!c) continue;
+            const uint32_t sbase = __shfl_sync(TS_FULL, s0, gg * 4);
+            const ZdSeqCtx* cg = ctx + gg;
+            const bool mine = lane < c;
+            uint32_t ll = 0, ml = 3, ofv = 4;
+            if (mine) {
+                const uint32_t st = cg->s_ll[lane];
+                const uint32_t end = cg->s_ml[lane];                     // staged bit index just above this sequence's bits
+                const zf::FseDEntry eo = cg->of[st & 1023], em = cg->ml[(st >> 10) & 1023], el = cg->ll[st >> 20];
+                const uint32_t nbo = eo.nb_extra, nbv = (uint32_t)em.nb_extra + el.nb_extra;
+                const uint32_t ro = end - nbo, rv = ro - nbv;
+                const uint32_t xo = __funnelshift_r(cg->stage[ro >> 5], cg->stage[(ro >> 5) + 1], ro & 31) & (uint32_t)((1ull << nbo) - 1);
+                const uint32_t v = __funnelshift_r(cg->stage[rv >> 5], cg->stage[(rv >> 5) + 1], rv & 31) & (uint32_t)((1ull << nbv) - 1);
+                ofv = (1u << eo.sym) + xo;
+                ml = g_seq_tables.ml_base[em.sym] + (v >> el.nb_extra);
+                ll = g_seq_tables.ll_base[el.sym] + (v & ((1u << el.nb_extra) - 1));
+            }
+            // a repeat-offset code, or a field the sequence word cannot hold: not a block of this kind
+            const bool odd = mine && (ofv <= 3 || ofv - 3 >= ZD_OFF_SYM || ll >= (1u << 17) || ml - 3 >= (1u << 17));
+            const uint32_t any_odd = __ballot_sync(TS_FULL, odd);
+            const uint32_t of = ofv - 3;
+            if (mine && !any_odd) sq_base[(size_t)gg * ZDI_SEQ_SLOT + sbase + lane] = (uint64_t)of | ((uint64_t)ll << 30) | ((uint64_t)(ml - 3) << 47);
+            const uint32_t o1 = __shfl_sync(TS_FULL, of, c - 1), o2 = __shfl_sync(TS_FULL, of, c >= 2 ? c - 2 : 0), o3 = __shfl_sync(TS_FULL, of, c >= 3 ? c - 3 : 0);
+            if (g == gg) {
+                if (any_odd) refuse = 1;
+                const uint32_t q0 = r0, q1 = r1;
+                r2 = c >= 3 ? o3 : c == 2 ? q0 : q1;
+                r1 = c >= 2 ? o2 : q0;
+                r0 = o1;
+            }
+        }
+        s0 += cnt;
+        __syncwarp();                                    // stage / s_ll / s_ml are rewritten by the next round
+    }
+    refuse = __shfl_sync(TS_FULL, refuse, lead);
+    if (B.b < nblk && sub == 0 && (live || refuse)) {
+        if (refuse) { atomicOr(&info[3], 4u); meta->status = 2; }
+        else {
+            meta->nseq = nseq; meta->seq_off = B.b * ZDI_SEQ_SLOT;
+            meta->rep[0] = r0; meta->rep[1] = r1; meta->rep[2] = r2;
+            meta->status = 1;
+        }
+    }
+}
+
+// 2c: one WARP per block of such frames — the executor above with a "CTA" of 32: the block is assembled in 8 KiB of shared
+// memory and flushed with 128-bit stores.  A match that reaches before its block, or a block that does not regenerate exactly
+// its share, hands the frame to the frame executor (which consumes the same arenas).
+constexpr int ZXB_WPB = 4;
+constexpr uint32_t ZXB_SMEM_BYTES = ZXB_WPB * ZB;
+__global__ void __launch_bounds__(ZXB_WPB * 32, 6) zstd_dec_indep_execute_kernel(const __grid_constant__ ZstdDecArgs A) {
+    TS_DYN_SMEM(wins);
+    __shared__ ZxShared<32> shs[ZXB_WPB];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.y, b = blockIdx.x * ZXB_WPB + warp;
+    uint32_t* info = A.info + (size_t)chunk * ZD_INFO;
+    if (!info[5] || !info[8] || (info[3] & 6)) return;
+    const uint32_t fcs = info[0], nblk = info[1];
+    if (b >= nblk) return;
+    const uint32_t want = (uint64_t)b * ZB >= fcs ? 0u : min(ZB, fcs - b * ZB);
+    const uint8_t* p = A.in_base + A.in_off[chunk];
+    const uint32_t* bo = A.blk_off + (size_t)chunk * (A.blocks_per_chunk + 1);
+    const ZdBlkMeta* meta = (const ZdBlkMeta*)A.par_meta + (size_t)chunk * A.blocks_per_chunk;
+    uint8_t* win = wins + (size_t)warp * ZB;
+    ZxShared<32>* sh = &shs[warp];
+    const uint32_t made = zx_execute_blocks<32>(p, bo, meta, b, b + 1, win, ZB, nullptr, false, want,
+                                                A.par_lits + (size_t)chunk * A.par_lit_cap, A.par_seqs + (size_t)chunk * A.par_seq_cap,
+                                                A.in_len[chunk], sh, lane, true);
+    __syncwarp();
+    if (sh->err || made != want) { if (lane == 0) atomicOr(&info[3], 1u); return; }
+    if (lane == 0) atomicAdd(&A.stats[4], 1ull);
+    zx_flush<32>(A.out_base + A.out_off[chunk] + (size_t)b * ZB, win, made, lane);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -1129,8 +1797,10 @@ inline const char* zstd_dec_scratch_alloc(ZstdDecScratch& s, uint32_t chunk_cap,
     if ((e = rt::malloc_device((void**)&s.info, (size_t)max_batch * ZD_INFO * 4 + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.lits_general, (size_t)max_batch * ZD_LIT_GENERAL + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.pos_tmp, (size_t)(max_batch + 1) * 8 + 256))) return e;
-    s.par_lit_cap = (uint32_t)(((uint64_t)chunk_cap + 16ull * (s.blocks_per_chunk + 1) + 4096 + 15) & ~15ull);
-    s.par_seq_cap = chunk_cap / 3 + 64;
+    // the independent-block stage uses fixed slots: block b's literals at b * ZB (<= ZB bytes), its sequences at b * ZB / 3
+    const uint64_t zb_blocks = ((uint64_t)chunk_cap + ZB - 1) / ZB ? ((uint64_t)chunk_cap + ZB - 1) / ZB : 1;
+    s.par_lit_cap = (uint32_t)((zb_blocks * ZB + 16ull * (s.blocks_per_chunk + 1) + 4096 + 15) & ~15ull);
+    s.par_seq_cap = (uint32_t)std::max<uint64_t>(chunk_cap / 3 + 64, zb_blocks * (ZB / 3) + 64);
     if ((e = rt::malloc_device((void**)&s.par_meta, (size_t)max_batch * s.blocks_per_chunk * sizeof(ZdBlkMeta) + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.par_lits, (size_t)max_batch * s.par_lit_cap + 256))) return e;
     if ((e = rt::malloc_device((void**)&s.par_seqs, (size_t)max_batch * s.par_seq_cap * 8 + 256))) return e;
@@ -1155,6 +1825,9 @@ inline const char* zstd_kernels_configure() {
     if ((e = rt::allow_smem(zstd_dec_frames_kernel, ZD_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_par_entropy_kernel, ZD_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_regions_kernel, ZX_REGION_SMEM))) return e;
+    if ((e = rt::allow_smem(zstd_dec_blk_literals_kernel, ZDL_SMEM_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_dec_blk_sequences_kernel, ZDS_SMEM_BYTES))) return e;
+    if ((e = rt::allow_smem(zstd_dec_indep_execute_kernel, ZXB_SMEM_BYTES))) return e;
     if ((e = rt::allow_smem(zstd_dec_par_execute_kernel, ZX_FRAME_SMEM))) return e;
     return nullptr;
 }
@@ -1184,8 +1857,14 @@ inline int zstd_decompress_batch(ZstdDecScratch& s, rt::stream_t st, const uint8
     }
     const uint32_t rpc = (chunk_cap + ZR - 1) / ZR ? (chunk_cap + ZR - 1) / ZR : 1;
     const uint32_t bpc = rpc * ZR_SLICES;
+    TS_LAUNCH_P(prof, "zstd_dec_blk_literals", zstd_dec_blk_literals_kernel, dim3((bpc + ZDI_G - 1) / ZDI_G, n_chunks), dim3(32), ZDL_SMEM_BYTES, st, A);
+    if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
+    TS_LAUNCH_P(prof, "zstd_dec_blk_sequences", zstd_dec_blk_sequences_kernel, dim3((bpc + ZDI_G - 1) / ZDI_G, n_chunks), dim3(32), ZDS_SMEM_BYTES, st, A);
+    if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     TS_LAUNCH_P(prof, "zstd_dec_entropy", zstd_dec_par_entropy_kernel, dim3((bpc + ZD_WPB - 1) / ZD_WPB, n_chunks), dim3(ZD_WPB * 32),
                 ZD_SMEM_BYTES, st, A);
+    if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
+    TS_LAUNCH_P(prof, "zstd_dec_blk_exec", zstd_dec_indep_execute_kernel, dim3((bpc + ZXB_WPB - 1) / ZXB_WPB, n_chunks), dim3(ZXB_WPB * 32), ZXB_SMEM_BYTES, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
     TS_LAUNCH_P(prof, "zstd_dec_regions", zstd_dec_regions_kernel, dim3(rpc, n_chunks), dim3(ZX_T), ZX_REGION_SMEM, st, A);
     if ((e = rt::last_error())) { g_zstd_err = e; return -7; }
