@@ -291,7 +291,12 @@ def main_reference(args):
 def fetch_windows(nch, wch):
     """first chunk of each window: start, middle, end of the segment, then a sweep"""
     firsts = [0, nch // 2, nch - wch] + [(k * 37) % (nch - wch + 1) for k in range(1, 14)]
-    return firsts
+    seen, out = set(), []
+    for f in firsts:                                   # (a window as large as the segment — the bulk decode line — has one position)
+        f = min(f, nch - wch)
+        if f not in seen:
+            seen.add(f); out.append(f)
+    return out
 
 
 def make_object(args, flags, src_np, ctx_host, key, aad, ivs):

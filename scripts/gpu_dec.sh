@@ -1,7 +1,7 @@
 # fetch-side loop while tuning the decoder: parity subset, per-kernel times on own / libzstd frames, ncu captures of the block kernels
 set -x
 R=${1:-r02k}
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_paths.py tests/test_gpu_bench_shape.py -m gpu -q -x 2>&1 | tail -3
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_paths.py -m gpu -q -x -k "zstd or full_pipeline or grid or ranged or paths or identical or libzstd or executor" 2>&1 | tail -3
 python tests/perf/bench_detransform.py 256 2>gpurun_out/${R}_bench.err | python -c "
 import sys, json
 d = json.loads(sys.stdin.read().strip().splitlines()[-1])
@@ -14,7 +14,7 @@ d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('fetch $F: value %.2f GiB/s (%.2f ms/window) e2e %.2f ms/window' % (d['value'], d['ms_per_step'], d['e2e']['ms_per_window']), {k: round(v['ms'], 3) for k, v in d['kernels_ms_per_step'].items()}, d['verified'])"
 done
 if [ -z "$NO_NCU" ]; then
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:zstd_dec_blk_sequences -s 1 -c 1 -o gpurun_out/prof_${R}_dec_blk_sequences -f python tests/perf/bench_detransform.py 64 > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:zstd_dec_blk_literals -s 1 -c 1 -o gpurun_out/prof_${R}_dec_blk_literals -f python tests/perf/bench_detransform.py 64 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:zstd_dec_par_execute -s 0 -c 1 -o gpurun_out/prof_${R}_dec_frame_exec -f python bench.py --direction fetch --frames libzstd --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --segment-mib 64 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:zstd_dec_indep_execute -s 1 -c 1 -o gpurun_out/prof_${R}_dec_blk_exec -f python tests/perf/bench_detransform.py 64 > /dev/null 2>&1
 fi
 tail -3 gpurun_out/${R}_bench.err

@@ -80,3 +80,26 @@ def test_gpu_frames_are_identical_across_runs():
             assert sz == fs and np.array_equal(again, first)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_frame_executor_pointer_jumping_shapes():
+    # giant matches (periodic source / rounds), steps cut at the span limit, deep copy chains: every branch of the executor's
+    # pointer-jumping steps, on frames libzstd wrote at three levels; plus a 4 MiB frame of each shape family
+    from executor_shapes import executor_shapes
+    ctx = tsgpu.Context(max_chunk_bytes=4 << 20, max_batch=2)
+    try:
+        shapes = executor_shapes()
+        shapes["records_4MiB"] = np.resize(shapes["records"], 4 << 20)
+        shapes["mixed_4MiB"] = np.resize(shapes["mixed"], 4 << 20)
+        n = 0
+        for name, src in shapes.items():
+            for level in (1, 3, 19):
+                frame = np.frombuffer(ora.zstd_compress_level(src, level), dtype=np.uint8)
+                back, osz = ctx.detransform(Z, frame, [frame.size], src.size)
+                assert osz == [src.size] and np.array_equal(back, src), (name, level)
+                n += 1
+        st = ctx.decode_path_stats()
+        assert st["whole_frames"] == n and st["serial_frames"] == 0
+    finally:
+        ctx.close()

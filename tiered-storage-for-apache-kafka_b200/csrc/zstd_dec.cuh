@@ -1459,8 +1459,11 @@ __device__ __forceinline__ bool zd_huf_stream_staged(const uint16_t* __restrict_
         const uint8_t* a0 = (const uint8_t*)(((uintptr_t)(src + tb) - 60) & ~(uintptr_t)3);
         if (a0 < base) a0 = base;
         const int32_t sbit0 = (int32_t)(a0 - src) * 8;                   // stream bit index of stg word 0, bit 0 (may be negative)
+        uint32_t t[16];                                                  // all sixteen loads in flight before the first store
         _Pragma("unroll")
-        for (int j = 0; j < 16; j++) { const uint8_t* q = a0 + 4 * j; stg[32 * j] = q < lim ? *(const uint32_t*)q : 0u; }
+        for (int j = 0; j < 16; j++) { const uint8_t* q = a0 + 4 * j; t[j] = q < lim ? __ldg((const uint32_t*)q) : 0u; }
+        _Pragma("unroll")
+        for (int j = 0; j < 16; j++) stg[32 * j] = t[j];
         for (int r = 0; r < 10 && i + 4 <= count && bits >= 44; r++) {
             uint32_t out = 0;
             _Pragma("unroll")
@@ -1669,8 +1672,11 @@ __global__ void __launch_bounds__(32) zstd_dec_blk_sequences_kernel(const __grid
         if (a0 < base) a0 = base;
         const int32_t sbit0 = (int32_t)(a0 - bs) * 8;
         if (gmore) {
+            uint32_t t[8];                                               // all eight loads in flight before the first store
             _Pragma("unroll")
-            for (int j = 0; j < 8; j++) { const uint8_t* q = a0 + 4 * (sub * 8 + j); cx->stage[sub * 8 + j] = q < lim ? *(const uint32_t*)q : 0u; }
+            for (int j = 0; j < 8; j++) { const uint8_t* q = a0 + 4 * (sub * 8 + j); t[j] = q < lim ? __ldg((const uint32_t*)q) : 0u; }
+            _Pragma("unroll")
+            for (int j = 0; j < 8; j++) cx->stage[sub * 8 + j] = t[j];
         }
         __syncwarp();
         uint32_t cnt = 0;
