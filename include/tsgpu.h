@@ -11,8 +11,9 @@
  *
  * Conventions: plain pointers and sizes only; return 0 (TSGPU_OK) or a negative error code; never throws or
  * aborts; the caller owns every buffer and the library keeps no pointer after a call returns; a context may
- * be used from several threads (calls serialise per context); there is NO CPU fallback — without a CUDA
- * device tsgpu_create fails with TSGPU_E_NODEVICE.
+ * be used from several threads at once (a host-buffer call claims work slots — stream pair, arenas, pinned descriptor
+ * block — and concurrent calls overlap on the GPU; only the slot bookkeeping is under the context mutex); there is NO
+ * CPU fallback — without a CUDA device tsgpu_create fails with TSGPU_E_NODEVICE.
  */
 #ifndef TSGPU_H
 #define TSGPU_H
@@ -59,8 +60,9 @@ const char* tsgpu_version(void);
  * 8 of them in flight per device (work slots, allocated on first use; each has a compute stream and a copy-out stream).
  * With 4 MiB chunks `max_batch = 4` measured best through PCIe; device-resident callers pass whole segments.
  * Environment (read once by tsgpu_create; tuning only): TSGPU_SLOTS=1..16 slots per device, TSGPU_SPLIT_OUT=0 puts the
- * copies-out back on the compute stream.  Variants that are off by default and not yet timed:
- * TSGPU_ENC_SPLIT=1 (compressor as two launches), TSGPU_DEC_PARALLEL=1 (libzstd-shaped frames: entropy stage per block).
+ * copies-out back on the compute stream, TSGPU_ZSTD_MODE=dense makes TSGPU_FLAG_ZSTD_DENSE the context's default.
+ * (Round 1's opt-in variants are gone: the per-block entropy stage for libzstd-shaped frames is the only general decode
+ * path now, the two-launch compressor was deleted.)
  * --------------------------------------------------------------------------------------------------------- */
 int  tsgpu_create(const int* device_ids, int n_devices, uint32_t max_chunk_bytes, uint32_t max_batch,
                   tsgpu_ctx** out);
@@ -174,12 +176,22 @@ int tsgpu_chunk_positions(tsgpu_ctx* ctx, const uint32_t* sizes, uint32_t n, uin
 int tsgpu_chunk_sizes_encode(const int32_t* v, uint32_t n, uint8_t* out, uint32_t* out_len);
 int tsgpu_chunk_sizes_decode(const uint8_t* in, uint32_t in_len, int32_t* out, uint32_t* n);
 int tsgpu_transformed_chunks_serialize(const int32_t* v, uint32_t n, char* out, uint32_t* out_len);
+/* Same field, compressed like the reference compresses it (TransformedChunksSerializer.java:40-48 runs libzstd over the codec
+ * bytes): the codec bytes go through this library's dense compressor as one chunk and the shorter of {that frame, the Raw-block
+ * frame of the ctx-less call} is kept — lists that repeat or cluster shrink as they do in the reference's manifests.  Frames of
+ * both calls are read by TransformedChunksDeserializer.java:36-49 and by tsgpu_transformed_chunks_deserialize. */
+int tsgpu_transformed_chunks_serialize_ctx(tsgpu_ctx* ctx, const int32_t* v, uint32_t n, char* out, uint32_t* out_len);
 /* deserialize needs a context: frames written by the reference are libzstd-compressed and are decoded on the GPU */
 int tsgpu_transformed_chunks_deserialize(tsgpu_ctx* ctx, const char* b64, int32_t* out, uint32_t* n);
 /* transformed_chunk_size < 0 => variable index built from sizes[0..n); else fixed (sizes may be NULL) */
 int tsgpu_chunk_index_json(int32_t original_chunk_size, int32_t original_file_size,
                            int32_t transformed_chunk_size, int32_t final_transformed_chunk_size,
                            const int32_t* sizes, uint32_t n, char* out, uint32_t* out_len);
+
+/* tsgpu_chunk_index_json with the variable index's transformedChunks compressed (tsgpu_transformed_chunks_serialize_ctx). */
+int tsgpu_chunk_index_json_ctx(tsgpu_ctx* ctx, int32_t original_chunk_size, int32_t original_file_size,
+                               int32_t transformed_chunk_size, int32_t final_transformed_chunk_size,
+                               const int32_t* sizes, uint32_t n, char* out, uint32_t* out_len);
 
 #ifdef __cplusplus
 }

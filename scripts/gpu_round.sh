@@ -26,3 +26,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:zstd
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:zstd_dec_par_entropy -s 0 -c 1 -o gpurun_out/prof_${R}_zstd_dec_entropy -f python bench.py --direction fetch --frames libzstd --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --segment-mib 64 > /dev/null 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:zstd_dec_par_execute -s 0 -c 1 -o gpurun_out/prof_${R}_zstd_dec_frame_exec -f python bench.py --direction fetch --frames libzstd --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --segment-mib 64 > /dev/null 2>&1
 ls -la gpurun_out | grep ${R} | tail -30; tail -5 gpurun_out/${R}_bench.err
+# compute-sanitizer over the smoke invocation (both compressors, every decode path, AES both ways): logs go under profiles/
+timeout 420 compute-sanitizer --tool memcheck --log-file gpurun_out/${R}_sanitizer_memcheck.log python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_sanitizer_memcheck.out 2>&1; echo "memcheck exit $?" >> gpurun_out/${R}_sanitizer_memcheck.out
+timeout 420 compute-sanitizer --tool racecheck --log-file gpurun_out/${R}_sanitizer_racecheck.log python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_sanitizer_racecheck.out 2>&1; echo "racecheck exit $?" >> gpurun_out/${R}_sanitizer_racecheck.out
+tail -3 gpurun_out/${R}_sanitizer_memcheck.log gpurun_out/${R}_sanitizer_racecheck.log

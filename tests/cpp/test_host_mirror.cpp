@@ -178,7 +178,9 @@ static void gpuChainTests(tsgpu_ctx* ctx) {
                 RemoteLogSegmentMetadataJson md{"lZ6vvmajTWKDBUTV6SQAtQ", "topic1", 7, "adh9f8BMS4anaUnD8KWfWg", 0, 99, 1, 2, 3, {{0, 0}}};
                 SegmentIndexesV1 six{{0, 10}, {10, 10}, {20, 10}, {30, 10}, std::nullopt};
                 const std::string text = segmentManifestV1Json(*idx, six, mode & 1, (mode & 2) ? std::optional<std::string>("k:AAEC") : std::nullopt,
-                                                               (mode & 2) ? &km.aad : nullptr, md);
+                                                               (mode & 2) ? &km.aad : nullptr, md, ctx);   // transformedChunks compressed on the device
+                CHECK(text.size() <= segmentManifestV1Json(*idx, six, mode & 1, (mode & 2) ? std::optional<std::string>("k:AAEC") : std::nullopt,
+                                                           (mode & 2) ? &km.aad : nullptr, md).size());
                 SegmentManifestV1 back = parseSegmentManifestV1(text, ctx);
                 CHECK(back.chunkIndex->chunks().size() == idx->chunks().size());
                 bool same = true;

@@ -214,6 +214,23 @@ def test_deserialize_reference_written_index(ctx):
     assert ctx.transformed_chunks_deserialize("KLUv/SAPeQAAAAAAAwAAAAoBAAoAAAAe") == [10, 20, 30]
 
 
+def test_transformed_chunks_compressed_like_the_reference(ctx):
+    # TransformedChunksSerializer.java:40-48: the manifest field is Base64(zstd(codec bytes)); the ctx-taking serializer
+    # compresses with the dense kernel — both readers accept it, the golden vector is unchanged, sizes track libzstd's
+    rng = np.random.default_rng(5)
+    for name, sizes in {"equal": [4194332] * 256, "clustered": (1350000 + rng.integers(-70000, 70000, 256)).tolist(),
+                        "tight": (1350000 + rng.integers(-700, 700, 4096)).tolist(), "golden": [10, 20, 30]}.items():
+        mine, ref, raw = ctx.transformed_chunks_serialize(sizes), ora.transformed_chunks_serialize(sizes), binding.transformed_chunks_serialize(sizes)
+        assert ora.transformed_chunks_deserialize(mine) == sizes and ctx.transformed_chunks_deserialize(mine) == sizes, name
+        assert len(mine) <= len(raw), name
+        if name == "golden":
+            assert mine == ref == "KLUv/SAPeQAAAAAAAwAAAAoBAAoAAAAe"
+        else:
+            assert len(mine) <= len(ref) + max(40, len(ref) // 10), (name, len(mine), len(ref), len(raw))
+    js = ctx.chunk_index_json(4 * MIB, 255 * 4 * MIB + 5, None, sizes=[4194332] * 256)
+    assert js.startswith('{"type":"variable","originalChunkSize":4194304,"originalFileSize":%d,"transformedChunks":"' % (255 * 4 * MIB + 5))
+
+
 def test_empty_segment_and_argument_errors(ctx):
     out, sizes = ctx.transform(Z | A, np.zeros(0, np.uint8), 4 * MIB, bytes(32), b"", bytes(12))
     assert sizes == [] and len(out) == 0

@@ -2,6 +2,7 @@
 through the C-ABI and checks them against the oracle (system libzstd): our frames decode with libzstd, libzstd's
 level-3 frames decode with ours, Frame_Content_Size is present, corrupt input is an error and never a crash.
 Logic check for the GPU-less build box; the -m gpu tests repeat this on a B200 at full sizes."""
+import json
 import os
 import subprocess
 import sys
@@ -122,6 +123,29 @@ def test_simt_reference_written_index_deserializes(ctx):
     assert ctx.transformed_chunks_deserialize("KLUv/SAPeQAAAAAAAwAAAAoBAAoAAAAe") == [10, 20, 30]
     pos = ctx.chunk_positions(sizes)
     assert [int(p) for p in pos[:-1]] == [c[3] for c in ora.ChunkIndex.variable(1 << 20, 599 * (1 << 20) + 1, sizes).chunks()]
+
+
+def test_simt_transformed_chunks_compressed_like_the_reference(ctx):
+    # TransformedChunksSerializer.java:40-48 compresses the codec bytes; the ctx-taking serializer does so with the dense
+    # compressor.  Both readers must accept the result, the golden vector must not change, and lists that repeat / cluster
+    # must come out about as small as libzstd makes them (the Raw-block framing of the ctx-less call does not shrink them).
+    rng = np.random.default_rng(5)
+    lists = {"equal": [4194332] * 256, "clustered": (1350000 + rng.integers(-70000, 70000, 256)).tolist(),
+             "tight": (1350000 + rng.integers(-700, 700, 1024)).tolist(), "golden": [10, 20, 30], "one": [123456]}
+    for name, sizes in lists.items():
+        mine, ref, raw = ctx.transformed_chunks_serialize(sizes), ora.transformed_chunks_serialize(sizes), binding.transformed_chunks_serialize(sizes, lib_path=SIMT_LIB)
+        assert ora.transformed_chunks_deserialize(mine) == sizes, name           # the reference-side reader (libzstd)
+        assert ctx.transformed_chunks_deserialize(mine) == sizes, name
+        assert len(mine) <= len(raw), name
+        if name == "golden":
+            assert mine == ref == "KLUv/SAPeQAAAAAAAwAAAAoBAAoAAAAe"
+        if name in ("equal", "clustered", "tight"):
+            print(name, len(mine), len(ref), len(raw))
+            assert len(mine) <= len(ref) + max(40, len(ref) // 10), (name, len(mine), len(ref), len(raw))
+    js = json.loads(ctx.chunk_index_json(1 << 22, 255 * (1 << 22) + 5, None, sizes=lists["clustered"]))
+    want = json.loads(ora.ChunkIndex.variable(1 << 22, 255 * (1 << 22) + 5, lists["clustered"]).to_json())
+    assert list(js) == list(want) and all(js[k] == want[k] for k in js if k != "transformedChunks")
+    assert ora.transformed_chunks_deserialize(js["transformedChunks"]) == lists["clustered"]
 
 
 def test_simt_index_files_ride_one_ragged_batch(ctx):

@@ -25,7 +25,7 @@ SYMBOLS = [
     "tsgpu_transform_device", "tsgpu_detransform_device", "tsgpu_launch_count", "tsgpu_chunk_positions",
     "tsgpu_chunk_sizes_encode", "tsgpu_chunk_sizes_decode", "tsgpu_transformed_chunks_serialize",
     "tsgpu_transformed_chunks_deserialize", "tsgpu_chunk_index_json", "tsgpu_profile_enable", "tsgpu_profile_report",
-    "tsgpu_decode_path_stats",
+    "tsgpu_decode_path_stats", "tsgpu_transformed_chunks_serialize_ctx", "tsgpu_chunk_index_json_ctx",
 ]
 
 
@@ -76,6 +76,8 @@ def load(path=None):
     L.tsgpu_transformed_chunks_serialize.argtypes = [vp, u32, C.c_char_p, C.POINTER(u32)]
     L.tsgpu_transformed_chunks_deserialize.argtypes = [vp, C.c_char_p, vp, C.POINTER(u32)]
     L.tsgpu_chunk_index_json.argtypes = [i32, i32, i32, i32, vp, u32, C.c_char_p, C.POINTER(u32)]
+    L.tsgpu_transformed_chunks_serialize_ctx.argtypes = [vp, vp, u32, C.c_char_p, C.POINTER(u32)]
+    L.tsgpu_chunk_index_json_ctx.argtypes = [vp, i32, i32, i32, i32, vp, u32, C.c_char_p, C.POINTER(u32)]
     _libs[path] = L
     return L
 
@@ -215,6 +217,24 @@ class Context:
         n = C.c_uint32(cap)
         self._check(self.lib.tsgpu_transformed_chunks_deserialize(self._h, b64.encode(), out.ctypes.data, C.byref(n)))
         return [int(x) for x in out[:n.value]]
+
+    def transformed_chunks_serialize(self, values):
+        """TransformedChunksSerializer with the codec bytes compressed (dense compressor), like the reference's manifests"""
+        v = np.ascontiguousarray(values, dtype=np.int32)
+        buf = C.create_string_buffer(256 + 8 * v.size)
+        n = C.c_uint32(len(buf))
+        self._check(self.lib.tsgpu_transformed_chunks_serialize_ctx(self._h, _p(v), v.size, buf, C.byref(n)))
+        return buf.value.decode()
+
+    def chunk_index_json(self, original_chunk_size, original_file_size, transformed_chunk_size=None,
+                         final_transformed_chunk_size=0, sizes=None):
+        v = np.ascontiguousarray(sizes if sizes is not None else [], dtype=np.int32)
+        buf = C.create_string_buffer(1024 + 8 * v.size)
+        n = C.c_uint32(len(buf))
+        tcs = -1 if transformed_chunk_size is None else transformed_chunk_size
+        self._check(self.lib.tsgpu_chunk_index_json_ctx(self._h, original_chunk_size, original_file_size, tcs,
+                                                        final_transformed_chunk_size, _p(v), v.size, buf, C.byref(n)))
+        return buf.value.decode()
 
 
 def _raise(L, rc):

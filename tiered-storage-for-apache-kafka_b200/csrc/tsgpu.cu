@@ -947,6 +947,35 @@ extern "C" int tsgpu_transformed_chunks_serialize(const int32_t* v, uint32_t n, 
     memcpy(out, s.c_str(), s.size() + 1); *out_len = (uint32_t)s.size();
     return TSGPU_OK;
 }
+// TransformedChunksSerializer.java:40-48 compresses the codec bytes with libzstd before Base64; the ctx-taking form does the
+// same with this library's dense compressor (one frame with Frame_Content_Size, the codec bytes as ONE chunk) and keeps
+// whichever of {compressed frame, Raw-block frame} is shorter — so manifests of segments whose chunk sizes repeat or cluster
+// are as small as the reference's instead of carrying the bit-packed list verbatim.
+static int serialize_transformed_chunks_ctx(tsgpu_ctx* c, const int32_t* v, uint32_t n, std::string& out) {
+    tshost::Error err;
+    if (!serialize_transformed_chunks(v, n, out, err)) return fail(TSGPU_E_ARG, "%s", err.msg.c_str());
+    std::vector<uint8_t> raw;
+    if (!tshost::ChunkSizesBinaryCodec::encode(v, n, raw, err)) return fail(TSGPU_E_ARG, "%s", err.msg.c_str());
+    if (raw.size() < 64 || raw.size() > c->chunk_cap) return TSGPU_OK;          // nothing to gain / larger than the context's chunks
+    const uint32_t fl = TSGPU_FLAG_ZSTD | TSGPU_FLAG_ZSTD_DENSE;
+    std::vector<uint8_t> z((size_t)tsgpu_transform_bound(fl, raw.size(), 0) + 64);
+    uint32_t tsz = 0, nch = 1;
+    const int rc = tsgpu_transform(c, fl, raw.data(), raw.size(), 0, nullptr, nullptr, 0, nullptr, z.data(), z.size(), &tsz, &nch);
+    if (rc) return rc;
+    if (nch == 1 && tsz) {
+        std::string b = tshost::base64Encode(z.data(), tsz);
+        if (b.size() < out.size()) out.swap(b);
+    }
+    return TSGPU_OK;
+}
+extern "C" int tsgpu_transformed_chunks_serialize_ctx(tsgpu_ctx* c, const int32_t* v, uint32_t n, char* out, uint32_t* out_len) try {
+    if (!c || !out_len || (n && !v)) return fail(TSGPU_E_ARG, "null argument");
+    std::string s;
+    if (int rc = serialize_transformed_chunks_ctx(c, v, n, s)) return rc;
+    if (!out || *out_len < s.size() + 1) { *out_len = (uint32_t)s.size() + 1; return fail(TSGPU_E_SHORT, "out too small"); }
+    memcpy(out, s.c_str(), s.size() + 1); *out_len = (uint32_t)s.size();
+    return TSGPU_OK;
+} catch (const std::bad_alloc&) { return fail(TSGPU_E_NOMEM, "out of memory"); }
 extern "C" int tsgpu_transformed_chunks_deserialize(tsgpu_ctx* c, const char* b64, int32_t* out, uint32_t* n) {
     if (!c || !b64 || !n) return fail(TSGPU_E_ARG, "null argument");
     std::vector<uint8_t> z; tshost::Error err;
@@ -965,8 +994,19 @@ extern "C" int tsgpu_transformed_chunks_deserialize(tsgpu_ctx* c, const char* b6
     return TSGPU_OK;
 }
 
+static int chunk_index_json_impl(tsgpu_ctx* c, int32_t ocs, int32_t ofs, int32_t tcs, int32_t ftcs, const int32_t* sizes, uint32_t n,
+                                 char* out, uint32_t* out_len);
 extern "C" int tsgpu_chunk_index_json(int32_t ocs, int32_t ofs, int32_t tcs, int32_t ftcs, const int32_t* sizes, uint32_t n,
                                       char* out, uint32_t* out_len) {
+    return chunk_index_json_impl(nullptr, ocs, ofs, tcs, ftcs, sizes, n, out, out_len);
+}
+extern "C" int tsgpu_chunk_index_json_ctx(tsgpu_ctx* c, int32_t ocs, int32_t ofs, int32_t tcs, int32_t ftcs, const int32_t* sizes, uint32_t n,
+                                          char* out, uint32_t* out_len) try {
+    if (!c) return fail(TSGPU_E_ARG, "null argument");
+    return chunk_index_json_impl(c, ocs, ofs, tcs, ftcs, sizes, n, out, out_len);
+} catch (const std::bad_alloc&) { return fail(TSGPU_E_NOMEM, "out of memory"); }
+static int chunk_index_json_impl(tsgpu_ctx* c, int32_t ocs, int32_t ofs, int32_t tcs, int32_t ftcs, const int32_t* sizes, uint32_t n,
+                                 char* out, uint32_t* out_len) {
     if (!out_len) return fail(TSGPU_E_ARG, "null argument");
     if (ocs <= 0) return fail(TSGPU_E_ARG, "Original chunk size must be positive, %d given", ocs);
     if (ofs < 0) return fail(TSGPU_E_ARG, "Original file size must be non-negative, %d given", ofs);
@@ -980,7 +1020,8 @@ extern "C" int tsgpu_chunk_index_json(int32_t ocs, int32_t ofs, int32_t tcs, int
     } else {
         if (!sizes || n == 0) return fail(TSGPU_E_ARG, "transformedChunks cannot be null");
         std::string b64; tshost::Error err;
-        if (!serialize_transformed_chunks(sizes, n, b64, err)) return fail(TSGPU_E_ARG, "%s", err.msg.c_str());
+        if (c) { if (int rc = serialize_transformed_chunks_ctx(c, sizes, n, b64)) return rc; }
+        else if (!serialize_transformed_chunks(sizes, n, b64, err)) return fail(TSGPU_E_ARG, "%s", err.msg.c_str());
         snprintf(buf, sizeof buf, "{\"type\":\"variable\",\"originalChunkSize\":%d,\"originalFileSize\":%d,\"transformedChunks\":\"", ocs, ofs);
         s = std::string(buf) + b64 + "\"}";
     }

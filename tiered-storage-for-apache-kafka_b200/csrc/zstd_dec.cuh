@@ -484,9 +484,9 @@ __device__ __forceinline__ uint32_t zd_compressed_block(const uint8_t* blk, uint
 }
 
 // ------------------------------------------------------------------------------------------ parallel general path
-// (TSGPU_DEC_PARALLEL=1; off by default, not yet timed.)  Frames written by libzstd have few, large blocks that inherit
-// tables and repeat offsets from each other, so the fast path does not apply and one warp per frame is slow for a lone
-// frame.  Here every block's ENTROPY decoding (Huffman literals, FSE sequences) runs on its own warp into global scratch:
+// (The general decode path of the product; round 1 had it behind TSGPU_DEC_PARALLEL=1.)  Frames written by libzstd have few,
+// large blocks that inherit tables and repeat offsets from each other, so the per-block fast path does not apply and one
+// warp per frame is slow for a lone frame.  Here every block's ENTROPY decoding (Huffman literals, FSE sequences) runs on its own warp into global scratch:
 // tables a block inherits (treeless literals, Repeat_Mode) are rebuilt by replaying the table definitions of the blocks
 // before it; offsets stay unresolved offset VALUES.  One warp per frame then resolves repeat offsets and executes the
 // sequences in order.  The stages are the same textual includes the serial decoder is made of.

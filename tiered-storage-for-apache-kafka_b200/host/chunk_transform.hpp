@@ -73,7 +73,9 @@ public:
         }
         return r;
     }
-    virtual std::string toJson() const = 0;
+    // ctx != nullptr: a variable index's transformedChunks is compressed like the reference compresses it
+    // (TransformedChunksSerializer.java:40-48; tsgpu_chunk_index_json_ctx) instead of framed as a Raw block
+    virtual std::string toJson(tsgpu_ctx* ctx = nullptr) const = 0;
     const int originalChunkSize, originalFileSize, finalTransformedChunkSize, chunkCount;
 
 protected:
@@ -103,10 +105,13 @@ protected:
     std::vector<Chunk> chunks_;
 };
 
-inline std::string jsonFromAbi(int ocs, int ofs, int tcs, int ftcs, const std::vector<int32_t>* sizes) {
+inline std::string jsonFromAbi(int ocs, int ofs, int tcs, int ftcs, const std::vector<int32_t>* sizes, tsgpu_ctx* ctx = nullptr) {
     std::vector<char> buf(1024 + (sizes ? sizes->size() * 8 : 0));
     uint32_t n = (uint32_t)buf.size();
-    int rc = tsgpu_chunk_index_json(ocs, ofs, tcs, ftcs, sizes ? sizes->data() : nullptr, sizes ? (uint32_t)sizes->size() : 0, buf.data(), &n);
+    const int32_t* sp = sizes ? sizes->data() : nullptr;
+    const uint32_t sn = sizes ? (uint32_t)sizes->size() : 0;
+    int rc = ctx ? tsgpu_chunk_index_json_ctx(ctx, ocs, ofs, tcs, ftcs, sp, sn, buf.data(), &n)
+                 : tsgpu_chunk_index_json(ocs, ofs, tcs, ftcs, sp, sn, buf.data(), &n);
     if (rc) throw IllegalArgumentException(tsgpu_last_error());
     return std::string(buf.data(), n);
 }
@@ -116,7 +121,7 @@ public:
     FixedSizeChunkIndex(int ocs, int ofs, int tcs, int ftcs)
         : ChunkIndex(ocs, ofs, ftcs, count(ocs, ofs)), transformedChunkSize(checkNonNeg(tcs, "Transformed chunk size")) { materializeChunks(); }
     const int transformedChunkSize;
-    std::string toJson() const override { return jsonFromAbi(originalChunkSize, originalFileSize, transformedChunkSize, finalTransformedChunkSize, nullptr); }
+    std::string toJson(tsgpu_ctx* = nullptr) const override { return jsonFromAbi(originalChunkSize, originalFileSize, transformedChunkSize, finalTransformedChunkSize, nullptr); }
 protected:
     int transformedChunkSizeAt(int i) const override { return i == chunkCount - 1 ? finalTransformedChunkSize : transformedChunkSize; }
 private:
@@ -128,7 +133,7 @@ public:
     VariableSizeChunkIndex(int ocs, int ofs, std::vector<int32_t> sizes)
         : ChunkIndex(ocs, ofs, last(sizes), (int)sizes.size()), transformedChunks(std::move(sizes)) { materializeChunks(); }
     const std::vector<int32_t> transformedChunks;
-    std::string toJson() const override { return jsonFromAbi(originalChunkSize, originalFileSize, -1, 0, &transformedChunks); }
+    std::string toJson(tsgpu_ctx* ctx = nullptr) const override { return jsonFromAbi(originalChunkSize, originalFileSize, -1, 0, &transformedChunks, ctx); }
 protected:
     int transformedChunkSizeAt(int i) const override { return transformedChunks[i]; }
 private:
@@ -514,11 +519,11 @@ inline std::string base64Std(const uint8_t* in, size_t n) {
 }
 inline std::string segmentManifestV1Json(const ChunkIndex& chunkIndex, const SegmentIndexesV1& idx, bool compression,
                                          const std::optional<std::string>& wrappedDataKey, const Bytes* aad,
-                                         const RemoteLogSegmentMetadataJson& m) {
+                                         const RemoteLogSegmentMetadataJson& m, tsgpu_ctx* ctx = nullptr) {
     auto one = [](const char* name, const SegmentIndexV1& i) {
         return std::string("\"") + name + "\":{\"position\":" + std::to_string(i.position) + ",\"size\":" + std::to_string(i.size) + "}";
     };
-    std::string s = "{\"version\":\"1\",\"chunkIndex\":" + chunkIndex.toJson() + ",\"segmentIndexes\":{";
+    std::string s = "{\"version\":\"1\",\"chunkIndex\":" + chunkIndex.toJson(ctx) + ",\"segmentIndexes\":{";
     s += one("offset", idx.offset) + "," + one("timestamp", idx.timestamp) + "," + one("producerSnapshot", idx.producerSnapshot) + "," +
          one("leaderEpoch", idx.leaderEpoch) + ",";
     s += idx.transaction ? one("transaction", *idx.transaction) : std::string("\"transaction\":null");
