@@ -27,7 +27,7 @@ extern "C" {
 #define TSGPU_FLAG_ZSTD 1u     /* compression.enabled  (RemoteStorageManagerConfig.java:132-138) */
 #define TSGPU_FLAG_AES  2u     /* encryption.enabled   (RemoteStorageManagerConfig.java:147-153) */
 /* Modifier of TSGPU_FLAG_ZSTD on the transform side (ignored by detransform): compress for size rather than for speed.
- * Default: independent 8 KiB blocks, ~3.1 : 1 on Kafka-like text at ~15 ms per GiB on a B200 — the segment pipeline stays
+ * Default: independent 8 KiB blocks, ~3.1 : 1 on Kafka-like text at ~14.7 ms per GiB on a B200 — the segment pipeline stays
  * PCIe-bound.  Dense: 64 KiB regions sharing one window and one set of entropy tables, ~3.5 : 1 at ~27 ms per GiB and
  * byte-identical frames on every run.  Both are plain zstd frames with Frame_Content_Size; libzstd and this library read both.
  * TSGPU_ZSTD_MODE=dense in the environment makes dense the default of a context. */

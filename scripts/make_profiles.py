@@ -29,25 +29,40 @@ for f in sorted(glob.glob(os.path.join(G, R + "_bench_*.json")) + glob.glob(os.p
     print("bench line", os.path.basename(f))
 
 traffic = {}
+
+
+def num(s):
+    v, _, u = s.partition(" ")
+    return float(v.replace(",", "")) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u.strip(), 1.0)
+
+
+# gpu_round.sh summarises every .ncu-rep on the box (gpurun copies back at most 64 MiB): <R>_<name>.ncu.json holds one
+# entry per captured kernel, <R>_<name>.by_line.txt the top source lines; a report that did come back is summarised here
 for rep in sorted(glob.glob(os.path.join(G, "prof_" + R + "_*.ncu-rep"))):
     name = os.path.basename(rep)[len("prof_"):-len(".ncu-rep")]
-    out = os.path.join(P, name + ".ncu.json")
-    txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, out], capture_output=True, text=True).stdout
+    if not os.path.exists(os.path.join(G, name + ".ncu.json")):
+        subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, os.path.join(G, name + ".ncu.json")], capture_output=True)
+for f in sorted(glob.glob(os.path.join(G, R + "_*.ncu.json"))):
+    name = os.path.basename(f)[:-len(".ncu.json")]
     try:
-        d = json.loads(txt)[0]
-    except (ValueError, IndexError):
-        print("could not read", rep)
+        ds = json.load(open(f))
+    except ValueError:
+        print("could not read", f)
         continue
-    def num(s):
-        v, _, u = s.partition(" ")
-        return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u.strip(), 1.0)
-    if "dram_read" in d and "dram_write" in d:
-        key = name[len(R) + 1:]                      # e.g. zstd_enc_blocks
-        traffic[key] = {"bytes": num(d["dram_read"]) + num(d["dram_write"]), "capture": "profiles/%s.ncu.json" % name,
-                        "duration_under_ncu": d.get("duration")}
-    print("ncu summary", name, d.get("duration"), d.get("issue_active_pct"))
+    shutil.copy(f, os.path.join(P, name + ".ncu.json"))
+    for d in ds:
+        kern = d.get("kernel", "").split("(")[0].split("<")[0].replace("_kernel", "")
+        if "dram_read" in d and "dram_write" in d:
+            traffic[kern] = {"bytes": num(d["dram_read"]) + num(d["dram_write"]), "capture": "profiles/%s.ncu.json" % name,
+                             "duration_under_ncu": d.get("duration")}
+        print("ncu summary", name, kern, d.get("duration"), d.get("issue_active_pct"))
 if traffic:
     json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+for f in sorted(glob.glob(os.path.join(G, R + "_*.by_line.txt")) + glob.glob(os.path.join(G, R + "_sanitizer_*")) +
+                glob.glob(os.path.join(G, R + "_pcie_ceiling*.json"))):
+    if os.path.getsize(f) < (1 << 20):
+        shutil.copy(f, os.path.join(P, os.path.basename(f)))
+        print("copied", os.path.basename(f))
 
 lst = os.path.join(G, R + "_launches.csv")
 if os.path.exists(lst):

@@ -339,10 +339,16 @@ __device__ __forceinline__ void ze_lb_store(unsigned long long* w, unsigned long
 }
 // st: the chunk's words; idx: this unit; size: its bytes; head: what precedes unit 0 (the frame header).  Returns the
 // unit's offset in the frame (warp-uniform).  `last` units do not publish (nobody looks back at them).
+#ifndef ZE_TUNE_LB_BACKOFF   // 1: exponential back-off (100 ns .. 1.6 us) while a predecessor has not published its size yet
+#define ZE_TUNE_LB_BACKOFF 0
+#endif
 __device__ __forceinline__ uint32_t ze_lookback(unsigned long long* st, uint32_t idx, uint32_t size, uint32_t head, bool last, uint32_t lane) {
     if (lane == 0 && !last) ze_lb_store(&st[idx], ZE_LB_SIZE | size);
     uint64_t excl = 0;
     int32_t hi = (int32_t)idx - 1;                           // the window is units hi, hi-1, ..., hi-31 (lane 0 = nearest)
+#if ZE_TUNE_LB_BACKOFF
+    uint32_t pause = 100;                                    // doubles per failed probe: a waiting warp should not eat issue slots
+#endif
     while (true) {
         const int32_t i = hi - (int32_t)lane;
         unsigned long long v = i >= 0 ? ze_lb_load(&st[i]) : (i == -1 ? (ZE_LB_PREFIX | head) : 0ull);
@@ -354,6 +360,9 @@ __device__ __forceinline__ uint32_t ze_lookback(unsigned long long* st, uint32_t
         if (empty & need) {                                  // a predecessor has not finished encoding yet
 #ifdef TSGPU_SIMT
             simt::yield();
+#elif ZE_TUNE_LB_BACKOFF
+            __nanosleep(pause);
+            pause = min(pause * 2, 1600u);
 #else
             __nanosleep(200);
 #endif

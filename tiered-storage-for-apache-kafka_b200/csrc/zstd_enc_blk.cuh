@@ -4,7 +4,7 @@
 // different trade: every 8 KiB block is self-contained (own Huffman tree, own FSE tables, no match leaves the block), so a
 // 1 GiB segment is 131,072 independent warps with no barrier between them, 20 warps per SM.  That is the round-1 kernel with
 // the streamlined FSE chains and the backwards growth of taken matches ("catch up"); it compresses the K corpus ~3.1 : 1 at
-// ~15 ms per GiB, where the region kernel of zstd_enc.cuh reaches ~3.5 : 1 at ~27 ms per GiB (one 64 KiB window and one set
+// ~14.7 ms per GiB, where the region kernel of zstd_enc.cuh reaches ~3.5 : 1 at ~27 ms per GiB (one 64 KiB window and one set
 // of tables per 8 blocks).  TSGPU_FLAG_ZSTD picks this kernel, TSGPU_FLAG_ZSTD | TSGPU_FLAG_ZSTD_DENSE the region kernel;
 // the decoder reads both through the same region path (zstd_dec.cuh).
 //   zstd_enc_blocks_kernel    one WARP per block: block staged in shared memory; 32 positions hashed and verified per step
@@ -30,6 +30,12 @@ constexpr uint32_t ZB_HSIZE = 1u << ZB_HLOG;
 #endif
 #ifndef ZB_TUNE_BACK      // 1: taken matches grow backwards over up to 4 literals ("catch up"): +3.6 % ratio for +0.76 ms per GiB (measured)
 #define ZB_TUNE_BACK 1
+#endif
+#ifndef ZB_TUNE_STRAIGHT  // 1: per-lane match extension as straight-line code over 12 bytes instead of a divergent loop:
+#define ZB_TUNE_STRAIGHT 1 //   16.21 -> 14.72 ms per GiB on the B200 (the loop was 16 % of the kernel's stall samples; profiles/r02_ab.md)
+#endif
+#ifndef ZB_TUNE_EXTLDS    // 1: the warp-wide extension of long matches reads shared memory with LDS word pairs instead of generic loads
+#define ZB_TUNE_EXTLDS 0  //    (measured on the B200: 14.92 instead of 14.72 ms per GiB — off; profiles/r02_ab.md)
 #endif
 constexpr int ZB_WPB = ZB_TUNE_WPB;            // warps (= blocks in flight) per CTA
 constexpr uint32_t ZB_LANE_EXT = ZB_TUNE_LANE_EXT;   // bytes a lane extends its own match beyond the first 4
@@ -542,6 +548,18 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zstd_enc_blocks_kernel(const __gr
         const uint32_t bkr = 0;
 #endif
         uint32_t len = 0;
+#if ZB_TUNE_STRAIGHT
+        {   // the 12 bytes after the verified 4, straight-line on all lanes (three more words per stream): no divergent loop
+            static_assert(ZB_TUNE_LANE_EXT == 12, "the straight-line extension measures exactly 12 bytes");
+            const uint32_t a2 = wp[2], a3 = wp[3], a4 = wp[4], c2 = wc[2], c3 = wc[3], c4 = wc[4];
+            const uint32_t x1 = __funnelshift_r(a1, a2, shp) ^ __funnelshift_r(c1, c2, shc);
+            const uint32_t x2 = __funnelshift_r(a2, a3, shp) ^ __funnelshift_r(c2, c3, shc);
+            const uint32_t x3 = __funnelshift_r(a3, a4, shp) ^ __funnelshift_r(c3, c4, shc);
+            const uint32_t e1 = ze_common_bytes(x1), e2 = ze_common_bytes(x2), e3 = ze_common_bytes(x3);   // 0..4 each
+            const uint32_t e = e1 + (e1 >> 2) * (e2 + (e2 >> 2) * e3);         // branch-free: a word counts only if the one before it matched whole
+            len = ok ? min(4 + e, min(bn - p, 4 + ZB_LANE_EXT)) : 0u;
+        }
+#else
         if (ok) {
             len = 4;
             const uint32_t lim = min(bn - p, 4 + ZB_LANE_EXT);
@@ -553,6 +571,7 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zstd_enc_blocks_kernel(const __gr
             }
             len = min(len, lim);
         }
+#endif
         const uint32_t mask = __ballot_sync(TS_FULL, ok && len >= ZE_MIN_MATCH);
         // Greedy selection, left to right.  Every lane precomputes where its match would end and which candidate would
         // come next, so one shuffle per taken match walks the chain (the only serial part of the parse).
@@ -574,7 +593,14 @@ __global__ void __launch_bounds__(ZB_WPB * 32) zstd_enc_blocks_kernel(const __gr
                     const uint32_t q = mpos + L + 4 * lane;
                     uint32_t c = 0;
                     if (q < bn) {
+#if ZB_TUNE_EXTLDS      // shared-memory word pairs + funnel shifts (ld_u32_unaligned goes through a generic pointer: LD.E, not LDS)
+                        const uint32_t r = q - off;
+                        const uint32_t* wq = (const uint32_t*)(buf + (q & ~3u));
+                        const uint32_t* wr = (const uint32_t*)(buf + (r & ~3u));
+                        c = ze_common_bytes(__funnelshift_r(wq[0], wq[1], (q & 3) * 8) ^ __funnelshift_r(wr[0], wr[1], (r & 3) * 8));
+#else
                         c = ze_common_bytes(ld_u32_unaligned(buf + q) ^ ld_u32_unaligned(buf + q - off));
+#endif
                         c = min(c, bn - q);
                     }
                     const uint32_t stop = __ballot_sync(TS_FULL, c < 4);
