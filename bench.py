@@ -633,8 +633,9 @@ def main_tsgpu(args):
                 # keys are kernel names ("zstd_enc_blocks"); values {"bytes": per-launch DRAM read + write, "capture": file}
                 tj = json.load(open(tpath))
                 ent = tj.get(name, tj.get(name.rsplit("_", 1)[0]))
-                traffic = ent.get("bytes") if isinstance(ent, dict) else ent
-                traffic_capture = ent.get("capture") if isinstance(ent, dict) else None
+                here = "%s|%s|%s|%d" % (args.workload, args.zstd_mode, args.corpus, args.segment_mib)
+                if isinstance(ent, dict) and ent.get("bench_config") == here:      # only a capture taken at THIS configuration
+                    traffic, traffic_capture = ent.get("bytes"), ent.get("capture")
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",

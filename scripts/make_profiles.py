@@ -51,13 +51,24 @@ for f in sorted(glob.glob(os.path.join(G, R + "_*.ncu.json"))):
         continue
     shutil.copy(f, os.path.join(P, name + ".ncu.json"))
     for d in ds:
-        kern = d.get("kernel", "").split("(")[0].split("<")[0].replace("_kernel", "")
+        kern = d.get("kernel", "").split("(")[0].split("<")[0].replace("_kernel", "").replace("void ", "").strip()
         if "dram_read" in d and "dram_write" in d:
+            # the bench configuration the capture was taken at (scripts/gpu_round.sh); bench.py quotes the bytes only for that one
+            at = {"zstd_enc_blocks": "zstd+aes|speed|K|1024", "gcm_main": "zstd+aes|speed|K|1024",
+                  "zstd_enc_regions": "zstd+aes|dense|K|1024"}.get(kern)
             traffic[kern] = {"bytes": num(d["dram_read"]) + num(d["dram_write"]), "capture": "profiles/%s.ncu.json" % name,
-                             "duration_under_ncu": d.get("duration")}
+                             "duration_under_ncu": d.get("duration"), "bench_config": at}
         print("ncu summary", name, kern, d.get("duration"), d.get("issue_active_pct"))
 if traffic:
-    json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+    tpath = os.path.join(P, "traffic.json")
+    merged = {}
+    if os.path.exists(tpath):                     # keep the kernels this run did not capture (a later partial run must not drop them)
+        try:
+            merged = json.load(open(tpath))
+        except ValueError:
+            merged = {}
+    merged.update(traffic)
+    json.dump(merged, open(tpath, "w"), indent=1)
 for f in sorted(glob.glob(os.path.join(G, R + "_*.by_line.txt")) + glob.glob(os.path.join(G, R + "_sanitizer_*")) +
                 glob.glob(os.path.join(G, R + "_pcie_ceiling*.json"))):
     if os.path.getsize(f) < (1 << 20):

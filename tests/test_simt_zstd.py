@@ -168,6 +168,30 @@ def test_simt_index_files_ride_one_ragged_batch(ctx):
         ctx.transform_chunks(A, src, [10, 0, 5], key, aad, ivs)
 
 
+def test_simt_straight_line_extension_is_the_same_parse(tmp_path):
+    # The per-lane match extension of the speed-mode compressor exists as a loop (ZB_TUNE_STRAIGHT=0, the code until round 2)
+    # and as straight-line branch-free code (=1, the product: profiles/r02_ab.md).  It is a restructuring, not a different
+    # parse: with the emulator's fixed lane order both builds must emit identical frames.
+    libs = {}
+    for v in (0, 1):
+        so = str(tmp_path / ("libtsgpu_simt_straight%d.so" % v))
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DTSGPU_SIMT=1", "-DZB_TUNE_STRAIGHT=%d" % v,
+                               "-I" + os.path.join(ROOT, "tests", "simt"), "-I" + os.path.join(ROOT, "tiered-storage-for-apache-kafka_b200", "csrc"),
+                               "-x", "c++", os.path.join(ROOT, "tiered-storage-for-apache-kafka_b200", "csrc", "tsgpu.cu"),
+                               os.path.join(ROOT, "tests", "simt", "simt.cpp"), "-o", so, "-Wno-unknown-pragmas"])
+        libs[v] = so
+    code = ("import sys, hashlib; sys.path.insert(0, %r); import numpy as np, tsgpu; from tsgpu import corpus\n"
+            "c = tsgpu.Context(max_chunk_bytes=1 << 20, max_batch=4, lib_path=sys.argv[1])\n"
+            "h = hashlib.sha256()\n"
+            "for kind, n, cs in (('K', 300000, 131072), ('K', 70001, 0), ('R', 40000, 0), ('Z', 70000, 32768), ('M', 150000, 50000)):\n"
+            "    src = corpus.gen_segment(kind, 0, n, cs if cs else n) if kind != 'M' else np.concatenate([corpus.gen_chunk('K', 3, 0, n // 2), np.random.default_rng(3).integers(0, 256, n - n // 2, dtype=np.uint8)])\n"
+            "    out, sizes = c.transform(1, src, cs)\n"
+            "    h.update(out.tobytes()); h.update(repr(sizes).encode())\n"
+            "print(h.hexdigest(), len(out))\n") % ROOT
+    digests = {v: subprocess.check_output([sys.executable, "-c", code, libs[v]], text=True).strip() for v in (0, 1)}
+    assert digests[0] == digests[1], digests
+
+
 def test_simt_frames_do_not_depend_on_lane_order():
     # Retried uploads must produce identical objects: in the dense mode (TSGPU_FLAG_ZSTD_DENSE) hash-slot
     # winners are the highest position of a step, so the frame bytes may not depend on which lane the hardware (here: the
