@@ -168,6 +168,21 @@ def test_simt_index_files_ride_one_ragged_batch(ctx):
         ctx.transform_chunks(A, src, [10, 0, 5], key, aad, ivs)
 
 
+@pytest.mark.parametrize("mode", [0, tsgpu.FLAG_ZSTD_DENSE])
+def test_simt_matches_that_end_at_the_block_end(ctx, mode):
+    # the per-lane extension measures 16 bytes past a position and the warp-wide one 128 per probe, both clamped to the block:
+    # matches that run exactly to the last byte of a block / slice / chunk, for every alignment of that end
+    rng = np.random.default_rng(21)
+    head = rng.integers(0, 256, 3000, dtype=np.uint8)
+    for n in [3000 + k for k in (5, 6, 7, 8, 15, 16, 17, 19, 20, 21, 130, 131)] + [8189, 8190, 8191, 8192, 8193, 8197, 16383, 16384 + 5, 65536, 65536 + 11]:
+        src = np.concatenate([head, np.resize(head[:1000], n - 3000)]) if n > 3000 else head[:n]
+        out, sizes = ctx.transform(Z | mode, src, 0)
+        assert ora.zstd_decompress_chunk(out[:sizes[0]]) == src.tobytes(), n
+        assert sizes[0] < n // 2 or n < 3200, (n, sizes)
+        back, _ = ctx.detransform(Z, out, sizes, n)
+        assert np.array_equal(back, src), n
+
+
 def test_simt_straight_line_extension_is_the_same_parse(tmp_path):
     # The per-lane match extension of the speed-mode compressor exists as a loop (ZB_TUNE_STRAIGHT=0, the code until round 2)
     # and as straight-line branch-free code (=1, the product: profiles/r02_ab.md).  It is a restructuring, not a different
