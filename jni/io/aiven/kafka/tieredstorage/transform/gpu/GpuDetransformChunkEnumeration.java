@@ -93,7 +93,7 @@ public class GpuDetransformChunkEnumeration implements DetransformChunkEnumerati
             final ReadableByteChannel ch = Channels.newChannel(in);
             while (sb.hasRemaining()) {               // the ranged GET lands directly in pinned memory
                 if (ch.read(sb) < 0) {
-                    throw new IllegalArgumentException("Stream has fewer bytes than expected");
+                    throw new RuntimeException("Stream has fewer bytes than expected");   // the reference's type and message
                 }
             }
             final int[] osizes = new int[tsizes.length];

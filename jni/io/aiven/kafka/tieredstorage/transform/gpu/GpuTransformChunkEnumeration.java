@@ -24,6 +24,7 @@ import io.aiven.kafka.tieredstorage.transform.TransformChunkEnumeration;
  */
 public class GpuTransformChunkEnumeration implements TransformChunkEnumeration, AutoCloseable {
     private final long ctx;
+    private final InputStream inputStream;
     private final ReadableByteChannel channel;
     private final int originalChunkSize;
     private final int flags;
@@ -43,18 +44,22 @@ public class GpuTransformChunkEnumeration implements TransformChunkEnumeration, 
             throw new NullPointerException("inputStream cannot be null");
         }
         if (originalChunkSize < 0) {
-            throw new IllegalArgumentException("Original chunk size must be non-negative, " + originalChunkSize + " given");
+            throw new IllegalArgumentException(
+                "originalChunkSize must be non-negative, " + originalChunkSize + " given");   // BaseTransformChunkEnumeration.java:45-48
         }
         this.ctx = ctx;
         this.pool = pool;
+        this.inputStream = inputStream;
         this.channel = Channels.newChannel(inputStream);
         this.originalChunkSize = originalChunkSize;
         this.flags = (compression ? TsGpu.FLAG_ZSTD : 0) | (keyAndAad != null ? TsGpu.FLAG_AES : 0);
         this.keyAndAad = keyAndAad;
         this.batchChunks = batchChunks;
-        final long batchBytes = (long) batchChunks * originalChunkSize;
-        this.src = pool.lease(batchBytes);
-        this.dst = pool.lease(TsGpu.transformBound(flags, batchBytes, originalChunkSize));
+        if (originalChunkSize > 0) {
+            final long batchBytes = (long) batchChunks * originalChunkSize;
+            this.src = pool.lease(batchBytes);
+            this.dst = pool.lease(TsGpu.transformBound(flags, batchBytes, originalChunkSize));
+        }   // chunking disabled (size 0, BaseTransformChunkEnumeration.java:37-39): the buffers are sized once the stream has been read
     }
 
     @Override
@@ -88,6 +93,10 @@ public class GpuTransformChunkEnumeration implements TransformChunkEnumeration, 
 
     private void fill() {
         if (!ready.isEmpty() || eof) {
+            return;
+        }
+        if (originalChunkSize == 0) {
+            fillUnchunked();
             return;
         }
         try {
@@ -131,6 +140,40 @@ public class GpuTransformChunkEnumeration implements TransformChunkEnumeration, 
         } catch (final RuntimeException e) {
             release();
             throw e;
+        }
+    }
+
+    /** Chunking disabled: the whole stream is ONE chunk (readAllBytes in the reference, BaseTransformChunkEnumeration.java:84-88);
+     *  an empty stream yields no element. */
+    private void fillUnchunked() {
+        eof = true;
+        try {
+            final byte[] all = inputStream.readAllBytes();
+            if (all.length == 0) {
+                return;
+            }
+            src = pool.lease(all.length);
+            dst = pool.lease(TsGpu.transformBound(flags, all.length, 0));
+            final ByteBuffer in = src.buffer();
+            in.clear();
+            in.put(all);
+            final byte[] ivs = new byte[TsGpu.IV_SIZE];
+            random.nextBytes(ivs);
+            final int[] sizes = new int[1];
+            final ByteBuffer out = dst.buffer();
+            final int n = TsGpu.transform(ctx, flags, in, all.length, 0,
+                keyAndAad == null ? null : keyAndAad.dataKey.getEncoded(), keyAndAad == null ? null : keyAndAad.aad,
+                ivs, out, sizes);
+            out.clear();
+            for (int i = 0; i < n; i++) {
+                final byte[] chunk = new byte[sizes[i]];
+                out.get(chunk);
+                ready.add(chunk);
+            }
+        } catch (final IOException e) {
+            throw new RuntimeException(e);
+        } finally {
+            release();
         }
     }
 
