@@ -74,6 +74,10 @@ REFERENCE_VECTORS = {
 }
 
 
+DENSE_CASES = (("K", 11, 300000, 131072), ("K", 12, 70001, 70001), ("R", 13, 40000, 40000), ("Z", 14, 70000, 32768),
+               ("K", 15, 1 << 19, 1 << 19), ("K", 16, 8192 * 3 + 17, 8192))
+
+
 def main():
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
         json.dump(REFERENCE_VECTORS, f, indent=1)
@@ -93,6 +97,24 @@ def main():
         json.dump(frames, f, indent=1)
         f.write("\n")
     print("wrote", len(frames["frames"]), "frames,", sum(len(x["frame_b64"]) for x in frames["frames"]), "base64 bytes")
+    # dense-mode frames of THIS library are a function of the input: digests of what the emulated kernels write,
+    # so that (a) an unintended change of the compressed bytes shows up and (b) the B200 can be checked against the emulator
+    import subprocess
+    simt = os.path.join(ROOT, "tests", "simt", "libtsgpu_simt.so")
+    subprocess.check_call(["make", "-s", "-C", ROOT, "tests/simt/libtsgpu_simt.so"])
+    ctx = tsgpu.Context(max_chunk_bytes=1 << 19, max_batch=4, lib_path=simt)
+    dense = {"generator": "the product's dense compressor (TSGPU_FLAG_ZSTD | TSGPU_FLAG_ZSTD_DENSE) under the test-only SIMT emulator, "
+                          "tests/golden/make_golden.py", "cases": []}
+    for kind, seed, n, cs in DENSE_CASES:
+        src = corpus.gen_segment(kind, seed, n, cs)
+        out, sizes = ctx.transform(tsgpu.FLAG_ZSTD | tsgpu.FLAG_ZSTD_DENSE, src, cs)
+        dense["cases"].append({"kind": kind, "seed": seed, "n": n, "chunk_size": cs, "sizes": [int(x) for x in sizes],
+                               "sha256": hashlib.sha256(out.tobytes()).hexdigest()})
+    ctx.close()
+    with open(os.path.join(HERE, "dense_frames.json"), "w") as f:
+        json.dump(dense, f, indent=1)
+        f.write("\n")
+    print("wrote", len(dense["cases"]), "dense-frame digests")
 
 
 if __name__ == "__main__":
