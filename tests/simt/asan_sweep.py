@@ -23,20 +23,25 @@ cases.append((rng.integers(0, 4, 40000, dtype=np.uint8) * 60 + 3).astype(np.uint
 cases.append(np.repeat(rng.integers(0, 256, 700, dtype=np.uint8), 37)[:25000].copy())  # long runs
 key, aad = rng.bytes(32), rng.bytes(32)
 for src in cases:
-    for flags in (1, 3):
+    for flags in (1, 3, 5, 7):                                                          # 4 = dense compressor (64 KiB regions)
         ivs = rng.bytes(12)
         out, sizes = c.transform(flags, src, 0, key, aad, ivs)
-        back, _ = ora.detransform_chunks(flags, out, sizes, src.size, key, aad)
+        back, _ = ora.detransform_chunks(flags & 3, out, sizes, src.size, key, aad)
         assert np.array_equal(back, src)
-        back, _ = c.detransform(flags, out, sizes, src.size, key, aad)
+        back, _ = c.detransform(flags & 3, out, sizes, src.size, key, aad)
         assert np.array_equal(back, src)
     ref = np.frombuffer(ora.zstd_compress_chunk(src), dtype=np.uint8)                   # libzstd frames: general path
     back, _ = c.detransform(1, ref, [ref.size], src.size)
     assert np.array_equal(back, src)
 seg = corpus.gen_segment("K", 1, 100000, 30000)                                        # several chunks, two batches
-out, sizes = c.transform(3, seg, 30000, key, aad, rng.bytes(12 * 4))
-back, _ = c.detransform(3, out, sizes, seg.size, key, aad)
-assert np.array_equal(back, seg)
+for flags in (3, 7):
+    out, sizes = c.transform(flags, seg, 30000, key, aad, rng.bytes(12 * 4))
+    back, _ = c.detransform(3, out, sizes, seg.size, key, aad)
+    assert np.array_equal(back, seg)
+big_seg = corpus.gen_segment("K", 2, (1 << 18) + 4097, 1 << 18)                        # a full-size chunk: 4 regions + a ragged tail chunk
+out, sizes = c.transform(5, big_seg, 1 << 18)
+back, _ = c.detransform(1, out, sizes, big_seg.size)
+assert np.array_equal(back, big_seg)
 blobs = [rng.integers(0, 256, n, dtype=np.uint8) for n in (10485, 37, 126)]
 out, sizes = c.transform_chunks(2, np.concatenate(blobs), [x.size for x in blobs], key, aad, rng.bytes(36))
 assert sizes == [x.size + 28 for x in blobs]

@@ -57,7 +57,10 @@ def ctxs():
     a.close()
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture, HealthCheck.data_too_large])
+EXAMPLES = int(os.environ.get("TSGPU_HYP_EXAMPLES", "40"))     # a soak run sets it higher (scripts/README.md)
+
+
+@settings(max_examples=EXAMPLES, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture, HealthCheck.data_too_large])
 @given(src=structured_bytes(), level=st.sampled_from([1, 3, 7, 19]))
 def test_compressor_and_decode_paths(ctxs, src, level):
     serial = ctxs
@@ -66,6 +69,11 @@ def test_compressor_and_decode_paths(ctxs, src, level):
     assert ora.zstd_content_size(out[:sizes[0]]) == n
     assert ora.zstd_decompress_chunk(out[:sizes[0]]) == src.tobytes()
     back, _ = serial.detransform(Z, out, sizes, n)
+    assert np.array_equal(back, src)
+    dout, dsizes = serial.transform(Z | tsgpu.FLAG_ZSTD_DENSE, src, 0)          # the dense compressor: same contract
+    assert ora.zstd_content_size(dout[:dsizes[0]]) == n
+    assert ora.zstd_decompress_chunk(dout[:dsizes[0]]) == src.tobytes()
+    back, _ = serial.detransform(Z, dout, dsizes, n)
     assert np.array_equal(back, src)
     ref = np.frombuffer(ora.zstd_compress_level(src, level), dtype=np.uint8)
     back, osz = serial.detransform(Z, ref, [ref.size], n)
