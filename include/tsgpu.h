@@ -117,7 +117,8 @@ int tsgpu_transform_chunks(tsgpu_ctx* ctx, uint32_t flags,
  *   original_sizes[n]  out: bytes produced per chunk (may be NULL)
  *   dst/dst_cap    receives the original bytes of the chunks back to back
  * Returns TSGPU_E_AUTH if any tag fails (no plaintext of that batch is released: dst is zeroed),
- * TSGPU_E_CORRUPT for malformed frames.
+ * TSGPU_E_CORRUPT for malformed frames — a compressed chunk must be exactly one zstd frame with Frame_Content_Size (skippable
+ * frames may follow it); bytes after the frame are refused like Zstd.decompress(chunk, size) refuses them.
  * --------------------------------------------------------------------------------------------------------- */
 int tsgpu_detransform(tsgpu_ctx* ctx, uint32_t flags,
                       const uint8_t* src, uint64_t src_len, const uint32_t* transformed_sizes, uint32_t n_chunks,

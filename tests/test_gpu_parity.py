@@ -231,6 +231,34 @@ def test_transformed_chunks_compressed_like_the_reference(ctx):
     assert js.startswith('{"type":"variable","originalChunkSize":4194304,"originalFileSize":%d,"transformedChunks":"' % (255 * 4 * MIB + 5))
 
 
+def test_bytes_after_the_frame_are_refused_like_libzstd(small_ctx):
+    # DecompressionChunkEnumeration.java:41-45 hands the whole chunk to Zstd.decompress(chunk, size): libzstd refuses bytes after the
+    # frame ("Src size is incorrect") and a second frame ("Destination buffer is too small"), and steps over skippable frames
+    src = corpus.gen_segment("K", 3, 9000, 9000)
+    skippable = np.frombuffer(bytes([0x53, 0x2A, 0x4D, 0x18, 3, 0, 0, 0, 9, 9, 9]), dtype=np.uint8)
+    frames = {"libzstd": np.frombuffer(ora.zstd_compress_level(src, 3), dtype=np.uint8)}
+    for name, flags in (("speed", Z), ("dense", Z | tsgpu.FLAG_ZSTD_DENSE)):
+        out, sizes = small_ctx.transform(flags, src, 0)
+        frames[name] = np.array(out[:sizes[0]], copy=True)
+    for name, f in frames.items():
+        for what, tail, accepted in (("exact", np.zeros(0, np.uint8), True), ("garbage", np.array([1, 2, 3, 4, 5], np.uint8), False),
+                                     ("one byte", np.zeros(1, np.uint8), False), ("second frame", f, False),
+                                     ("skippable frame", skippable, True), ("truncated skippable frame", skippable[:9], False)):
+            chunk = np.concatenate([f, tail])
+            try:
+                ref_ok = ora.zstd_decompress_chunk(chunk) == src.tobytes()
+            except Exception:
+                ref_ok = False
+            assert ref_ok == accepted, (name, what)                       # the expectation IS libzstd's behaviour
+            try:
+                back, _ = small_ctx.detransform(Z, chunk, [chunk.size], 9000)
+                mine_ok = np.array_equal(back, src)
+            except tsgpu.TsgpuError as e:
+                assert e.code == binding.E_CORRUPT
+                mine_ok = False
+            assert mine_ok == accepted, (name, what)
+
+
 def test_empty_segment_and_argument_errors(ctx):
     out, sizes = ctx.transform(Z | A, np.zeros(0, np.uint8), 4 * MIB, bytes(32), b"", bytes(12))
     assert sizes == [] and len(out) == 0

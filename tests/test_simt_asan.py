@@ -22,3 +22,16 @@ def test_emulated_kernels_are_clean_under_sanitizers(san, lib):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt", "asan_sweep.py"), lib], env=env,
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "sanitizer sweep ok" in out.stdout, (out.stdout + out.stderr)[-4000:]
+
+
+def test_mutated_frames_never_overrun_under_asan():
+    # bit flips, stomps, truncations, appended bytes on frames of both compressors and of libzstd (levels 1 / 3 / 19): any answer
+    # but an out-of-bounds access; bytes after the frame are refused like zstd-jni refuses them ("Src size is incorrect")
+    runtime = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(runtime) or not os.path.exists(runtime):
+        pytest.skip("libasan not available")
+    subprocess.check_call(["make", "-s", "-C", ROOT, "tests/simt/libtsgpu_simt_asan.so"])
+    env = dict(os.environ, LD_PRELOAD=runtime, ASAN_OPTIONS="detect_leaks=0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "simt", "asan_corrupt.py"), "libtsgpu_simt_asan.so", "8", "11"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "corrupt-frame sweep ok" in out.stdout, (out.stdout + out.stderr)[-4000:]

@@ -168,6 +168,34 @@ def test_simt_index_files_ride_one_ragged_batch(ctx):
         ctx.transform_chunks(A, src, [10, 0, 5], key, aad, ivs)
 
 
+def test_simt_bytes_after_the_frame_are_refused_like_libzstd(ctx):
+    # DecompressionChunkEnumeration.java:41-45 hands the whole chunk to Zstd.decompress(chunk, size): libzstd refuses bytes after the
+    # frame ("Src size is incorrect") and a second frame ("Destination buffer is too small"), and steps over skippable frames
+    src = corpus.gen_segment("K", 3, 9000, 9000)
+    skippable = np.frombuffer(bytes([0x53, 0x2A, 0x4D, 0x18, 3, 0, 0, 0, 9, 9, 9]), dtype=np.uint8)
+    frames = {"libzstd": np.frombuffer(ora.zstd_compress_level(src, 3), dtype=np.uint8)}
+    for name, flags in (("speed", Z), ("dense", Z | tsgpu.FLAG_ZSTD_DENSE)):
+        out, sizes = ctx.transform(flags, src, 0)
+        frames[name] = np.array(out[:sizes[0]], copy=True)
+    for name, f in frames.items():
+        for what, tail, accepted in (("exact", np.zeros(0, np.uint8), True), ("garbage", np.array([1, 2, 3, 4, 5], np.uint8), False),
+                                     ("one byte", np.zeros(1, np.uint8), False), ("second frame", f, False),
+                                     ("skippable frame", skippable, True), ("truncated skippable frame", skippable[:9], False)):
+            chunk = np.concatenate([f, tail])
+            try:
+                ref_ok = ora.zstd_decompress_chunk(chunk) == src.tobytes()
+            except Exception:
+                ref_ok = False
+            assert ref_ok == accepted, (name, what)                       # the expectation IS libzstd's behaviour
+            try:
+                back, _ = ctx.detransform(Z, chunk, [chunk.size], 9000)
+                mine_ok = np.array_equal(back, src)
+            except tsgpu.TsgpuError as e:
+                assert e.code == binding.E_CORRUPT
+                mine_ok = False
+            assert mine_ok == accepted, (name, what)
+
+
 @pytest.mark.parametrize("mode", [0, tsgpu.FLAG_ZSTD_DENSE])
 def test_simt_matches_that_end_at_the_block_end(ctx, mode):
     # the per-lane extension measures 16 bytes past a position and the warp-wide one 128 per probe, both clamped to the block:

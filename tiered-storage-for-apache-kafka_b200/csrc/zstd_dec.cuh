@@ -1109,6 +1109,22 @@ __device__ __forceinline__ uint32_t zd_frame_header(const uint8_t* p, uint32_t n
     return pos + fl;
 }
 
+// What may follow the last block of the frame inside the chunk: the 4-byte Content_Checksum when the frame header announces one
+// (not verified here — the reference's writer never sets it, CompressionChunkEnumeration.java:52-61), then only skippable
+// frames (ZSTD_decompress steps over those).  Anything else — trailing bytes, a second frame — is what zstd-jni's
+// Zstd.decompress(chunk, size) rejects ("Src size is incorrect" / "Destination buffer is too small"), so it is corrupt here too.
+__device__ __forceinline__ bool zd_frame_tail_ok(const uint8_t* p, uint32_t n, uint32_t pos) {
+    if (p[4] & 0x04) { if (pos + 4 > n) return false; pos += 4; }
+    while (pos < n) {
+        if (pos + 8 > n) return false;
+        const uint32_t magic = p[pos] | (p[pos + 1] << 8) | (p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24);
+        const uint32_t size = p[pos + 4] | (p[pos + 5] << 8) | (p[pos + 6] << 16) | ((uint32_t)p[pos + 7] << 24);
+        if ((magic & 0xfffffff0u) != 0x184D2A50u || size > n - pos - 8) return false;
+        pos += 8 + size;
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------ kernel 1: index
 __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_constant__ ZstdDecArgs A) {
     const uint32_t lane = threadIdx.x & 31;
@@ -1143,6 +1159,7 @@ __global__ void __launch_bounds__(128) zstd_dec_index_kernel(const __grid_consta
         pos += 3 + (type == 1 ? 1 : bsz);
         if (pos > n || nblk > want + 1) { if (pos > n) ok = false; break; }
     }
+    if (ok && last && !zd_frame_tail_ok(p, n, pos)) ok = false;
     if (!ok) { A.status[chunk] = ZD_ST_CORRUPT; info[3] = 2; return; }
     info[1] = nblk;
     // Frames whose blocks look like this library's (ceil(FCS / 8 KiB) blocks) are first tried region by region (64 KiB of
@@ -1218,7 +1235,7 @@ __global__ void __launch_bounds__(ZD_WPB * 32) zstd_dec_frames_kernel(const __gr
         __threadfence_block();
     }
     if (lane == 0) {
-        if (bad || op != fcs) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; }
+        if (bad || op != fcs || !zd_frame_tail_ok(p, n, pos)) { A.status[chunk] = ZD_ST_CORRUPT; A.out_len[chunk] = 0; }
     }
 }
 
