@@ -62,6 +62,8 @@ def lib():
             f.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t]
         L.ora_zstd_compress_level.restype = C.c_int64
         L.ora_zstd_compress_level.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.c_int]
+        L.ora_zstd_compress_checksum.restype = C.c_int64
+        L.ora_zstd_compress_checksum.argtypes = [u8p, C.c_size_t, u8p, C.c_size_t, C.c_int]
         L.ora_zstd_content_size.restype = C.c_int64
         L.ora_zstd_content_size.argtypes = [u8p, C.c_size_t]
         L.ora_aesgcm_encrypt_chunk.argtypes = [u8p, u8p, u8p, C.c_size_t, u8p, C.c_size_t, u8p]
@@ -126,6 +128,16 @@ def zstd_compress_level(data, level):
     d = _u8(data)
     out = np.empty(lib().ora_zstd_bound(d.size) + 64, dtype=np.uint8)
     r = lib().ora_zstd_compress_level(_p(d), d.size, _p(out), out.size, level)
+    if r < 0:
+        _err(r)
+    return out[:r].tobytes()
+
+
+def zstd_compress_checksum(data, level=3):
+    """a frame with Content_Checksum (the reference never writes one; its reader verifies it when present)"""
+    d = _u8(data)
+    out = np.empty(lib().ora_zstd_bound(d.size) + 64, dtype=np.uint8)
+    r = lib().ora_zstd_compress_checksum(_p(d), d.size, _p(out), out.size, level)
     if r < 0:
         _err(r)
     return out[:r].tobytes()

@@ -82,6 +82,21 @@ int64_t ora_zstd_compress_level(const uint8_t* src, size_t n, uint8_t* dst, size
     if (Z.isError(r)) return fail(ORA_E_SHORT, "zstd compress: %s", Z.getErrorName(r));
     return (int64_t)r;
 }
+/* A frame WITH Content_Checksum (ZSTD_c_checksumFlag): the reference never writes one (no setChecksum call anywhere), but
+ * zstd-jni's reader verifies it when present, so the decoder under test has to as well.  Test coverage only. */
+int64_t ora_zstd_compress_checksum(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int level) {
+    if (zload()) return ORA_E_NOLIB;
+    ZSTD_CCtx* c = Z.createCCtx();
+    if (!c) return fail(ORA_E_ARG, "ZSTD_createCCtx failed");
+    Z.setPledgedSrcSize(c, n);
+    Z.setParameter(c, ZSTD_c_contentSizeFlag, 1);
+    Z.setParameter(c, 201 /* ZSTD_c_checksumFlag */, 1);
+    Z.setParameter(c, 100 /* ZSTD_c_compressionLevel */, level);
+    size_t r = Z.compress2(c, dst, cap, src, n);
+    Z.freeCCtx(c);
+    if (Z.isError(r)) return fail(ORA_E_SHORT, "zstd compress: %s", Z.getErrorName(r));
+    return (int64_t)r;
+}
 /* Zstd.decompressedSize (DecompressionChunkEnumeration.java:41): <0 => "Invalid decompressed size" */
 int64_t ora_zstd_content_size(const uint8_t* frame, size_t n) {
     if (zload()) return ORA_E_NOLIB;

@@ -53,6 +53,7 @@ const char* ora_zstd_version(void);
 size_t  ora_zstd_bound(size_t n);
 int64_t ora_zstd_compress_chunk(const uint8_t* src, size_t n, uint8_t* dst, size_t cap);    /* <0 error */
 int64_t ora_zstd_compress_level(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int level);      /* test coverage only */
+int64_t ora_zstd_compress_checksum(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int level);   /* + Content_Checksum; test coverage only */
 int64_t ora_zstd_content_size(const uint8_t* frame, size_t n);                               /* <0: unknown/err */
 int64_t ora_zstd_decompress_chunk(const uint8_t* frame, size_t n, uint8_t* dst, size_t cap);
 

@@ -168,6 +168,25 @@ def test_simt_index_files_ride_one_ragged_batch(ctx):
         ctx.transform_chunks(A, src, [10, 0, 5], key, aad, ivs)
 
 
+def test_simt_content_checksum_is_verified_like_libzstd(ctx):
+    # zstd-jni's Zstd.decompress verifies the Content_Checksum (low 32 bits of XXH64 of the content) when a frame announces one; the
+    # reference's writer never does, a foreign writer (zstd CLI default) may: accepted when right, refused when wrong — as libzstd does
+    for n in (1, 31, 32, 33, 100, 8192, 70001, 300000):
+        src = corpus.gen_segment("K", n % 97, n, n)
+        for level in (1, 3):
+            f = np.frombuffer(ora.zstd_compress_checksum(src, level), dtype=np.uint8)
+            assert f[4] & 4
+            back, _ = ctx.detransform(Z, f, [f.size], n)
+            assert np.array_equal(back, src), (n, level)
+            bad = f.copy()
+            bad[-1 - (n % 4)] ^= 0x21
+            with pytest.raises(Exception):
+                ora.zstd_decompress_chunk(bad)
+            with pytest.raises(tsgpu.TsgpuError) as e:
+                ctx.detransform(Z, bad, [bad.size], n)
+            assert e.value.code == binding.E_CORRUPT
+
+
 def test_simt_bytes_after_the_frame_are_refused_like_libzstd(ctx):
     # DecompressionChunkEnumeration.java:41-45 hands the whole chunk to Zstd.decompress(chunk, size): libzstd refuses bytes after the
     # frame ("Src size is incorrect") and a second frame ("Destination buffer is too small"), and steps over skippable frames
