@@ -231,6 +231,38 @@ def test_transformed_chunks_compressed_like_the_reference(ctx):
     assert js.startswith('{"type":"variable","originalChunkSize":4194304,"originalFileSize":%d,"transformedChunks":"' % (255 * 4 * MIB + 5))
 
 
+def test_frame_header_fields_refused_like_libzstd(ctx):
+    # header fields a reader without a dictionary has to refuse, exactly where libzstd does: a Dictionary_ID other than 0
+    # ("Dictionary mismatch"), a Window_Descriptor above windowLog 31; a zero Dictionary_ID field and windowLog 31 are fine
+    src = corpus.gen_segment("K", 1, 600000, 600000)
+    f = np.frombuffer(ora.zstd_compress_level(src, 1), dtype=np.uint8).copy()
+    assert f[4] & 0x20 == 0                                          # not Single_Segment: byte 5 is the Window_Descriptor
+    small = corpus.gen_segment("K", 1, 9000, 9000)
+    f2 = np.frombuffer(ora.zstd_compress_level(small, 3), dtype=np.uint8).copy()
+    assert f2[4] & 0x20
+    u8 = lambda *v: np.array(v, np.uint8)
+    cases = [("plain", f, src), ("windowLog 32", np.concatenate([f[:5], u8(22 << 3), f[6:]]), src),
+             ("windowLog 31", np.concatenate([f[:5], u8(21 << 3), f[6:]]), src),
+             ("dictionary id 7", np.concatenate([f[:4], u8(f[4] | 1), f[5:6], u8(7), f[6:]]), src),
+             ("dictionary id field 0", np.concatenate([f[:4], u8(f[4] | 1), f[5:6], u8(0), f[6:]]), src),
+             ("single segment, dictionary id 257", np.concatenate([f2[:4], u8(f2[4] | 2), u8(1, 1), f2[5:]]), small),
+             ("reserved bit", np.concatenate([f2[:4], u8(f2[4] | 8), f2[5:]]), small)]
+    for name, frame, want in cases:
+        frame = np.ascontiguousarray(frame)
+        try:
+            ref_ok = ora.zstd_decompress_chunk(frame) == want.tobytes()
+        except Exception:
+            ref_ok = False
+        try:
+            back, _ = ctx.detransform(Z, frame, [frame.size], want.size)
+            mine_ok = bool(np.array_equal(back, want))
+        except tsgpu.TsgpuError as e:
+            assert e.code == binding.E_CORRUPT
+            mine_ok = False
+        assert mine_ok == ref_ok, (name, ref_ok, mine_ok)
+        assert ref_ok == (name in ("plain", "windowLog 31", "dictionary id field 0")), name
+
+
 def test_content_checksum_is_verified_like_libzstd(small_ctx):
     # zstd-jni's Zstd.decompress verifies the Content_Checksum (low 32 bits of XXH64 of the content) when a frame announces one; the
     # reference's writer never does, a foreign writer (zstd CLI default) may: accepted when right, refused when wrong — as libzstd does

@@ -1095,10 +1095,15 @@ __device__ __forceinline__ uint32_t zd_frame_header(const uint8_t* p, uint32_t n
     const uint32_t fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, dict = fhd & 3;
     if (fhd & 0x08) return 0;                            // reserved bit
     uint32_t pos = 5;
-    if (!single) pos += 1;                               // Window_Descriptor (the window is the whole output buffer here)
-    pos += dict == 0 ? 0 : dict == 1 ? 1 : dict == 2 ? 2 : 4;
+    if (!single) {                                       // Window_Descriptor (the window is the whole output buffer here);
+        if ((uint32_t)(p[5] >> 3) + 10 > 31) return 0;   // libzstd refuses a windowLog above ZSTD_WINDOWLOG_MAX (31)
+        pos += 1;
+    }
+    const uint32_t dl = dict == 0 ? 0 : dict == 1 ? 1 : dict == 2 ? 2 : 4;
     const uint32_t fl = fcs_flag == 0 ? (single ? 1 : 0) : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
-    if (pos + fl > n) return 0;
+    if (pos + dl + fl > n) return 0;
+    for (uint32_t k = 0; k < dl; k++) if (p[pos + k]) return 0;   // a Dictionary_ID other than 0: the reader has no dictionary ("Dictionary mismatch" in libzstd)
+    pos += dl;
     uint64_t v = 0xffffffffffffffffull;
     if (fl) {
         v = 0;
